@@ -1,0 +1,214 @@
+/* stcsp_b200.h -- C ABI of the B200-native search-and-propagate path of the stcsp solver.
+ *
+ * The reference (AllenZzw/stcsp-solver) has no plugin or FFI layer; its hot path is entered
+ * through exactly one call, `double solverSolve(Solver *solver, bool testing)`
+ * (reference src/solveralgorithm.h:11, body src/solveralgorithm.cpp:945-1005, callers
+ * src/solver.cpp:289 and :323).  This header is the drop-in boundary for that call: plain
+ * pointers and sizes, no C++ or torch types.  A reference maintainer flattens `Solver` into
+ * `stcsp_problem_t`, calls `stcsp_gpu_solve`, and rebuilds `Graph` from `stcsp_automaton_t`
+ * (the binding is shown in INTEGRATION.md).
+ *
+ * Everything here runs on the GPU; there is no CPU fallback.  If no CUDA device is usable the
+ * calls return STCSP_ERR_CUDA and `stcsp_last_error()` says why.
+ */
+#ifndef STCSP_B200_H
+#define STCSP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STCSP_ABI_VERSION 1
+
+/* ---------------------------------------------------------------------------------------------
+ * Constraint expressions: one postfix (post-order) token list per constraint.
+ *
+ * Replaces the heap-allocated `ConstraintNode` trees (reference src/constraint.h:24-31).  A tree
+ * is dumped left-to-right, children before parent; the arity of every operator is fixed, so the
+ * list is the tree.  Token meaning follows the reference's evaluator `solverValidateRe`
+ * (src/solveralgorithm.cpp:336-424).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct stcsp_tok {
+    int32_t op;   /* enum stcsp_op */
+    int32_t arg;  /* CONST: value; VAR: variable index; ARR: array index; AT: time offset n */
+} stcsp_tok_t;
+
+enum stcsp_op {
+    /* leaves */
+    STCSP_OP_CONST = 1,   /* reference token CONSTANT   */
+    STCSP_OP_VAR = 2,     /* reference token IDENTIFIER */
+    /* unary: operand precedes */
+    STCSP_OP_ARR = 3,     /* ARR_IDENTIFIER: T[operand]; out-of-range index poisons the evaluation */
+    STCSP_OP_ABS = 4,
+    STCSP_OP_NOT = 5,
+    STCSP_OP_FIRST = 6,
+    STCSP_OP_NEXT = 7,    /* only as the right side of `x == next y` */
+    STCSP_OP_AT = 8,      /* only as the right side of `x == y@n`; arg = n */
+    /* ternary: cond, then, else precede (reference IF/THEN node pair) */
+    STCSP_OP_IF = 9,
+    /* binary, expression level: left, right precede */
+    STCSP_OP_LT = 10, STCSP_OP_GT = 11, STCSP_OP_LE = 12, STCSP_OP_GE = 13,
+    STCSP_OP_EQ = 14, STCSP_OP_NE = 15,
+    STCSP_OP_AND = 16, STCSP_OP_OR = 17,
+    STCSP_OP_ADD = 18, STCSP_OP_SUB = 19, STCSP_OP_MUL = 20, STCSP_OP_DIV = 21, STCSP_OP_MOD = 22,
+    /* binary, constraint level: always the last token of a constraint */
+    STCSP_CON_LT = 32, STCSP_CON_GT = 33, STCSP_CON_LE = 34, STCSP_CON_GE = 35,
+    STCSP_CON_EQ = 36, STCSP_CON_NE = 37, STCSP_CON_IMPLY = 38, STCSP_CON_UNTIL = 39
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * Problem: what `solverSolve` reads from `Solver` (reference src/solver.h:22-49).
+ * Host-owned, read-only during the call.
+ *   variables   <- solver->varQueue   (src/variable.h:10-26: name, lb, ub), declaration order with
+ *                  the normaliser's auxiliaries `_V<n>` in creation order
+ *   arrays      <- solver->arrayQueue (src/variable.h:54-59)
+ *   constraints <- solver->constrQueue (src/constraint.h:38-49), normalised, in queue order.  Kind
+ *                  (NEXT / POINT / UNTIL / AT), `hasFirst` and the signature variables are derived
+ *                  from the token lists exactly as `solverConstraintQueuePush` does
+ *                  (src/constraint.cpp:254-318); the caller does not pass them.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct stcsp_problem {
+    int32_t abi_version;             /* STCSP_ABI_VERSION */
+    int32_t prefix_k;                /* solver->prefixK (flag -k, default 2) */
+    int32_t n_vars;
+    const int32_t *var_lb;           /* [n_vars] */
+    const int32_t *var_ub;           /* [n_vars] */
+    const char *const *var_names;    /* [n_vars] or NULL (only used for DOT headers) */
+    int32_t n_arrays;
+    const int32_t *arr_offsets;      /* [n_arrays + 1] into arr_values */
+    const int32_t *arr_values;
+    int32_t n_constraints;
+    const int32_t *con_offsets;      /* [n_constraints + 1] into con_tokens */
+    const stcsp_tok_t *con_tokens;
+} stcsp_problem_t;
+
+/* Options.  Zero-initialise, then set what you need; 0 always means "default". */
+typedef struct stcsp_options {
+    int32_t device;                  /* CUDA device ordinal; -1 or 0-with-use_current = current device */
+    int32_t use_current_device;      /* 1: do not call cudaSetDevice (the host framework already did) */
+    int32_t time_limit_s;            /* flag -m; 0 = none.  On expiry: STCSP_ERR_TIMEOUT */
+    int32_t verbosity;               /* flag -l */
+    int64_t enum_limit_now;          /* max tuples enumerated per constraint revision at the current time point */
+    int64_t enum_limit_ahead;        /* same, at look-ahead time points 1..k-1 */
+    int64_t max_frontier_nodes;      /* capacity of each search-node frontier buffer */
+    int64_t max_states;              /* capacity of the state table */
+    int64_t max_edges;               /* capacity of the edge store */
+    int32_t keep_failed_edges;       /* debugging: do not trim */
+    int32_t profile_kernels;         /* 1: CUDA-event time every expand launch (fills expand_ms) */
+    int32_t reserved[6];
+} stcsp_options_t;
+
+/* ---------------------------------------------------------------------------------------------
+ * Automaton: what `solverSolve` leaves in `solver->graph` (reference src/graph.h:47-72) before
+ * post-processing, i.e. after the fail rule (src/solveralgorithm.cpp:904-910) and before
+ * `graphTraverse`.  Library-owned until `stcsp_automaton_free`.
+ *   state 0 is the root (signature "S", constraint set 0).
+ *   sig[s]  = values of the signature variables in variable order, then one 0/1 flag per UNTIL
+ *             constraint (src/solveralgorithm.cpp:810-837); undefined for the root.
+ *   failed  = state has no surviving out-edge (src/solveralgorithm.cpp:865-868, 907-909).
+ *   edges   = (src, dst, the full assignment of the source time point), dst never failed
+ *             (src/graph.cpp:78-89).  Grouped by src (ascending); order within one source is unspecified.
+ *   constraint-set ids are dense but their numbering is this library's (the reference numbers
+ *   them in DFS discovery order); compare automata after canonical relabelling.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct stcsp_automaton {
+    int32_t n_vars;
+    int32_t n_sig_vars;              /* solver->numSignVar */
+    int32_t n_until;                 /* number of UNTIL constraints (flags per state) */
+    int32_t n_until_vars;            /* solver->numUntil (distinct right-hand variables) */
+    int32_t sig_len;                 /* n_sig_vars + n_until */
+    int32_t *sig_vars;               /* [n_sig_vars] variable index of each signature column */
+    int32_t root_final;              /* 1 iff the initial constraint set has no UNTIL constraint */
+    int32_t n_constraint_sets;
+    int64_t n_states;
+    int32_t *state_sig;              /* [n_states * sig_len] */
+    int32_t *state_cset;             /* [n_states] constraint-set id */
+    uint8_t *state_failed;           /* [n_states] */
+    int64_t n_edges;
+    int32_t *edge_src;               /* [n_edges] */
+    int32_t *edge_dst;               /* [n_edges] */
+    int32_t *edge_label;             /* [n_edges * n_vars] */
+    /* statistics (search-order dependent, not parity targets) */
+    int64_t n_search_nodes;          /* propagate-to-fixpoint calls (reference: generalisedArcConsistent calls) */
+    int64_t n_fails;                 /* search nodes that wiped out a domain */
+    int64_t n_leaves;                /* complete consistent assignments found */
+    int64_t n_dominance;             /* leaves that hit an existing state */
+    int64_t n_waves;                 /* frontier iterations */
+    int64_t n_tuples;                /* constraint evaluations */
+    int64_t n_kernel_launches;
+    double solve_ms;                 /* device time, CUDA events around the whole search */
+    double wall_ms;                  /* host wall clock of the call incl. uploads/downloads */
+    double expand_ms;                /* device time inside the expand kernel only (sum over waves) */
+    int64_t algorithmic_bytes;       /* SURVEY.md section 8(d) formula with this run's counts */
+    int64_t h2d_bytes, d2h_bytes;
+    void *impl;                      /* private */
+} stcsp_automaton_t;
+
+enum stcsp_status {
+    STCSP_OK = 0,
+    STCSP_ERR_INVALID = 1,           /* malformed problem (bad token list, bad index, abi mismatch) */
+    STCSP_ERR_UNSUPPORTED = 2,       /* domain wider than 64 values, too many variables ... */
+    STCSP_ERR_CUDA = 3,              /* no device / CUDA failure: there is NO CPU fallback */
+    STCSP_ERR_CAPACITY = 4,          /* frontier / state table / edge store full: raise the option */
+    STCSP_ERR_TIMEOUT = 5,
+    STCSP_ERR_PARSE = 6              /* front end: syntax error or undefined name */
+};
+
+/* Replaces solverSolve() (reference src/solveralgorithm.cpp:945-1005) up to, not including,
+ * graphTraverse.  `out` is filled on STCSP_OK and must be released with stcsp_automaton_free. */
+int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *options, stcsp_automaton_t *out);
+
+/* Replaces graphFree() (reference src/graph.cpp:156-163). */
+void stcsp_automaton_free(stcsp_automaton_t *a);
+
+/* Message of the last failing call on this thread (the reference logs to error.txt and exits,
+ * src/util.cpp:161-178; a library must not exit). */
+const char *stcsp_last_error(void);
+
+/* Number of usable CUDA devices (0 if none); never fails. */
+int stcsp_gpu_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Step-wise session API: the same search, one frontier wave at a time, so that a multi-GPU
+ * driver (one process per GPU) can exchange leaf records by hash owner between `expand` and
+ * `ingest`.  stcsp_gpu_solve() is exactly create / loop(expand, ingest) / finish on one rank.
+ *
+ * A leaf record is `rec_words` int32: [src_state_global, cset, n_until_flags.., sig.., label..];
+ * see DESIGN.md "leaf record".  Outbox/inbox buffers are caller-provided DEVICE memory so the
+ * caller's collective (NCCL all-to-all through torch.distributed) moves them without copies.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct stcsp_session stcsp_session_t;
+
+int stcsp_session_create(const stcsp_problem_t *problem, const stcsp_options_t *options,
+                         int32_t rank, int32_t world_size, stcsp_session_t **out);
+void stcsp_session_destroy(stcsp_session_t *s);
+/* int32 words per leaf record */
+int32_t stcsp_session_record_words(const stcsp_session_t *s);
+/* Expand the whole local frontier by one wave.  Leaves are written to `outbox` (device, capacity
+ * `outbox_capacity` records), grouped by owner rank; counts_per_rank[world_size] (host) receives
+ * the number of records for each rank; record r of rank q is at outbox + (offset_q + r)*rec_words
+ * with offset_q the exclusive prefix sum of the counts.  *frontier_left is the number of local
+ * search nodes waiting for the next wave (before ingest). */
+int stcsp_session_expand(stcsp_session_t *s, int32_t *outbox, int64_t outbox_capacity,
+                         int64_t *counts_per_rank, int64_t *frontier_left);
+/* Insert `n_records` leaf records (device memory) this rank owns: dedup against the state table,
+ * append edges, create the search nodes of new states.  *frontier_left as above, after ingest. */
+int stcsp_session_ingest(stcsp_session_t *s, const int32_t *inbox, int64_t n_records, int64_t *frontier_left);
+/* Local part of the automaton (states this rank owns and edges into them), untrimmed, with global
+ * state ids `local_index * world_size + rank`; the driver merges the parts and calls
+ * stcsp_automaton_trim on the union. */
+int stcsp_session_finish(stcsp_session_t *s, stcsp_automaton_t *out);
+/* Owner rank of a leaf record's destination state (same hash the device uses). */
+int32_t stcsp_record_owner(const int32_t *record_host, int32_t rec_words, int32_t key_offset, int32_t key_words,
+                           int32_t world_size);
+
+/* Fail rule as a greatest fixpoint (reference src/solveralgorithm.cpp:904-910): marks states without
+ * surviving out-edges, removes edges into them, repeats.  In place; edges stay sorted. */
+int stcsp_automaton_trim(stcsp_automaton_t *a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STCSP_B200_H */

@@ -1,0 +1,253 @@
+"""ctypes mirror of include/stcsp_b200.h and include/stcsp_host.h.
+
+This is the reference-facing call path of the package: text -> ``Model`` (front end + normaliser,
+host) -> ``solve`` (CUDA, through the C ABI only) -> ``Automaton`` -> ``postprocess`` (host).
+There is no CPU solver here: ``solve`` raises when the library reports ``STCSP_ERR_CUDA``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import canonical
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstcsp_b200.so")
+
+STCSP_OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY, ERR_TIMEOUT, ERR_PARSE = range(7)
+_STATUS = ["ok", "invalid", "unsupported", "cuda", "capacity", "timeout", "parse"]
+
+
+class Tok(C.Structure):
+    _fields_ = [("op", C.c_int32), ("arg", C.c_int32)]
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("prefix_k", C.c_int32), ("n_vars", C.c_int32),
+        ("var_lb", C.POINTER(C.c_int32)), ("var_ub", C.POINTER(C.c_int32)),
+        ("var_names", C.POINTER(C.c_char_p)),
+        ("n_arrays", C.c_int32), ("arr_offsets", C.POINTER(C.c_int32)), ("arr_values", C.POINTER(C.c_int32)),
+        ("n_constraints", C.c_int32), ("con_offsets", C.POINTER(C.c_int32)), ("con_tokens", C.POINTER(Tok)),
+    ]
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("use_current_device", C.c_int32), ("time_limit_s", C.c_int32),
+        ("verbosity", C.c_int32), ("enum_limit_now", C.c_int64), ("enum_limit_ahead", C.c_int64),
+        ("max_frontier_nodes", C.c_int64), ("max_states", C.c_int64), ("max_edges", C.c_int64),
+        ("keep_failed_edges", C.c_int32), ("profile_kernels", C.c_int32), ("reserved", C.c_int32 * 6),
+    ]
+
+
+class AutomatonC(C.Structure):
+    _fields_ = [
+        ("n_vars", C.c_int32), ("n_sig_vars", C.c_int32), ("n_until", C.c_int32), ("n_until_vars", C.c_int32),
+        ("sig_len", C.c_int32), ("sig_vars", C.POINTER(C.c_int32)), ("root_final", C.c_int32),
+        ("n_constraint_sets", C.c_int32), ("n_states", C.c_int64),
+        ("state_sig", C.POINTER(C.c_int32)), ("state_cset", C.POINTER(C.c_int32)),
+        ("state_failed", C.POINTER(C.c_uint8)), ("n_edges", C.c_int64),
+        ("edge_src", C.POINTER(C.c_int32)), ("edge_dst", C.POINTER(C.c_int32)), ("edge_label", C.POINTER(C.c_int32)),
+        ("n_search_nodes", C.c_int64), ("n_fails", C.c_int64), ("n_leaves", C.c_int64), ("n_dominance", C.c_int64),
+        ("n_waves", C.c_int64), ("n_tuples", C.c_int64), ("n_kernel_launches", C.c_int64),
+        ("solve_ms", C.c_double), ("wall_ms", C.c_double), ("expand_ms", C.c_double),
+        ("algorithmic_bytes", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("impl", C.c_void_p),
+    ]
+
+
+class SolutionC(C.Structure):
+    _fields_ = [
+        ("root_valid", C.c_int32), ("adver1", C.c_int32), ("adver2", C.c_int32),
+        ("n_states", C.c_int64), ("n_edges", C.c_int64), ("n_table_states", C.c_int64),
+        ("n_vars", C.c_int32), ("sig_len", C.c_int32),
+        ("state_cset", C.POINTER(C.c_int32)), ("state_final", C.POINTER(C.c_uint8)),
+        ("state_sig", C.POINTER(C.c_int32)),
+        ("edge_src", C.POINTER(C.c_int32)), ("edge_dst", C.POINTER(C.c_int32)), ("edge_label", C.POINTER(C.c_int32)),
+        ("impl", C.c_void_p),
+    ]
+
+
+class StcspError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__("stcsp %s error: %s" % (_STATUS[status] if 0 <= status < len(_STATUS) else status, message))
+        self.status = status
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libstcsp_b200.so (built in-tree by ``__graft_entry__.build()`` / ``make``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: run `python __graft_entry__.py build` (needs nvcc); "
+                              "there is no pure-Python or CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.stcsp_last_error.restype = C.c_char_p
+        L.stcsp_model_parse_text.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.stcsp_model_parse_file.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.stcsp_model_free.argtypes = [C.c_void_p]
+        L.stcsp_model_problem.argtypes = [C.c_void_p]
+        L.stcsp_model_problem.restype = C.POINTER(Problem)
+        L.stcsp_model_dump.argtypes = [C.c_void_p]
+        L.stcsp_model_dump.restype = C.c_void_p
+        L.stcsp_string_free.argtypes = [C.c_void_p]
+        L.stcsp_gpu_solve.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(AutomatonC)]
+        L.stcsp_automaton_free.argtypes = [C.POINTER(AutomatonC)]
+        L.stcsp_automaton_trim.argtypes = [C.POINTER(AutomatonC)]
+        L.stcsp_postprocess.argtypes = [C.POINTER(Problem), C.POINTER(AutomatonC), C.c_int32, C.c_int32,
+                                        C.POINTER(SolutionC)]
+        L.stcsp_solution_free.argtypes = [C.POINTER(SolutionC)]
+        L.stcsp_solution_dot.argtypes = [C.POINTER(Problem), C.POINTER(SolutionC)]
+        L.stcsp_solution_dot.restype = C.c_void_p
+        L.stcsp_solution_canonical.argtypes = [C.POINTER(Problem), C.POINTER(SolutionC)]
+        L.stcsp_solution_canonical.restype = C.c_void_p
+        L.stcsp_gpu_device_count.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != STCSP_OK:
+        raise StcspError(rc, (lib().stcsp_last_error() or b"").decode())
+
+
+def _take_string(ptr) -> str:
+    s = C.string_at(ptr).decode()
+    lib().stcsp_string_free(ptr)
+    return s
+
+
+class Model:
+    """A parsed and normalised .csp model (host side; reference solverParse, src/solver.cpp:138-159)."""
+
+    def __init__(self, text: str, prefix_k: int = 2):
+        self._h = C.c_void_p()
+        _check(lib().stcsp_model_parse_text(text.encode(), prefix_k, C.byref(self._h)))
+        self.problem = lib().stcsp_model_problem(self._h)
+
+    @classmethod
+    def from_file(cls, path: str, prefix_k: int = 2) -> "Model":
+        with open(path) as f:
+            return cls(f.read(), prefix_k)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().stcsp_model_free(self._h)
+            self._h = None
+
+    @property
+    def var_names(self) -> List[str]:
+        p = self.problem.contents
+        return [p.var_names[i].decode() for i in range(p.n_vars)]
+
+    @property
+    def n_vars(self) -> int:
+        return self.problem.contents.n_vars
+
+    @property
+    def n_constraints(self) -> int:
+        return self.problem.contents.n_constraints
+
+    def dump(self) -> str:
+        return _take_string(lib().stcsp_model_dump(self._h))
+
+
+def _np(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+class Automaton:
+    """Owner of one ``stcsp_automaton_t`` plus numpy copies of its arrays."""
+
+    def __init__(self, c_struct: AutomatonC, free_fn):
+        self.c = c_struct
+        self._free = free_fn
+        a = c_struct
+        self.n_vars, self.sig_len = a.n_vars, a.sig_len
+        self.n_states, self.n_edges = a.n_states, a.n_edges
+        self.sig_vars = _np(a.sig_vars, a.n_sig_vars, np.int32)
+        self.state_sig = _np(a.state_sig, a.n_states * a.sig_len, np.int32).reshape(a.n_states, a.sig_len)
+        self.state_cset = _np(a.state_cset, a.n_states, np.int32)
+        self.state_failed = _np(a.state_failed, a.n_states, np.uint8)
+        self.edge_src = _np(a.edge_src, a.n_edges, np.int32)
+        self.edge_dst = _np(a.edge_dst, a.n_edges, np.int32)
+        self.edge_label = _np(a.edge_label, a.n_edges * a.n_vars, np.int32).reshape(a.n_edges, a.n_vars)
+
+    def stats(self) -> dict:
+        a = self.c
+        return {k: getattr(a, k) for k in (
+            "n_states", "n_edges", "n_constraint_sets", "n_search_nodes", "n_fails", "n_leaves", "n_dominance",
+            "n_waves", "n_tuples", "n_kernel_launches", "solve_ms", "wall_ms", "expand_ms", "algorithmic_bytes",
+            "h2d_bytes", "d2h_bytes")}
+
+    def __del__(self):
+        if getattr(self, "_free", None):
+            self._free(C.byref(self.c))
+            self._free = None
+
+
+class Solution:
+    """Post-processed automaton (what the reference prints with -s)."""
+
+    def __init__(self, model: Model, automaton: Automaton, adversarial1: bool = False, adversarial2: bool = False):
+        self.model = model
+        self.c = SolutionC()
+        _check(lib().stcsp_postprocess(model.problem, C.byref(automaton.c), int(adversarial1), int(adversarial2),
+                                       C.byref(self.c)))
+        self.root_valid = bool(self.c.root_valid)
+        self.adver1, self.adver2 = self.c.adver1, self.c.adver2
+        self.n_states, self.n_edges = self.c.n_states, self.c.n_edges
+
+    def dot(self) -> str:
+        return _take_string(lib().stcsp_solution_dot(self.model.problem, C.byref(self.c)))
+
+    def canonical_text(self) -> str:
+        return _take_string(lib().stcsp_solution_canonical(self.model.problem, C.byref(self.c)))
+
+    def canonical_sha256(self) -> str:
+        import hashlib
+        return hashlib.sha256(self.canonical_text().encode()).hexdigest()
+
+    def to_python(self) -> canonical.Automaton:
+        """Re-parse the DOT text with the independent Python canonicaliser."""
+        return canonical.parse_dot(self.dot())
+
+    def __del__(self):
+        if getattr(self, "c", None) is not None and self.c.impl:
+            lib().stcsp_solution_free(C.byref(self.c))
+
+
+def default_options(**kw) -> Options:
+    o = Options()
+    o.device = -1
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def solve(model: Model, options: Optional[Options] = None) -> Automaton:
+    """Run the search on the GPU (stcsp_gpu_solve).  Raises StcspError(ERR_CUDA) without a device."""
+    out = AutomatonC()
+    opts = options if options is not None else default_options()
+    _check(lib().stcsp_gpu_solve(model.problem, C.byref(opts), C.byref(out)))
+    return Automaton(out, lib().stcsp_automaton_free)
+
+
+def solve_text(text: str, flags: Sequence[str] = (), options: Optional[Options] = None):
+    """Convenience mirror of the reference CLI: returns (Model, Automaton, Solution)."""
+    k = 2
+    for f in flags:
+        if f.startswith("-k"):
+            k = int(f[2:])
+    model = Model(text, k)
+    automaton = solve(model, options)
+    return model, automaton, Solution(model, automaton, "-a" in flags, "-z" in flags)

@@ -1,0 +1,591 @@
+// sm_100a kernels of the search-and-propagate path.
+//
+//   expand_kernel : one warp per search node.  Stages the node's domain block in shared memory,
+//                   propagates to a fixpoint (reference generalisedArcConsistent,
+//                   src/solveralgorithm.cpp:617-706), then either fails, emits a leaf record, or
+//                   branches on the first unbound variable (solverSolveRe, :911-939; here all values
+//                   of the variable at once instead of a binary split -- search order is not a
+//                   parity target).
+//   ingest_kernel : one warp per leaf record.  Builds the successor signature (:810-837), finds or
+//                   inserts it in the open-addressing state table (vertexTableGetVertex/AddVertex,
+//                   src/graph.cpp:108-123), appends the edge (edgeNew, src/graph.cpp:78-89) and, for a
+//                   new state, writes its first search node (variableAdvanceOneTimeStep,
+//                   src/variable.cpp:94-108).
+//
+// Propagation of a pointwise constraint replaces the reference's per-value nested-loop support
+// search (findSupportRe, :435-464) by ONE cooperative enumeration of the tuples over the current
+// domains of the still-unbound variables: 32 lanes walk the mixed-radix tuple space, evaluate the
+// constraint's bytecode (solverValidateRe, :336-424) and OR the bits of every satisfying tuple into
+// per-variable support sets; the new domains are the support sets (domain consistency, at least as
+// strong as the reference's bounds revision :476-523).  Enumerations larger than the budget are
+// skipped (sound: a skipped propagator only prunes less) and re-armed when a domain shrinks; at a
+// leaf every constraint has exactly one tuple, so every leaf is checked exactly.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace stcsp {
+
+namespace {
+
+typedef unsigned long long u64;
+
+struct WarpMem {
+    int32_t *nodew;     // node words (header + domains)
+    uint32_t *dirty;    // propagator bitmask
+    u64 *supp;          // [max_scope] support sets of the constraint being revised
+    int32_t *flb;       // [max_scope] lb of free variable r
+    int32_t *fdi;       // [max_scope] domain index (var*k+off) of free variable r
+    int32_t *cur;       // [max_scope][32] current tuple values per lane
+    int32_t *stk;       // [max_stack+1][32] evaluator stack per lane
+    uint8_t *vals;      // [max_scope][64] bit positions of the values of each scope variable
+    uint8_t *dig;       // [max_scope][32] mixed-radix digits per lane
+    uint8_t *fl, *fd, *sd, *rk;   // [max_scope] free slot list, radix, +32 step digits, slot -> rank
+};
+
+__host__ __device__ inline size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
+
+__host__ __device__ inline size_t warp_bytes(const DevModel &m) {
+    size_t b = 0;
+    b += align8((size_t)m.node_words * 4);
+    b += align8((size_t)m.max_words * 4);
+    b += (size_t)m.max_scope * 8;
+    b += align8((size_t)m.max_scope * 4) * 2;
+    b += (size_t)m.max_scope * 32 * 4;
+    b += (size_t)(m.max_stack + 1) * 32 * 4;
+    b += (size_t)m.max_scope * 64;
+    b += (size_t)m.max_scope * 32;
+    b += align8((size_t)m.max_scope) * 4;
+    return align8(b);
+}
+
+__device__ inline WarpMem carve(unsigned char *base, const DevModel &m) {
+    WarpMem w;
+    unsigned char *p = base;
+    w.nodew = (int32_t *)p; p += align8((size_t)m.node_words * 4);
+    w.dirty = (uint32_t *)p; p += align8((size_t)m.max_words * 4);
+    w.supp = (u64 *)p; p += (size_t)m.max_scope * 8;
+    w.flb = (int32_t *)p; p += align8((size_t)m.max_scope * 4);
+    w.fdi = (int32_t *)p; p += align8((size_t)m.max_scope * 4);
+    w.cur = (int32_t *)p; p += (size_t)m.max_scope * 32 * 4;
+    w.stk = (int32_t *)p; p += (size_t)(m.max_stack + 1) * 32 * 4;
+    w.vals = p; p += (size_t)m.max_scope * 64;
+    w.dig = p; p += (size_t)m.max_scope * 32;
+    w.fl = p; p += align8((size_t)m.max_scope);
+    w.fd = p; p += align8((size_t)m.max_scope);
+    w.sd = p; p += align8((size_t)m.max_scope);
+    w.rk = p;
+    return w;
+}
+
+__device__ __forceinline__ u64 width_mask(int w) { return w >= 64 ? ~0ull : ((1ull << w) - 1ull); }
+__device__ __forceinline__ u64 shift_bits(u64 v, int s) {
+    if (s >= 64 || s <= -64) return 0ull;
+    return s >= 0 ? (v << s) : (v >> (-s));
+}
+
+// ---- bytecode evaluator: one tuple per lane (reference solverValidateRe) --------------------------
+__device__ __forceinline__ int eval_tuple(const Instr *__restrict__ code, const int32_t *cur, int32_t *stk, int lane,
+                                          const DevModel &M) {
+    int pc = 0, sp = 0, tos = 0;
+    bool valid = true;
+    for (;;) {
+        const int2 in = __ldg(reinterpret_cast<const int2 *>(code) + pc);
+        pc++;
+        const int arg = in.y;
+        int l;
+        switch (in.x) {
+            case BC_END: return tos != 0;
+            case BC_PUSHC: stk[sp * 32 + lane] = tos; sp++; tos = arg; break;
+            case BC_PUSHV: stk[sp * 32 + lane] = tos; sp++; tos = cur[arg * 32 + lane]; break;
+            case BC_ARR: {
+                const int lo = M.arr_off[arg], n = M.arr_off[arg + 1] - lo;
+                if (tos < 0 || tos >= n) { valid = false; tos = 0; }
+                else tos = M.arr_val[lo + tos];
+                break;
+            }
+            case BC_ABS: tos = tos < 0 ? (int)(0u - (unsigned)tos) : tos; break;
+            case BC_NOT: tos = (tos == 0); break;
+            case BC_LT: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l < tos) : 0; break;
+            case BC_GT: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l > tos) : 0; break;
+            case BC_LE: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l <= tos) : 0; break;
+            case BC_GE: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l >= tos) : 0; break;
+            case BC_EQ: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l == tos) : 0; break;
+            case BC_NE: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l != tos) : 0; break;
+            case BC_ADD: sp--; l = stk[sp * 32 + lane]; tos = valid ? (int)((unsigned)l + (unsigned)tos) : 0; break;
+            case BC_SUB: sp--; l = stk[sp * 32 + lane]; tos = valid ? (int)((unsigned)l - (unsigned)tos) : 0; break;
+            case BC_MUL: sp--; l = stk[sp * 32 + lane]; tos = valid ? (int)((unsigned)l * (unsigned)tos) : 0; break;
+            case BC_DIV:
+            case BC_MOD:
+                sp--; l = stk[sp * 32 + lane];
+                if (!valid) tos = 0;
+                else if (tos == 0 || (l == (int)0x80000000 && tos == -1)) { valid = false; tos = 0; }
+                else tos = in.x == BC_DIV ? l / tos : l % tos;
+                break;
+            case BC_JZ: l = tos; sp--; tos = stk[sp * 32 + lane]; if (l == 0) pc = arg; break;
+            case BC_JMP: pc = arg; break;
+            case BC_AND_SC: if (tos == 0) pc = arg; else { sp--; tos = stk[sp * 32 + lane]; } break;
+            case BC_OR_SC: if (tos != 0) { tos = 1; pc = arg; } else { sp--; tos = stk[sp * 32 + lane]; } break;
+            case BC_IMPLY_SC: if (tos == 0) { tos = 1; pc = arg; } break;
+            case BC_IMPLY_FIN: sp--; l = stk[sp * 32 + lane]; tos = (l <= tos); break;
+            default: return 0;
+        }
+    }
+}
+
+__device__ __forceinline__ u64 sat_mul(u64 a, u64 b) {
+    const u64 cap = 1ull << 40;
+    if (a >= cap || b >= cap) return cap;
+    u64 p = a * b;          // < 2^80 would overflow only if both >= 2^24; clamp conservatively
+    if (a >= (1ull << 24) && b >= (1ull << 24)) return cap;
+    return p > cap ? cap : p;
+}
+
+struct NodeCtx {
+    const DevModel &M;
+    const DevSet &S;
+    WarpMem &wm;
+    u64 *dom;
+    int lane;
+    int expire;
+    unsigned long long tuples;
+};
+
+__device__ __forceinline__ void mark_changed(NodeCtx &c, int var, int off) {
+    const uint32_t *wk = c.M.wake + c.S.wake_off + ((size_t)var * c.M.k + off) * c.S.n_words;
+    for (int w = c.lane; w < c.S.n_words; w += 32) c.wm.dirty[w] |= wk[w];
+    __syncwarp();
+}
+
+// Pointwise constraint at one time offset.  Returns false on wipe-out.
+__device__ bool revise_point(NodeCtx &c, const DevCon &con, int off) {
+    const DevModel &M = c.M;
+    WarpMem &wm = c.wm;
+    const int lane = c.lane, n = con.n_scope, k = M.k;
+    const int myvar = lane < n ? M.scope[con.scope_off + lane] : 0;
+    const u64 myd = lane < n ? c.dom[myvar * k + off] : 1ull;
+    const int dsz = __popcll(myd);
+    u64 prod = (u64)dsz;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) prod = sat_mul(prod, __shfl_xor_sync(0xffffffffu, prod, s));
+    const long long limit = off == 0 ? M.enum_now : M.enum_ahead;
+    if ((long long)prod > limit) return true;           // skipped: re-armed when a domain of the scope shrinks
+    const unsigned fmask = __ballot_sync(0xffffffffu, lane < n && dsz > 1);
+    const int nf = __popc(fmask);
+    if (lane < n) {
+        int j = 0;
+        for (u64 w = myd; w; w &= w - 1) wm.vals[lane * 64 + j++] = (uint8_t)(__ffsll((long long)w) - 1);
+        wm.supp[lane] = 0ull;
+        if (dsz > 1) {
+            const int r = __popc(fmask & ((1u << lane) - 1u));
+            wm.fl[r] = (uint8_t)lane;
+            wm.fd[r] = (uint8_t)dsz;
+            wm.flb[r] = M.lb[myvar];
+            wm.fdi[r] = myvar * k + off;
+            wm.rk[lane] = (uint8_t)r;
+        } else {
+            wm.rk[lane] = 255;
+        }
+    }
+    __syncwarp();
+    {
+        int t = lane, t32 = 32;
+        for (int r = 0; r < nf; r++) {
+            const int f = wm.fd[r];
+            wm.dig[r * 32 + lane] = (uint8_t)(t % f);
+            t /= f;
+            if (lane == 0) wm.sd[r] = (uint8_t)(t32 % f);
+            t32 /= f;
+        }
+    }
+    __syncwarp();
+    for (int i = 0; i < n; i++) {
+        const int v = M.scope[con.scope_off + i];
+        const int r = wm.rk[i];
+        const int d = r == 255 ? 0 : wm.dig[r * 32 + lane];
+        wm.cur[i * 32 + lane] = M.lb[v] + wm.vals[i * 64 + d];
+    }
+    const Instr *code = M.code + con.code_off;
+    bool any = false;
+    u64 done = 0;
+    for (u64 tbase = 0; tbase < prod; tbase += 32) {
+        const bool active = tbase + lane < prod;
+        int ok = 0;
+        if (active) ok = eval_tuple(code, wm.cur, wm.stk, lane, M);
+        if (ok) {
+            for (int r = 0; r < nf; r++) {
+                const int i = wm.fl[r];
+                const u64 bit = 1ull << wm.vals[i * 64 + wm.dig[r * 32 + lane]];
+                if (!(wm.supp[i] & bit)) atomicOr(&wm.supp[i], bit);
+            }
+        }
+        any |= __ballot_sync(0xffffffffu, ok) != 0u;
+        done = tbase + 32;
+        __syncwarp();
+        const bool full = lane < nf ? (wm.supp[wm.fl[lane]] == c.dom[wm.fdi[lane]]) : true;
+        if (any && __all_sync(0xffffffffu, full)) break;    // every value already supported: nothing to prune
+        int carry = 0;
+        for (int r = 0; r < nf; r++) {
+            const int f = wm.fd[r];
+            int d = wm.dig[r * 32 + lane] + wm.sd[r] + carry;
+            carry = d >= f;
+            if (carry) d -= f;
+            wm.dig[r * 32 + lane] = (uint8_t)d;
+            const int i = wm.fl[r];
+            wm.cur[i * 32 + lane] = wm.flb[r] + wm.vals[i * 64 + d];
+        }
+    }
+    c.tuples += done < prod ? done : prod;
+    if (!any) return false;
+    bool changed = false;
+    int cvar_idx = 0;
+    if (lane < nf) {
+        const u64 nd = wm.supp[wm.fl[lane]];
+        cvar_idx = wm.fdi[lane];
+        if (nd != c.dom[cvar_idx]) { c.dom[cvar_idx] = nd; changed = true; }
+    }
+    unsigned cm = __ballot_sync(0xffffffffu, changed);
+    __syncwarp();
+    while (cm) {
+        const int r = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const int idx = __shfl_sync(0xffffffffu, cvar_idx, r);
+        mark_changed(c, idx / k, idx % k);
+    }
+    return true;
+}
+
+// x == next y: values of y at offset p+1 are the values of x at offset p (reference
+// enforceNextConsistency, src/solveralgorithm.cpp:544-593).
+__device__ bool revise_next(NodeCtx &c, const DevCon &con) {
+    const DevModel &M = c.M;
+    const int k = M.k, x = con.x, y = con.y;
+    const int s = M.lb[x] - M.lb[y];                    // bit index in y = bit index in x + s
+    for (int p = 0; p + 1 < k; p++) {
+        const u64 X = c.dom[x * k + p], Y = c.dom[y * k + p + 1];
+        const u64 nX = X & shift_bits(Y, -s) & width_mask(M.width[x]);
+        const u64 nY = Y & shift_bits(X, s) & width_mask(M.width[y]);
+        if (nX == 0ull || nY == 0ull) return false;
+        __syncwarp();
+        if (nX != X) {
+            if (c.lane == 0) c.dom[x * k + p] = nX;
+            mark_changed(c, x, p);
+        }
+        if (nY != Y) {
+            if (c.lane == 0) c.dom[y * k + p + 1] = nY;
+            mark_changed(c, y, p + 1);
+        }
+    }
+    return true;
+}
+
+// x until y (reference enforceUntilConsistency, src/solveralgorithm.cpp:598-614)
+__device__ bool revise_until(NodeCtx &c, const DevCon &con) {
+    if ((c.expire >> con.until_idx) & 1) return true;
+    const u64 L = c.dom[con.x * c.M.k], R = c.dom[con.y * c.M.k];
+    if (__popcll(L) == 1 && __popcll(R) == 1) {
+        const int lv = c.M.lb[con.x] + __ffsll((long long)L) - 1;
+        const int rv = c.M.lb[con.y] + __ffsll((long long)R) - 1;
+        if (lv != 1 && rv != 1) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const DevModel M, const Pools P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpMem wm = carve(smem + (size_t)warp * warp_bytes(M), M);
+    const long long n_in = (long long)P.counters[C_IN];
+    const long long total_warps = (long long)gridDim.x * kExpandWarps;
+    const int V = M.V, k = M.k, NW = M.node_words;
+    unsigned long long st_nodes = 0, st_fails = 0, st_tuples = 0;
+
+    for (long long ni = (long long)blockIdx.x * kExpandWarps + warp; ni < n_in; ni += total_warps) {
+        const int32_t *src = P.in_nodes + ni * NW;
+        for (int w = lane; w < NW; w += 32) wm.nodew[w] = src[w];
+        __syncwarp();
+        const int cid = wm.nodew[1], bvar = wm.nodew[3];
+        const DevSet S = M.sets[cid];
+        NodeCtx ctx{M, S, wm, reinterpret_cast<u64 *>(wm.nodew + 4), lane, wm.nodew[2], 0ull};
+        u64 *dom = ctx.dom;
+
+        bool empty = false;
+        for (int i = lane; i < V * k; i += 32) empty |= dom[i] == 0ull;
+        bool fail = __any_sync(0xffffffffu, empty);
+
+        for (int w = lane; w < S.n_words; w += 32) {
+            uint32_t m;
+            if (bvar < 0) {
+                const int left = S.n_prop - w * 32;
+                m = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+            } else {
+                m = M.wake[S.wake_off + ((size_t)bvar * k) * S.n_words + w];
+            }
+            wm.dirty[w] = m;
+        }
+        __syncwarp();
+
+        while (!fail) {
+            int q = -1;
+            for (int base = 0; base < S.n_words; base += 32) {
+                const uint32_t w = base + lane < S.n_words ? wm.dirty[base + lane] : 0u;
+                const unsigned b = __ballot_sync(0xffffffffu, w != 0u);
+                if (b) {
+                    const int l = __ffs(b) - 1;
+                    const uint32_t ww = __shfl_sync(0xffffffffu, w, l);
+                    q = (base + l) * 32 + __ffs(ww) - 1;
+                    break;
+                }
+            }
+            if (q < 0) break;
+            const DevProp pr = M.props[S.prop_off + q];
+            const DevCon con = M.cons[pr.con];
+            bool ok;
+            if (con.kind == DK_POINT) ok = revise_point(ctx, con, pr.offset);
+            else if (con.kind == DK_NEXT) ok = revise_next(ctx, con);
+            else ok = revise_until(ctx, con);
+            __syncwarp();
+            if (lane == 0) wm.dirty[q >> 5] &= ~(1u << (q & 31));   // revisions are idempotent
+            __syncwarp();
+            fail = !ok;
+        }
+        st_nodes++;
+        st_tuples += ctx.tuples;
+        if (fail) { st_fails++; continue; }
+
+        int bv = -1;
+        for (int base = 0; base < V; base += 32) {
+            const int v = base + lane;
+            const bool unbound = v < V && __popcll(dom[v * k]) > 1;
+            const unsigned b = __ballot_sync(0xffffffffu, unbound);
+            if (b) { bv = base + __ffs(b) - 1; break; }
+        }
+        if (bv < 0) {
+            // leaf: every variable bound at the current time point
+            unsigned long long li = 0;
+            if (lane == 0) li = atomicAdd(&P.counters[C_LEAVES], 1ull);
+            li = __shfl_sync(0xffffffffu, li, 0);
+            if ((long long)li >= P.leaf_cap) {
+                if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 2ull);
+                continue;
+            }
+            int32_t *rec = P.leaves + li * M.rec_words;
+            if (lane < 4) rec[lane] = lane == 3 ? 0 : wm.nodew[lane];
+            for (int v = lane; v < V; v += 32) rec[4 + v] = M.lb[v] + __ffsll((long long)dom[v * k]) - 1;
+        } else {
+            const u64 D = dom[bv * k];
+            const int d = __popcll(D);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&P.counters[C_OUT], (unsigned long long)d);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((long long)(base + d) > P.out_cap) {
+                if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
+                continue;
+            }
+            const int dw = 4 + 2 * (bv * k);
+            int j = 0;
+            for (u64 w = D; w; w &= w - 1, j++) {
+                const u64 one = w & (~w + 1ull);
+                int32_t *dst = P.out_nodes + (base + j) * NW;
+                for (int i = lane; i < NW; i += 32) {
+                    int32_t val = wm.nodew[i];
+                    if (i == 3) val = bv;
+                    else if (i == dw) val = (int32_t)(uint32_t)(one & 0xffffffffull);
+                    else if (i == dw + 1) val = (int32_t)(uint32_t)(one >> 32);
+                    dst[i] = val;
+                }
+            }
+        }
+    }
+    if (lane == 0 && st_nodes) {
+        atomicAdd(&P.counters[C_NODES], st_nodes);
+        if (st_fails) atomicAdd(&P.counters[C_FAILS], st_fails);
+        if (st_tuples) atomicAdd(&P.counters[C_TUPLES], st_tuples);
+    }
+}
+
+// ---- ingest ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+
+__device__ __forceinline__ int key_word(const DevModel &M, const int32_t *rec, int ncid, int nexp, int j) {
+    if (j == 0) return ncid;
+    if (j <= M.n_sig) return rec[4 + M.sig_vars[j - 1]];
+    return (nexp >> (j - 1 - M.n_sig)) & 1;
+}
+
+__host__ __device__ inline uint32_t cap_hash(int cid, const int32_t *vals, int n) {
+    uint32_t h = 0x9e3779b9u * (uint32_t)(cid + 1);
+    for (int i = 0; i < n; i++) {
+        h ^= (uint32_t)vals[i] + 0x9e3779b9u + (h << 6) + (h >> 2);
+    }
+    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
+    return h;
+}
+
+__global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const Pools P, const int32_t *list, long long count) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long n = list ? count : (long long)P.counters[C_LEAVES];
+    const int V = M.V, k = M.k, KW = M.key_words, NW = M.node_words;
+
+    for (long long it = warp_id; it < n; it += total_warps) {
+        const long long li = list ? (long long)list[it] : it;
+        const int32_t *rec = P.leaves + li * M.rec_words;
+        const int src = rec[0], cid = rec[1], exp = rec[2];
+        const DevSet S = M.sets[cid];
+        int ncid = S.static_next;
+        if (S.n_cap > 0) {
+            // successor constraint set depends on the values captured by `first`
+            int found = -1;
+            if (lane == 0) {
+                int32_t vals[Limits::kMaxCap];
+                for (int i = 0; i < S.n_cap; i++) vals[i] = rec[4 + M.aux[S.cap_off + i]];
+                uint32_t h = cap_hash(cid, vals, S.n_cap) & (uint32_t)P.capmap_mask;
+                for (;;) {
+                    const CapEntry &e = P.capmap[h];
+                    if (e.cid == -1) break;
+                    bool eq = e.cid == cid;
+                    for (int i = 0; eq && i < S.n_cap; i++) eq = e.vals[i] == vals[i];
+                    if (eq) { found = e.next; break; }
+                    h = (h + 1) & (uint32_t)P.capmap_mask;
+                }
+            }
+            found = __shfl_sync(0xffffffffu, found, 0);
+            if (found < 0) {
+                if (lane == 0) {
+                    const unsigned long long u = atomicAdd(&P.counters[C_UNRESOLVED], 1ull);
+                    if ((long long)u < P.unresolved_cap) P.unresolved[u] = (int32_t)li;
+                    else atomicOr(&P.counters[C_OVERFLOW], 16ull);
+                }
+                continue;
+            }
+            ncid = found;
+        }
+        const DevSet NS = M.sets[ncid];
+        int nexp = exp;                                   // until flags (src/solveralgorithm.cpp:821-834)
+        for (int u = 0; u < NS.n_until; u++)
+            if (rec[4 + M.aux[NS.until_off + u]] == 1) nexp |= 1 << u;
+
+        uint32_t h = 0;
+        for (int j = lane; j < KW; j += 32) h ^= mix32((uint32_t)key_word(M, rec, ncid, nexp, j) * 0x9e3779b1u + (uint32_t)j);
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, s);
+        h = mix32(h);
+
+        long long slot = (long long)h & P.table_mask;
+        int dst = -1;
+        bool is_new = false, abort_leaf = false;
+        for (;;) {
+            int v = 0;
+            if (lane == 0) v = atomicCAS(&P.table[slot], -1, -2);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            if (v == -1) {                                // slot claimed: this leaf creates the state
+                unsigned long long id = 0;
+                if (lane == 0) id = atomicAdd(&P.counters[C_STATES], 1ull);
+                id = __shfl_sync(0xffffffffu, id, 0);
+                if ((long long)id >= P.state_cap) {
+                    if (lane == 0) { atomicOr(&P.counters[C_OVERFLOW], 4ull); atomicExch(&P.table[slot], -3); }
+                    abort_leaf = true;
+                    break;
+                }
+                for (int j = lane; j < KW; j += 32) P.state_key[id * KW + j] = key_word(M, rec, ncid, nexp, j);
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicExch(&P.table[slot], (int)id);
+                dst = (int)id;
+                is_new = true;
+                break;
+            }
+            if (v == -2) {                                // another warp is writing this slot's key
+                if (lane == 0) {
+                    volatile int32_t *vs = P.table + slot;
+                    do { v = *vs; } while (v == -2);
+                }
+                v = __shfl_sync(0xffffffffu, v, 0);
+            }
+            if (v == -3) { abort_leaf = true; break; }
+            __threadfence();
+            bool eq = true;
+            for (int j = lane; j < KW; j += 32) eq &= __ldcg(&P.state_key[(long long)v * KW + j]) == key_word(M, rec, ncid, nexp, j);
+            if (__all_sync(0xffffffffu, eq)) { dst = v; break; }
+            slot = (slot + 1) & P.table_mask;
+        }
+        if (abort_leaf) continue;
+
+        if (is_new) {
+            // first search node of the new state: next-linked variables take the values just chosen,
+            // everything else restarts from its declared range
+            unsigned long long o = 0;
+            if (lane == 0) o = atomicAdd(&P.counters[C_OUT], 1ull);
+            o = __shfl_sync(0xffffffffu, o, 0);
+            if ((long long)o >= P.out_cap) {
+                if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
+            } else {
+                int32_t *node = P.out_nodes + o * NW;
+                if (lane == 0) { node[0] = dst; node[1] = ncid; node[2] = nexp; node[3] = -1; }
+                u64 *nd = reinterpret_cast<u64 *>(node + 4);
+                for (int i = lane; i < V * k; i += 32) {
+                    const int v = i / k, p = i % k;
+                    u64 m = width_mask(M.width[v]);
+                    if (p == 0) {
+                        for (int t = 0; t < NS.n_next; t++) {
+                            if (M.aux[NS.next_off + 2 * t + 1] != v) continue;
+                            const int b = rec[4 + M.aux[NS.next_off + 2 * t]] - M.lb[v];
+                            m &= (b >= 0 && b < 64) ? (1ull << b) : 0ull;
+                        }
+                    }
+                    nd[i] = m;
+                }
+            }
+        } else if (lane == 0) {
+            atomicAdd(&P.counters[C_DOMINANCE], 1ull);
+        }
+        unsigned long long e = 0;
+        if (lane == 0) e = atomicAdd(&P.counters[C_EDGES], 1ull);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if ((long long)e >= P.edge_cap) {
+            if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 8ull);
+            continue;
+        }
+        if (lane == 0) { P.edge_src[e] = src; P.edge_dst[e] = dst; }
+        for (int v = lane; v < V; v += 32) P.edge_label[e * V + v] = rec[4 + v];
+    }
+}
+
+__global__ void fill_kernel(int32_t *ptr, long long n, int32_t value) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        ptr[i] = value;
+}
+
+}  // namespace
+
+uint32_t capmap_hash(int cid, const int32_t *vals, int n) { return cap_hash(cid, vals, n); }
+
+size_t expand_smem_bytes(const DevModel &m) { return warp_bytes(m) * kExpandWarps; }
+
+void launch_expand(const DevModel &m, const Pools &p, int grid, cudaStream_t stream) {
+    const size_t smem = expand_smem_bytes(m);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    expand_kernel<<<grid, kExpandWarps * 32, smem, stream>>>(m, p);
+}
+
+void launch_ingest(const DevModel &m, const Pools &p, const int32_t *list, long long count, int grid, cudaStream_t stream) {
+    ingest_kernel<<<grid, 256, 0, stream>>>(m, p, list, count);
+}
+
+void launch_fill(int32_t *ptr, long long n, int32_t value, cudaStream_t stream) {
+    if (n <= 0) return;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    fill_kernel<<<(int)blocks, 256, 0, stream>>>(ptr, n, value);
+}
+
+}  // namespace stcsp

@@ -1,0 +1,104 @@
+// Device side of the search: data layout shared between the kernels and the host driver.
+//
+// SEARCH NODE (reference: the trail-protected currLB/currUB windows of all variables at one point
+// of solverSolveRe, src/variable.h:19-20) -- a self-contained block of int32 words:
+//     [0] source state id   [1] constraint-set id   [2] until-expired bits   [3] branched variable (-1: new state)
+//     [4 ...] V*k uint64 domain bitsets, index (var*k + offset); bit b of variable v = value lb[v] + b
+// LEAF RECORD (a complete consistent assignment of one time point, src/solveralgorithm.cpp:739-749):
+//     [0] source state id   [1] constraint-set id   [2] until-expired bits   [3] 0   [4 ...] V values
+//   after route_kernel: [1] SUCCESSOR constraint-set id (-1: host must resolve)  [2] successor until bits
+//                       [3] hash of the successor's state key (owner rank and table slot derive from it)
+// STATE IDS are global: local index * world + rank.
+// STATE KEY (reference Signature, src/graph.h:14-21):
+//     [0] constraint-set id (root: -1 unless the signature is empty)   [1 ...] signature values, until flags
+#pragma once
+
+#include <cstdint>
+
+#include "compile.h"
+
+namespace stcsp {
+
+enum Counter : int {
+    C_IN = 0,          // nodes in the input frontier of the current wave
+    C_OUT,             // nodes written to the output frontier
+    C_LEAVES,          // leaf records written this wave
+    C_STATES,          // states allocated (all waves)
+    C_EDGES,           // edges appended (all waves)
+    C_UNRESOLVED,      // leaves whose successor constraint set the host must compute
+    C_OVERFLOW,        // bit flags: 1 frontier, 2 leaves, 4 states, 8 edges, 16 unresolved list
+    C_NODES,           // statistics: search nodes propagated
+    C_FAILS,
+    C_TUPLES,
+    C_DOMINANCE,
+    C_LEAVES_TOTAL,
+    C_OWNER0,          // C_OWNER0 + r: routed leaves owned by rank r (this wave)
+    C_COUNT = C_OWNER0 + 16
+};
+
+struct DevModel {
+    int32_t V, k;
+    int32_t world, rank;        // one process per GPU; states are owned by hash (world == 1: everything local)
+    int32_t node_words, rec_words, key_words;
+    int32_t n_sig, sig_len;
+    int32_t max_scope, max_stack, max_words;
+    long long enum_now, enum_ahead;
+    const int32_t *lb, *width, *sig_vars;
+    const DevSet *sets;
+    const DevCon *cons;
+    const DevProp *props;
+    const int32_t *scope;
+    const Instr *code;
+    const uint32_t *wake;
+    const int32_t *aux;
+    const int32_t *arr_off, *arr_val;
+};
+
+struct CapEntry {          // (constraint set, captured values) -> successor set; host-filled
+    int32_t cid;           // -1 = empty slot
+    int32_t next;
+    int32_t vals[Limits::kMaxCap];
+};
+
+struct Pools {
+    // frontier / leaves
+    const int32_t *in_nodes;
+    int32_t *out_nodes;
+    long long out_cap;
+    int32_t *leaves;
+    long long leaf_cap;
+    // automaton
+    int32_t *table;         // open addressing: state id, -1 empty, -2 being written
+    long long table_mask;
+    int32_t *state_key;     // [state * key_words]
+    long long state_cap;
+    int32_t *edge_src, *edge_dst, *edge_label;
+    long long edge_cap;
+    // constraint-set transitions
+    const CapEntry *capmap;
+    int32_t capmap_mask;
+    int32_t *unresolved;    // leaf indices
+    long long unresolved_cap;
+    unsigned long long *counters;
+};
+
+constexpr int kExpandWarps = 8;      // warps per CTA of the expand kernel
+
+size_t expand_smem_bytes(const DevModel &m);
+void launch_expand(const DevModel &m, const Pools &p, int grid, cudaStream_t stream);
+// leaves [first, first + count) or, when list != nullptr, the leaves list[0 .. count)
+void launch_route(const DevModel &m, const Pools &p, const int32_t *list, long long count, int grid,
+                  cudaStream_t stream);
+// records [0, count) of `records` (count < 0: the local leaf buffer, length read from the device counter)
+void launch_ingest(const DevModel &m, const Pools &p, const int32_t *records, long long count, int grid,
+                   cudaStream_t stream);
+// group the routed local leaves by owner rank into `outbox` (offsets = exclusive prefix of owner_counts)
+void launch_scatter(const DevModel &m, const Pools &p, long long n_leaves, const long long *dev_offsets,
+                    unsigned long long *dev_fill, int32_t *outbox, int grid, cudaStream_t stream);
+void launch_wave_reset(const Pools &p, cudaStream_t stream);
+uint32_t capmap_hash(int cid, const int32_t *vals, int n);
+uint32_t state_key_hash(const int32_t *key, int key_words);
+int32_t owner_of_hash(uint32_t h, int32_t world, int32_t sig_len);
+void launch_fill(int32_t *ptr, long long n, int32_t value, cudaStream_t stream);
+
+}  // namespace stcsp
