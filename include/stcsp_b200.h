@@ -95,9 +95,10 @@ typedef struct stcsp_options {
     int64_t max_frontier_nodes;      /* capacity of each search-node frontier buffer */
     int64_t max_states;              /* capacity of the state table */
     int64_t max_edges;               /* capacity of the edge store */
-    int32_t keep_failed_edges;       /* debugging: do not trim */
+    int32_t reserved0;
     int32_t profile_kernels;         /* 1: CUDA-event time every expand launch (fills expand_ms) */
-    int32_t reserved[6];
+    int32_t no_trim;                 /* 1: stcsp_gpu_solve returns the untrimmed automaton */
+    int32_t reserved[5];
 } stcsp_options_t;
 
 /* ---------------------------------------------------------------------------------------------
@@ -137,10 +138,12 @@ typedef struct stcsp_automaton {
     int64_t n_dominance;             /* leaves that hit an existing state */
     int64_t n_waves;                 /* frontier iterations */
     int64_t n_tuples;                /* constraint evaluations */
+    int64_t n_revisions;             /* propagator executions */
     int64_t n_kernel_launches;
     double solve_ms;                 /* device time, CUDA events around the whole search */
     double wall_ms;                  /* host wall clock of the call incl. uploads/downloads */
-    double expand_ms;                /* device time inside the expand kernel only (sum over waves) */
+    double expand_ms;                /* device time inside the expand kernel only (sum over waves; needs profile_kernels) */
+    int64_t n_expand_launches;
     int64_t algorithmic_bytes;       /* SURVEY.md section 8(d) formula with this run's counts */
     int64_t h2d_bytes, d2h_bytes;
     void *impl;                      /* private */
@@ -173,39 +176,59 @@ int stcsp_gpu_device_count(void);
 /* ---------------------------------------------------------------------------------------------
  * Step-wise session API: the same search, one frontier wave at a time, so that a multi-GPU
  * driver (one process per GPU) can exchange leaf records by hash owner between `expand` and
- * `ingest`.  stcsp_gpu_solve() is exactly create / loop(expand, ingest) / finish on one rank.
+ * `ingest`.  stcsp_gpu_solve() is exactly create / loop(expand, [resolve], ingest) / finish /
+ * assemble / trim on one rank.
  *
- * A leaf record is `rec_words` int32: [src_state_global, cset, n_until_flags.., sig.., label..];
- * see DESIGN.md "leaf record".  Outbox/inbox buffers are caller-provided DEVICE memory so the
- * caller's collective (NCCL all-to-all through torch.distributed) moves them without copies.
+ * One wave on every rank:
+ *   expand   propagate + branch every search node of the local frontier; route every leaf
+ *            (successor constraint set, until flags, hash of the successor's state key)
+ *   pending / resolve   only when a leaf's successor constraint set is not known yet (models whose
+ *            `first` captures values, reference src/constraint.cpp:466-548): the driver collects the
+ *            requests of ALL ranks, sorts them, and hands the same list to every rank, so that
+ *            constraint-set ids are identical everywhere
+ *   outbox   (world_size > 1) leaves grouped by owner rank into caller-provided DEVICE memory; the
+ *            caller's collective (NCCL all-to-all through torch.distributed) moves them
+ *   ingest   dedup the received leaves against the local state table, append edges, create the
+ *            first search node of every new state; ends the wave
+ *
+ * A leaf record is `rec_words` int32: [src_state_global, successor_cset, successor_until_bits,
+ * state_key_hash, label[n_vars]].
  * ------------------------------------------------------------------------------------------- */
 typedef struct stcsp_session stcsp_session_t;
 
 int stcsp_session_create(const stcsp_problem_t *problem, const stcsp_options_t *options,
                          int32_t rank, int32_t world_size, stcsp_session_t **out);
 void stcsp_session_destroy(stcsp_session_t *s);
-/* int32 words per leaf record */
+/* int32 words per leaf record / per resolve request (1 + n_vars: constraint set, assignment) */
 int32_t stcsp_session_record_words(const stcsp_session_t *s);
-/* Expand the whole local frontier by one wave.  Leaves are written to `outbox` (device, capacity
- * `outbox_capacity` records), grouped by owner rank; counts_per_rank[world_size] (host) receives
- * the number of records for each rank; record r of rank q is at outbox + (offset_q + r)*rec_words
- * with offset_q the exclusive prefix sum of the counts.  *frontier_left is the number of local
- * search nodes waiting for the next wave (before ingest). */
-int stcsp_session_expand(stcsp_session_t *s, int32_t *outbox, int64_t outbox_capacity,
-                         int64_t *counts_per_rank, int64_t *frontier_left);
-/* Insert `n_records` leaf records (device memory) this rank owns: dedup against the state table,
- * append edges, create the search nodes of new states.  *frontier_left as above, after ingest. */
-int stcsp_session_ingest(stcsp_session_t *s, const int32_t *inbox, int64_t n_records, int64_t *frontier_left);
-/* Local part of the automaton (states this rank owns and edges into them), untrimmed, with global
- * state ids `local_index * world_size + rank`; the driver merges the parts and calls
- * stcsp_automaton_trim on the union. */
-int stcsp_session_finish(stcsp_session_t *s, stcsp_automaton_t *out);
-/* Owner rank of a leaf record's destination state (same hash the device uses). */
-int32_t stcsp_record_owner(const int32_t *record_host, int32_t rec_words, int32_t key_offset, int32_t key_words,
-                           int32_t world_size);
+int32_t stcsp_session_request_words(const stcsp_session_t *s);
+/* Expand the local frontier by one wave.  *n_leaves: leaves found; *n_pending: distinct resolve
+ * requests this rank has (0 almost always). */
+int stcsp_session_expand(stcsp_session_t *s, int64_t *n_leaves, int64_t *n_pending);
+/* Copy the pending requests to host memory [n_pending * request_words]. */
+int stcsp_session_pending(stcsp_session_t *s, int32_t *requests);
+/* Resolve requests (the union over all ranks, same order on every rank; duplicates allowed). */
+int stcsp_session_resolve(stcsp_session_t *s, const int32_t *requests, int64_t n_requests);
+/* Group this wave's leaves by owner rank into `outbox` (device, capacity in records >= n_leaves);
+ * counts_per_rank[world_size] (host) receives the record count for each rank; rank q's records
+ * start at record index sum(counts_per_rank[0..q)). */
+int stcsp_session_outbox(stcsp_session_t *s, int32_t *outbox, int64_t outbox_capacity, int64_t *counts_per_rank);
+/* Insert `n_records` routed leaf records (device memory) owned by this rank and end the wave.
+ * inbox == NULL: ingest this rank's own leaves (world_size == 1).  *frontier_next = local search
+ * nodes waiting for the next wave. */
+int stcsp_session_ingest(stcsp_session_t *s, const int32_t *inbox, int64_t n_records, int64_t *frontier_next);
+/* Local part of the automaton: the states this rank owns (rows in local-index order, global id =
+ * local_index * world_size + rank) and the edges INTO them with global src/dst ids, untrimmed and
+ * unsorted.  Release with stcsp_automaton_free. */
+int stcsp_session_finish(stcsp_session_t *s, stcsp_automaton_t *part);
+
+/* Merge the per-rank parts (parts[r] = part of rank r; arrays may live in caller memory) into one
+ * automaton with dense state ids (ascending global id, root = 0) and edges grouped by source;
+ * statistics are summed, times are the maximum over parts.  Does not trim. */
+int stcsp_automaton_assemble(const stcsp_automaton_t *parts, int32_t n_parts, stcsp_automaton_t *out);
 
 /* Fail rule as a greatest fixpoint (reference src/solveralgorithm.cpp:904-910): marks states without
- * surviving out-edges, removes edges into them, repeats.  In place; edges stay sorted. */
+ * surviving out-edges, removes edges into them, repeats.  In place; edges stay grouped by source. */
 int stcsp_automaton_trim(stcsp_automaton_t *a);
 
 #ifdef __cplusplus

@@ -40,7 +40,8 @@ class Options(C.Structure):
         ("device", C.c_int32), ("use_current_device", C.c_int32), ("time_limit_s", C.c_int32),
         ("verbosity", C.c_int32), ("enum_limit_now", C.c_int64), ("enum_limit_ahead", C.c_int64),
         ("max_frontier_nodes", C.c_int64), ("max_states", C.c_int64), ("max_edges", C.c_int64),
-        ("keep_failed_edges", C.c_int32), ("profile_kernels", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("reserved0", C.c_int32), ("profile_kernels", C.c_int32), ("no_trim", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -53,8 +54,10 @@ class AutomatonC(C.Structure):
         ("state_failed", C.POINTER(C.c_uint8)), ("n_edges", C.c_int64),
         ("edge_src", C.POINTER(C.c_int32)), ("edge_dst", C.POINTER(C.c_int32)), ("edge_label", C.POINTER(C.c_int32)),
         ("n_search_nodes", C.c_int64), ("n_fails", C.c_int64), ("n_leaves", C.c_int64), ("n_dominance", C.c_int64),
-        ("n_waves", C.c_int64), ("n_tuples", C.c_int64), ("n_kernel_launches", C.c_int64),
+        ("n_waves", C.c_int64), ("n_tuples", C.c_int64), ("n_revisions", C.c_int64),
+        ("n_kernel_launches", C.c_int64),
         ("solve_ms", C.c_double), ("wall_ms", C.c_double), ("expand_ms", C.c_double),
+        ("n_expand_launches", C.c_int64),
         ("algorithmic_bytes", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("impl", C.c_void_p),
     ]
@@ -186,7 +189,8 @@ class Automaton:
         a = self.c
         return {k: getattr(a, k) for k in (
             "n_states", "n_edges", "n_constraint_sets", "n_search_nodes", "n_fails", "n_leaves", "n_dominance",
-            "n_waves", "n_tuples", "n_kernel_launches", "solve_ms", "wall_ms", "expand_ms", "algorithmic_bytes",
+            "n_waves", "n_tuples", "n_revisions", "n_kernel_launches", "n_expand_launches", "solve_ms", "wall_ms",
+            "expand_ms", "algorithmic_bytes",
             "h2d_bytes", "d2h_bytes")}
 
     def __del__(self):

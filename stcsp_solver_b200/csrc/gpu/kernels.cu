@@ -291,14 +291,14 @@ __device__ bool revise_until(NodeCtx &c, const DevCon &con) {
     return true;
 }
 
-__global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const DevModel M, const Pools P) {
+__global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const DevModel M, const ExpandArgs P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpMem wm = carve(smem + (size_t)warp * warp_bytes(M), M);
-    const long long n_in = (long long)P.counters[C_IN];
+    const long long n_in = P.n_in;
     const long long total_warps = (long long)gridDim.x * kExpandWarps;
     const int V = M.V, k = M.k, NW = M.node_words;
-    unsigned long long st_nodes = 0, st_fails = 0, st_tuples = 0;
+    unsigned long long st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0;
 
     for (long long ni = (long long)blockIdx.x * kExpandWarps + warp; ni < n_in; ni += total_warps) {
         const int32_t *src = P.in_nodes + ni * NW;
@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const DevMode
             __syncwarp();
             if (lane == 0) wm.dirty[q >> 5] &= ~(1u << (q & 31));   // revisions are idempotent
             __syncwarp();
+            st_rev++;
             fail = !ok;
         }
         st_nodes++;
@@ -401,20 +402,22 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const DevMode
         atomicAdd(&P.counters[C_NODES], st_nodes);
         if (st_fails) atomicAdd(&P.counters[C_FAILS], st_fails);
         if (st_tuples) atomicAdd(&P.counters[C_TUPLES], st_tuples);
+        if (st_rev) atomicAdd(&P.counters[C_REVISIONS], st_rev);
     }
 }
 
-// ---- ingest ----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+// ---- hashing ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
     return h;
 }
 
-__device__ __forceinline__ int key_word(const DevModel &M, const int32_t *rec, int ncid, int nexp, int j) {
-    if (j == 0) return ncid;
-    if (j <= M.n_sig) return rec[4 + M.sig_vars[j - 1]];
-    return (nexp >> (j - 1 - M.n_sig)) & 1;
+// Order-independent over the words, so a warp can hash a key cooperatively with an xor-reduction.
+__host__ __device__ __forceinline__ uint32_t key_word_hash(int32_t word, int j) {
+    return mix32((uint32_t)word * 0x9e3779b1u + (uint32_t)j * 0x7f4a7c15u + 0x165667b1u);
 }
+
+__host__ __device__ inline uint32_t owner_hash(uint32_t h) { return mix32(h ^ 0x5bd1e995u); }
 
 __host__ __device__ inline uint32_t cap_hash(int cid, const int32_t *vals, int n) {
     uint32_t h = 0x9e3779b9u * (uint32_t)(cid + 1);
@@ -425,23 +428,32 @@ __host__ __device__ inline uint32_t cap_hash(int cid, const int32_t *vals, int n
     return h;
 }
 
-__global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const Pools P, const int32_t *list, long long count) {
+// word j of the state key of the successor described by a routed record
+__device__ __forceinline__ int key_word(const DevModel &M, const int32_t *rec, int ncid, int nexp, int j) {
+    if (j == 0) return ncid;
+    if (j <= M.n_sig) return rec[4 + M.sig_vars[j - 1]];
+    return (nexp >> (j - 1 - M.n_sig)) & 1;
+}
+
+// ---- route: successor constraint set, until flags and state-key hash of every leaf --------------------
+// (reference src/solveralgorithm.cpp:755-837: constraint rewriting -> constraintID, signature)
+__global__ void __launch_bounds__(256) route_kernel(const DevModel M, const RouteArgs P) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long n = list ? count : (long long)P.counters[C_LEAVES];
-    const int V = M.V, k = M.k, KW = M.key_words, NW = M.node_words;
+    const long long n = P.list ? P.count : (long long)P.counters[C_LEAVES];
+    const int KW = M.key_words;
 
     for (long long it = warp_id; it < n; it += total_warps) {
-        const long long li = list ? (long long)list[it] : it;
-        const int32_t *rec = P.leaves + li * M.rec_words;
-        const int src = rec[0], cid = rec[1], exp = rec[2];
+        const long long li = P.list ? (long long)P.list[it] : it;
+        int32_t *rec = P.leaves + li * M.rec_words;
+        const int cid = rec[1], exp = rec[2];
         const DevSet S = M.sets[cid];
         int ncid = S.static_next;
-        if (S.n_cap > 0) {
-            // successor constraint set depends on the values captured by `first`
+        if (ncid < 0) {
+            // the successor set depends on the values captured by `first`: host-filled map
             int found = -1;
-            if (lane == 0) {
+            if (lane == 0 && P.capmap_mask >= 0) {
                 int32_t vals[Limits::kMaxCap];
                 for (int i = 0; i < S.n_cap; i++) vals[i] = rec[4 + M.aux[S.cap_off + i]];
                 uint32_t h = cap_hash(cid, vals, S.n_cap) & (uint32_t)P.capmap_mask;
@@ -471,13 +483,70 @@ __global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const Poo
             if (rec[4 + M.aux[NS.until_off + u]] == 1) nexp |= 1 << u;
 
         uint32_t h = 0;
-        for (int j = lane; j < KW; j += 32) h ^= mix32((uint32_t)key_word(M, rec, ncid, nexp, j) * 0x9e3779b1u + (uint32_t)j);
+        for (int j = lane; j < KW; j += 32) h ^= key_word_hash(key_word(M, rec, ncid, nexp, j), j);
 #pragma unroll
         for (int s = 16; s >= 1; s >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, s);
         h = mix32(h);
+        __syncwarp();
+        if (lane == 0) {
+            rec[1] = ncid;
+            rec[2] = nexp;
+            rec[3] = (int32_t)h;
+            const int owner = M.world > 1 ? (int)(owner_hash(h) % (uint32_t)M.world) : 0;
+            atomicAdd(&P.counters[C_OWNER0 + owner], 1ull);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- scatter: group routed leaves by owner rank (multi-GPU only) ---------------------------------------
+__global__ void __launch_bounds__(256) scatter_kernel(const DevModel M, const int32_t *leaves, long long n,
+                                                      const long long *offsets, unsigned long long *fill,
+                                                      int32_t *outbox) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int RW = M.rec_words;
+    for (long long li = warp_id; li < n; li += total_warps) {
+        const int32_t *rec = leaves + li * RW;
+        const int owner = (int)(owner_hash((uint32_t)rec[3]) % (uint32_t)M.world);
+        unsigned long long pos = 0;
+        if (lane == 0) pos = atomicAdd(&fill[owner], 1ull);
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        int32_t *dst = outbox + (offsets[owner] + (long long)pos) * RW;
+        for (int w = lane; w < RW; w += 32) dst[w] = rec[w];
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const int32_t *src, const int32_t *list, long long count,
+                                                     int rec_words, int32_t *dst) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp_id; i < count; i += total_warps) {
+        const int32_t *rec = src + (long long)list[i] * rec_words;
+        for (int w = lane; w < rec_words; w += 32) dst[i * rec_words + w] = rec[w];
+    }
+}
+
+// ---- ingest: state dedup, edge append, first search node of every new state ------------------------------
+// One warp per routed leaf record (reference vertexTableGetVertex/AddVertex src/graph.cpp:108-123,
+// edgeNew src/graph.cpp:78-89, variableAdvanceOneTimeStep src/variable.cpp:94-108).
+__global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const IngestArgs P) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int V = M.V, k = M.k, KW = M.key_words, NW = M.node_words;
+    unsigned long long st_dom = 0;
+
+    for (long long it = warp_id; it < P.count; it += total_warps) {
+        const int32_t *rec = P.records + it * M.rec_words;
+        const int src = rec[0], ncid = rec[1], nexp = rec[2];
+        const uint32_t h = (uint32_t)rec[3];
+        const DevSet NS = M.sets[ncid];
 
         long long slot = (long long)h & P.table_mask;
-        int dst = -1;
+        int dst = -1;                                     // local index of the destination state
         bool is_new = false, abort_leaf = false;
         for (;;) {
             int v = 0;
@@ -510,11 +579,13 @@ __global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const Poo
             if (v == -3) { abort_leaf = true; break; }
             __threadfence();
             bool eq = true;
-            for (int j = lane; j < KW; j += 32) eq &= __ldcg(&P.state_key[(long long)v * KW + j]) == key_word(M, rec, ncid, nexp, j);
+            for (int j = lane; j < KW; j += 32)
+                eq &= __ldcg(&P.state_key[(long long)v * KW + j]) == key_word(M, rec, ncid, nexp, j);
             if (__all_sync(0xffffffffu, eq)) { dst = v; break; }
             slot = (slot + 1) & P.table_mask;
         }
         if (abort_leaf) continue;
+        const int dst_global = dst * M.world + M.rank;
 
         if (is_new) {
             // first search node of the new state: next-linked variables take the values just chosen,
@@ -526,23 +597,23 @@ __global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const Poo
                 if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
             } else {
                 int32_t *node = P.out_nodes + o * NW;
-                if (lane == 0) { node[0] = dst; node[1] = ncid; node[2] = nexp; node[3] = -1; }
+                if (lane == 0) { node[0] = dst_global; node[1] = ncid; node[2] = nexp; node[3] = -1; }
                 u64 *nd = reinterpret_cast<u64 *>(node + 4);
                 for (int i = lane; i < V * k; i += 32) {
                     const int v = i / k, p = i % k;
                     u64 m = width_mask(M.width[v]);
-                    if (p == 0) {
+                    if (p == 0 && k > 1) {                // with k == 1 the reference never links time points
                         for (int t = 0; t < NS.n_next; t++) {
                             if (M.aux[NS.next_off + 2 * t + 1] != v) continue;
-                            const int b = rec[4 + M.aux[NS.next_off + 2 * t]] - M.lb[v];
+                            const long long b = (long long)rec[4 + M.aux[NS.next_off + 2 * t]] - (long long)M.lb[v];
                             m &= (b >= 0 && b < 64) ? (1ull << b) : 0ull;
                         }
                     }
                     nd[i] = m;
                 }
             }
-        } else if (lane == 0) {
-            atomicAdd(&P.counters[C_DOMINANCE], 1ull);
+        } else {
+            st_dom++;
         }
         unsigned long long e = 0;
         if (lane == 0) e = atomicAdd(&P.counters[C_EDGES], 1ull);
@@ -551,8 +622,23 @@ __global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const Poo
             if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 8ull);
             continue;
         }
-        if (lane == 0) { P.edge_src[e] = src; P.edge_dst[e] = dst; }
+        if (lane == 0) { P.edge_src[e] = src; P.edge_dst[e] = dst_global; }
         for (int v = lane; v < V; v += 32) P.edge_label[e * V + v] = rec[4 + v];
+    }
+    if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+}
+
+// Re-insert every state into a fresh table after growth (one thread per state).
+__global__ void __launch_bounds__(256) rehash_kernel(const DevModel M, int32_t *table, long long mask,
+                                                     const int32_t *state_key, long long n_states) {
+    const int KW = M.key_words;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_states;
+         s += (long long)gridDim.x * blockDim.x) {
+        uint32_t h = 0;
+        for (int j = 0; j < KW; j++) h ^= key_word_hash(state_key[s * KW + j], j);
+        h = mix32(h);
+        long long slot = (long long)h & mask;
+        while (atomicCAS(&table[slot], -1, (int)s) != -1) slot = (slot + 1) & mask;
     }
 }
 
@@ -565,20 +651,65 @@ __global__ void fill_kernel(int32_t *ptr, long long n, int32_t value) {
 
 uint32_t capmap_hash(int cid, const int32_t *vals, int n) { return cap_hash(cid, vals, n); }
 
+uint32_t state_key_hash(const int32_t *key, int key_words) {
+    uint32_t h = 0;
+    for (int j = 0; j < key_words; j++) h ^= key_word_hash(key[j], j);
+    return mix32(h);
+}
+
+int32_t owner_of_hash(uint32_t h, int32_t world) { return world > 1 ? (int32_t)(owner_hash(h) % (uint32_t)world) : 0; }
+
 size_t expand_smem_bytes(const DevModel &m) { return warp_bytes(m) * kExpandWarps; }
 
-void launch_expand(const DevModel &m, const Pools &p, int grid, cudaStream_t stream) {
-    const size_t smem = expand_smem_bytes(m);
+static void configure_expand(size_t smem) {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    expand_kernel<<<grid, kExpandWarps * 32, smem, stream>>>(m, p);
 }
 
-void launch_ingest(const DevModel &m, const Pools &p, const int32_t *list, long long count, int grid, cudaStream_t stream) {
-    ingest_kernel<<<grid, 256, 0, stream>>>(m, p, list, count);
+int expand_max_grid(const DevModel &m, int sm_count) {
+    const size_t smem = expand_smem_bytes(m);
+    configure_expand(smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_kernel, kExpandWarps * 32, smem) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 1;
+    return per_sm * sm_count;
+}
+
+void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, cudaStream_t stream) {
+    const size_t smem = expand_smem_bytes(m);
+    configure_expand(smem);
+    expand_kernel<<<grid, kExpandWarps * 32, smem, stream>>>(m, a);
+}
+
+void launch_route(const DevModel &m, const RouteArgs &a, int grid, cudaStream_t stream) {
+    route_kernel<<<grid, 256, 0, stream>>>(m, a);
+}
+
+void launch_ingest(const DevModel &m, const IngestArgs &a, int grid, cudaStream_t stream) {
+    if (a.count <= 0) return;
+    ingest_kernel<<<grid, 256, 0, stream>>>(m, a);
+}
+
+void launch_scatter(const DevModel &m, const int32_t *leaves, long long n_leaves, const long long *dev_offsets,
+                    unsigned long long *dev_fill, int32_t *outbox, int grid, cudaStream_t stream) {
+    if (n_leaves <= 0) return;
+    scatter_kernel<<<grid, 256, 0, stream>>>(m, leaves, n_leaves, dev_offsets, dev_fill, outbox);
+}
+
+void launch_gather(const int32_t *src, const int32_t *list, long long count, int rec_words, int32_t *dst, int grid,
+                   cudaStream_t stream) {
+    if (count <= 0) return;
+    gather_kernel<<<grid, 256, 0, stream>>>(src, list, count, rec_words, dst);
+}
+
+void launch_rehash(const DevModel &m, int32_t *table, long long table_mask, const int32_t *state_key,
+                   long long n_states, int grid, cudaStream_t stream) {
+    if (n_states <= 0) return;
+    rehash_kernel<<<grid, 256, 0, stream>>>(m, table, table_mask, state_key, n_states);
 }
 
 void launch_fill(int32_t *ptr, long long n, int32_t value, cudaStream_t stream) {

@@ -6,7 +6,7 @@
 //     [4 ...] V*k uint64 domain bitsets, index (var*k + offset); bit b of variable v = value lb[v] + b
 // LEAF RECORD (a complete consistent assignment of one time point, src/solveralgorithm.cpp:739-749):
 //     [0] source state id   [1] constraint-set id   [2] until-expired bits   [3] 0   [4 ...] V values
-//   after route_kernel: [1] SUCCESSOR constraint-set id (-1: host must resolve)  [2] successor until bits
+//   after route_kernel: [1] SUCCESSOR constraint-set id   [2] successor until bits
 //                       [3] hash of the successor's state key (owner rank and table slot derive from it)
 // STATE IDS are global: local index * world + rank.
 // STATE KEY (reference Signature, src/graph.h:14-21):
@@ -20,21 +20,23 @@
 namespace stcsp {
 
 enum Counter : int {
-    C_IN = 0,          // nodes in the input frontier of the current wave
+    // allocation cursors, live for the whole search
+    C_STATES = 0,      // states allocated on this rank
+    C_EDGES,           // edges appended on this rank
+    // per wave (zeroed by the host before each expand)
     C_OUT,             // nodes written to the output frontier
-    C_LEAVES,          // leaf records written this wave
-    C_STATES,          // states allocated (all waves)
-    C_EDGES,           // edges appended (all waves)
+    C_LEAVES,          // leaf records written
     C_UNRESOLVED,      // leaves whose successor constraint set the host must compute
     C_OVERFLOW,        // bit flags: 1 frontier, 2 leaves, 4 states, 8 edges, 16 unresolved list
     C_NODES,           // statistics: search nodes propagated
     C_FAILS,
     C_TUPLES,
+    C_REVISIONS,
     C_DOMINANCE,
-    C_LEAVES_TOTAL,
-    C_OWNER0,          // C_OWNER0 + r: routed leaves owned by rank r (this wave)
+    C_OWNER0,          // C_OWNER0 + r: routed leaves owned by rank r
     C_COUNT = C_OWNER0 + 16
 };
+constexpr int kMaxWorld = 16;
 
 struct DevModel {
     int32_t V, k;
@@ -60,45 +62,61 @@ struct CapEntry {          // (constraint set, captured values) -> successor set
     int32_t vals[Limits::kMaxCap];
 };
 
-struct Pools {
-    // frontier / leaves
+struct ExpandArgs {
     const int32_t *in_nodes;
+    long long n_in;
     int32_t *out_nodes;
     long long out_cap;
     int32_t *leaves;
     long long leaf_cap;
-    // automaton
-    int32_t *table;         // open addressing: state id, -1 empty, -2 being written
+    unsigned long long *counters;
+};
+
+struct RouteArgs {
+    int32_t *leaves;
+    const int32_t *list;        // nullptr: leaves [0, C_LEAVES); else the leaves list[0 .. count)
+    long long count;
+    const CapEntry *capmap;
+    int32_t capmap_mask;
+    int32_t *unresolved;        // leaf indices that need the host
+    long long unresolved_cap;
+    unsigned long long *counters;
+};
+
+struct IngestArgs {
+    const int32_t *records;     // routed leaf records
+    long long count;
+    int32_t *table;             // open addressing: local state index, -1 empty, -2 being written
     long long table_mask;
-    int32_t *state_key;     // [state * key_words]
+    int32_t *state_key;         // [local state * key_words]
     long long state_cap;
     int32_t *edge_src, *edge_dst, *edge_label;
     long long edge_cap;
-    // constraint-set transitions
-    const CapEntry *capmap;
-    int32_t capmap_mask;
-    int32_t *unresolved;    // leaf indices
-    long long unresolved_cap;
+    int32_t *out_nodes;
+    long long out_cap;
     unsigned long long *counters;
 };
 
 constexpr int kExpandWarps = 8;      // warps per CTA of the expand kernel
 
 size_t expand_smem_bytes(const DevModel &m);
-void launch_expand(const DevModel &m, const Pools &p, int grid, cudaStream_t stream);
-// leaves [first, first + count) or, when list != nullptr, the leaves list[0 .. count)
-void launch_route(const DevModel &m, const Pools &p, const int32_t *list, long long count, int grid,
-                  cudaStream_t stream);
-// records [0, count) of `records` (count < 0: the local leaf buffer, length read from the device counter)
-void launch_ingest(const DevModel &m, const Pools &p, const int32_t *records, long long count, int grid,
-                   cudaStream_t stream);
-// group the routed local leaves by owner rank into `outbox` (offsets = exclusive prefix of owner_counts)
-void launch_scatter(const DevModel &m, const Pools &p, long long n_leaves, const long long *dev_offsets,
+int expand_max_grid(const DevModel &m, int sm_count);      // resident CTAs of the expand kernel on this device
+void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, cudaStream_t stream);
+void launch_route(const DevModel &m, const RouteArgs &a, int grid, cudaStream_t stream);
+void launch_ingest(const DevModel &m, const IngestArgs &a, int grid, cudaStream_t stream);
+// group the routed local leaves by owner rank into `outbox` (dev_offsets = exclusive prefix of the owner counts)
+void launch_scatter(const DevModel &m, const int32_t *leaves, long long n_leaves, const long long *dev_offsets,
                     unsigned long long *dev_fill, int32_t *outbox, int grid, cudaStream_t stream);
-void launch_wave_reset(const Pools &p, cudaStream_t stream);
+// dst[i] = src record list[i]
+void launch_gather(const int32_t *src, const int32_t *list, long long count, int rec_words, int32_t *dst, int grid,
+                   cudaStream_t stream);
+// re-insert states [0, n_states) into a fresh (all -1) table
+void launch_rehash(const DevModel &m, int32_t *table, long long table_mask, const int32_t *state_key,
+                   long long n_states, int grid, cudaStream_t stream);
+void launch_fill(int32_t *ptr, long long n, int32_t value, cudaStream_t stream);
+
 uint32_t capmap_hash(int cid, const int32_t *vals, int n);
 uint32_t state_key_hash(const int32_t *key, int key_words);
-int32_t owner_of_hash(uint32_t h, int32_t world, int32_t sig_len);
-void launch_fill(int32_t *ptr, long long n, int32_t value, cudaStream_t stream);
+int32_t owner_of_hash(uint32_t h, int32_t world);
 
 }  // namespace stcsp

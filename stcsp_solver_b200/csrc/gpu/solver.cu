@@ -1,0 +1,844 @@
+// Host driver of the GPU search: owns the device pools, runs the frontier waves, and implements the
+// C ABI of include/stcsp_b200.h (stcsp_gpu_solve, the step-wise session, assemble, trim).
+//
+// Replaces the recursion of solverSolve / solverSolveRe (reference src/solveralgorithm.cpp:733-1005):
+// instead of a depth-first walk with an undo trail, every search node is a self-contained domain
+// block in HBM and one WAVE propagates and branches all of them at once (expand_kernel), routes the
+// complete assignments found (route_kernel) and merges them into the automaton (ingest_kernel).
+// There is no CPU solver in this file: without a CUDA device every entry point fails with
+// STCSP_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../host/error.h"
+#include "kernels.cuh"
+#include "stcsp_b200.h"
+
+namespace stcsp {
+namespace {
+
+struct Failure : std::runtime_error {
+    int code;
+    Failure(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            throw Failure(STCSP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t cap = 0;     // elements
+    DBuf() = default;
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    ~DBuf() { if (p) cudaFree(p); }
+    // at least `need` elements; the first `keep` elements survive a reallocation
+    bool reserve(size_t need, size_t keep, cudaStream_t st) {
+        if (need <= cap) return false;
+        size_t ncap = std::max(need, cap + cap / 2);
+        T *np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+        if (e != cudaSuccess)
+            throw Failure(STCSP_ERR_CAPACITY, "device allocation of " + std::to_string(ncap * sizeof(T)) +
+                                                  " bytes failed: " + cudaGetErrorString(e));
+        if (keep) CK(cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        if (p) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(p);
+        }
+        p = np;
+        cap = ncap;
+        return true;
+    }
+};
+
+struct AutoStore {      // backing storage of a library-owned stcsp_automaton_t
+    std::vector<int32_t> sig_vars, state_sig, state_cset, edge_src, edge_dst, edge_label;
+    std::vector<uint8_t> state_failed;
+};
+
+void bind_store(stcsp_automaton_t *a, AutoStore *st) {
+    a->impl = st;
+    a->sig_vars = st->sig_vars.data();
+    a->state_sig = st->state_sig.data();
+    a->state_cset = st->state_cset.data();
+    a->state_failed = st->state_failed.data();
+    a->edge_src = st->edge_src.data();
+    a->edge_dst = st->edge_dst.data();
+    a->edge_label = st->edge_label.data();
+}
+
+}  // namespace
+}  // namespace stcsp
+
+using namespace stcsp;
+
+struct stcsp_session {
+    SetTable sets;
+    stcsp_options_t opt{};
+    int rank = 0, world = 1, device = 0, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    DevModel dm{};
+    // model pools
+    DBuf<int32_t> d_lb, d_width, d_sigvars, d_scope, d_aux, d_arr_off, d_arr_val;
+    DBuf<DevSet> d_sets;
+    DBuf<DevCon> d_cons;
+    DBuf<DevProp> d_props;
+    DBuf<Instr> d_code;
+    DBuf<uint32_t> d_wake;
+    // search pools
+    DBuf<int32_t> frontier[2];
+    int cur = 0;
+    DBuf<int32_t> leaves, unresolved, gathered, table, state_key, edge_src, edge_dst, edge_label;
+    DBuf<CapEntry> d_capmap;
+    DBuf<unsigned long long> counters;
+    DBuf<long long> d_offsets;
+    unsigned long long *h_counters = nullptr;       // pinned
+    long long table_size = 0;
+    long long n_in = 0, n_out = 0, n_leaves = 0, n_unres = 0, n_states = 0, n_edges = 0;
+    int expand_grid_max = 148;
+    // constraint-set transitions resolved so far
+    std::vector<CapEntry> capmap;
+    long long capmap_used = 0;
+    std::map<std::vector<int32_t>, int32_t> cap_lookup;
+    std::vector<int32_t> pending;                   // flat requests [cid, values[V]]
+    // statistics
+    long long t_nodes = 0, t_fails = 0, t_tuples = 0, t_revisions = 0, t_leaves = 0, t_dominance = 0, t_waves = 0,
+              t_launches = 0, t_expand_launches = 0, h2d = 0, d2h = 0;
+    double expand_ms = 0, t_create = 0;
+    bool timing_open = false;
+
+    ~stcsp_session() {
+        if (h_counters) cudaFreeHost(h_counters);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (evk0) cudaEventDestroy(evk0);
+        if (evk1) cudaEventDestroy(evk1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    template <class T>
+    void upload(DBuf<T> &b, const std::vector<T> &v) {
+        b.reserve(std::max<size_t>(v.size(), 1), 0, stream);
+        if (!v.empty()) {
+            CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+            h2d += (long long)(v.size() * sizeof(T));
+        }
+    }
+
+    void upload_model() {
+        upload(d_lb, sets.lb());
+        upload(d_width, sets.width());
+        upload(d_sigvars, sets.sig_vars());
+        upload(d_sets, sets.dev_sets);
+        upload(d_cons, sets.dev_cons);
+        upload(d_props, sets.dev_props);
+        upload(d_scope, sets.dev_scope);
+        upload(d_code, sets.dev_code);
+        upload(d_wake, sets.dev_wake);
+        upload(d_aux, sets.dev_aux);
+        upload(d_arr_off, sets.arr_off);
+        upload(d_arr_val, sets.arr_val);
+        CK(cudaStreamSynchronize(stream));      // the host vectors may be reallocated by the next set
+        dm.V = sets.n_vars();
+        dm.k = sets.k();
+        dm.world = world;
+        dm.rank = rank;
+        dm.n_sig = (int32_t)sets.sig_vars().size();
+        dm.sig_len = dm.n_sig + sets.n_until();
+        dm.node_words = 4 + 2 * dm.V * dm.k;
+        dm.rec_words = 4 + dm.V;
+        dm.key_words = 1 + dm.sig_len;
+        dm.max_scope = sets.max_scope();
+        dm.max_stack = sets.max_stack();
+        dm.max_words = (sets.max_props() + 31) / 32;
+        dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : (1ll << 12);
+        dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : (1ll << 9);
+        dm.lb = d_lb.p;
+        dm.width = d_width.p;
+        dm.sig_vars = d_sigvars.p;
+        dm.sets = d_sets.p;
+        dm.cons = d_cons.p;
+        dm.props = d_props.p;
+        dm.scope = d_scope.p;
+        dm.code = d_code.p;
+        dm.wake = d_wake.p;
+        dm.aux = d_aux.p;
+        dm.arr_off = d_arr_off.p;
+        dm.arr_val = d_arr_val.p;
+        if (expand_smem_bytes(dm) > 200 * 1024)
+            throw Failure(STCSP_ERR_UNSUPPORTED, "model needs more shared memory per CTA than an SM has");
+        expand_grid_max = expand_max_grid(dm, sm_count);
+        sets.clear_dirty();
+    }
+
+    void zero_wave_counters() {
+        CK(cudaMemsetAsync(counters.p + C_OUT, 0, (C_COUNT - C_OUT) * sizeof(unsigned long long), stream));
+    }
+    void read_counters() {
+        CK(cudaMemcpyAsync(h_counters, counters.p, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        d2h += C_COUNT * 8;
+    }
+
+    void ensure_table(long long states_needed) {
+        long long want = table_size ? table_size : (1ll << 16);
+        while (want < 2 * states_needed) want <<= 1;
+        if (want == table_size) return;
+        // a fresh table, every known state re-inserted
+        DBuf<int32_t> fresh;
+        fresh.reserve((size_t)want, 0, stream);
+        launch_fill(fresh.p, want, -1, stream);
+        // (the root's key starts with -1 unless its signature is empty, so it can sit in the table unreachable)
+        if (n_states > 0) {
+            launch_rehash(dm, fresh.p, want - 1, state_key.p, n_states, sm_count * 4, stream);
+            t_launches++;
+        }
+        CK(cudaStreamSynchronize(stream));
+        std::swap(table.p, fresh.p);
+        std::swap(table.cap, fresh.cap);
+        table_size = want;
+    }
+    void init(const stcsp_problem_t *problem, const stcsp_options_t *options, int r, int w) {
+        t_create = now_s();
+        if (options) opt = *options;
+        rank = r;
+        world = w;
+        if (w < 1 || w > kMaxWorld || r < 0 || r >= w) throw Failure(STCSP_ERR_INVALID, "bad rank / world size");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Failure(STCSP_ERR_CUDA, std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                                              "); this library has no CPU fallback");
+        if (!opt.use_current_device) {
+            device = opt.device >= 0 ? opt.device : 0;
+            if (device >= ndev) throw Failure(STCSP_ERR_CUDA, "CUDA device ordinal out of range");
+            CK(cudaSetDevice(device));
+        } else {
+            CK(cudaGetDevice(&device));
+        }
+        CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        CK(cudaEventCreate(&evk0));
+        CK(cudaEventCreate(&evk1));
+        try {
+            sets.init(*problem);
+        } catch (const std::invalid_argument &ex) {
+            throw Failure(STCSP_ERR_UNSUPPORTED, ex.what());
+        } catch (const std::runtime_error &ex) {
+            throw Failure(STCSP_ERR_INVALID, ex.what());
+        }
+        upload_model();
+        counters.reserve(C_COUNT, 0, stream);
+        CK(cudaMemsetAsync(counters.p, 0, C_COUNT * sizeof(unsigned long long), stream));
+        CK(cudaMallocHost(&h_counters, C_COUNT * sizeof(unsigned long long)));
+        d_offsets.reserve(2 * kMaxWorld, 0, stream);
+
+        const int NW = dm.node_words, KW = dm.key_words;
+        frontier[0].reserve((size_t)4096 * NW, 0, stream);
+        frontier[1].reserve((size_t)4096 * NW, 0, stream);
+        state_key.reserve((size_t)4096 * KW, 0, stream);
+        edge_src.reserve(8192, 0, stream);
+        edge_dst.reserve(8192, 0, stream);
+        edge_label.reserve((size_t)8192 * dm.V, 0, stream);
+        if (rank == 0) {
+            // root state (reference src/solveralgorithm.cpp:951-954) and its search node
+            std::vector<int32_t> key(KW, 0);
+            key[0] = dm.sig_len == 0 ? 0 : -1;
+            CK(cudaMemcpyAsync(state_key.p, key.data(), KW * 4, cudaMemcpyHostToDevice, stream));
+            std::vector<int32_t> node(NW, 0);
+            node[3] = -1;
+            for (int v = 0; v < dm.V; v++)
+                for (int o = 0; o < dm.k; o++) {
+                    const int w_ = sets.width()[v];
+                    const unsigned long long m = w_ >= 64 ? ~0ull : ((1ull << w_) - 1ull);
+                    memcpy(&node[4 + 2 * (v * dm.k + o)], &m, 8);
+                }
+            CK(cudaMemcpyAsync(frontier[0].p, node.data(), NW * 4, cudaMemcpyHostToDevice, stream));
+            const unsigned long long one = 1;
+            CK(cudaMemcpyAsync(counters.p + C_STATES, &one, 8, cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+            h2d += (KW + NW) * 4 + 8;
+            n_states = 1;
+            n_in = 1;
+        }
+        ensure_table(std::max<long long>(n_states, 1));
+    }
+
+    void begin_timing() {
+        if (!timing_open) {
+            CK(cudaEventRecord(ev0, stream));
+            timing_open = true;
+        }
+    }
+
+    void expand(int64_t *out_leaves, int64_t *out_pending) {
+        begin_timing();
+        pending.clear();
+        n_leaves = n_unres = 0;
+        n_out = 0;
+        zero_wave_counters();
+        if (n_in > 0) {
+            const int NW = dm.node_words, RW = dm.rec_words;
+            leaves.reserve((size_t)n_in * RW, 0, stream);
+            unresolved.reserve((size_t)n_in, 0, stream);
+            DBuf<int32_t> &out = frontier[cur ^ 1];
+            out.reserve((size_t)std::max<long long>(2 * n_in, 4096) * NW, 0, stream);
+            for (;;) {
+                ExpandArgs ea{};
+                ea.in_nodes = frontier[cur].p;
+                ea.n_in = n_in;
+                ea.out_nodes = out.p;
+                ea.out_cap = (long long)(out.cap / NW);
+                ea.leaves = leaves.p;
+                ea.leaf_cap = (long long)(leaves.cap / RW);
+                ea.counters = counters.p;
+                const int grid = (int)std::min<long long>((n_in + kExpandWarps - 1) / kExpandWarps, expand_grid_max);
+                if (opt.profile_kernels) CK(cudaEventRecord(evk0, stream));
+                launch_expand(dm, ea, grid, stream);
+                if (opt.profile_kernels) CK(cudaEventRecord(evk1, stream));
+                RouteArgs ra{};
+                ra.leaves = leaves.p;
+                ra.list = nullptr;
+                ra.capmap = d_capmap.p;
+                ra.capmap_mask = capmap.empty() ? -1 : (int32_t)capmap.size() - 1;
+                ra.unresolved = unresolved.p;
+                ra.unresolved_cap = (long long)unresolved.cap;
+                ra.counters = counters.p;
+                launch_route(dm, ra, (int)std::min<long long>((n_in + 7) / 8, sm_count * 8), stream);
+                CK(cudaGetLastError());
+                read_counters();
+                t_launches += 2;
+                t_expand_launches++;
+                if (opt.profile_kernels) {
+                    float ms = 0;
+                    CK(cudaEventElapsedTime(&ms, evk0, evk1));
+                    expand_ms += ms;
+                }
+                const unsigned long long ov = h_counters[C_OVERFLOW];
+                if (ov & 1ull) {        // frontier buffer too small: nothing but scratch was written, run the wave again
+                    out.reserve((size_t)std::max<unsigned long long>(h_counters[C_OUT] + h_counters[C_OUT] / 4,
+                                                                     2 * (out.cap / NW)) * NW, 0, stream);
+                    zero_wave_counters();
+                    continue;
+                }
+                if (ov) throw Failure(STCSP_ERR_CAPACITY, "internal: leaf buffers overflowed");
+                break;
+            }
+            n_out = (long long)h_counters[C_OUT];
+            n_leaves = (long long)h_counters[C_LEAVES];
+            n_unres = (long long)h_counters[C_UNRESOLVED];
+            t_nodes += (long long)h_counters[C_NODES];
+            t_fails += (long long)h_counters[C_FAILS];
+            t_tuples += (long long)h_counters[C_TUPLES];
+            t_revisions += (long long)h_counters[C_REVISIONS];
+            t_leaves += n_leaves;
+            t_waves++;
+            if (n_unres > 0) collect_pending();
+        }
+        if (out_leaves) *out_leaves = n_leaves;
+        if (out_pending) *out_pending = (int64_t)(pending.size() / (size_t)(1 + dm.V));
+    }
+
+    std::vector<int32_t> cap_key(int32_t cid, const int32_t *values) const {
+        const HostSet &hs = sets.host_set(cid);
+        std::vector<int32_t> key;
+        key.reserve(1 + hs.cap_vars.size());
+        key.push_back(cid);
+        for (int32_t v : hs.cap_vars) key.push_back(values[v]);
+        return key;
+    }
+
+    void collect_pending() {
+        const int RW = dm.rec_words, V = dm.V;
+        gathered.reserve((size_t)n_unres * RW, 0, stream);
+        launch_gather(leaves.p, unresolved.p, n_unres, RW, gathered.p, (int)std::min<long long>((n_unres + 7) / 8, sm_count * 8), stream);
+        t_launches++;
+        std::vector<int32_t> host((size_t)n_unres * RW);
+        CK(cudaMemcpyAsync(host.data(), gathered.p, host.size() * 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        d2h += (long long)host.size() * 4;
+        std::map<std::vector<int32_t>, int> seen;
+        for (long long i = 0; i < n_unres; i++) {
+            const int32_t *rec = host.data() + i * RW;
+            std::vector<int32_t> key = cap_key(rec[1], rec + 4);
+            if (cap_lookup.count(key) || !seen.emplace(key, 1).second) continue;
+            pending.push_back(rec[1]);
+            pending.insert(pending.end(), rec + 4, rec + 4 + V);
+        }
+    }
+
+    void capmap_insert(int32_t cid, const std::vector<int32_t> &key, int32_t next) {
+        if ((capmap_used + 1) * 2 > (long long)capmap.size()) {
+            std::vector<CapEntry> old;
+            old.swap(capmap);
+            CapEntry empty{};
+            empty.cid = -1;
+            capmap.assign(std::max<size_t>(64, old.size() * 2), empty);
+            capmap_used = 0;
+            for (const CapEntry &e : old)
+                if (e.cid != -1) place(e);
+        }
+        CapEntry e{};
+        e.cid = cid;
+        e.next = next;
+        for (size_t i = 1; i < key.size(); i++) e.vals[i - 1] = key[i];
+        place(e);
+    }
+    void place(const CapEntry &e) {
+        const int n = (int)sets.host_set(e.cid).cap_vars.size();
+        uint32_t h = capmap_hash(e.cid, e.vals, n) & (uint32_t)(capmap.size() - 1);
+        while (capmap[h].cid != -1) h = (h + 1) & (uint32_t)(capmap.size() - 1);
+        capmap[h] = e;
+        capmap_used++;
+    }
+
+    void resolve(const int32_t *requests, int64_t n_req) {
+        const int V = dm.V;
+        bool added = false;
+        for (int64_t i = 0; i < n_req; i++) {
+            const int32_t *rq = requests + i * (1 + V);
+            const int32_t cid = rq[0];
+            if (cid < 0 || cid >= sets.n_sets()) throw Failure(STCSP_ERR_INVALID, "resolve request names an unknown constraint set");
+            std::vector<int32_t> key = cap_key(cid, rq + 1);
+            if (cap_lookup.count(key)) continue;
+            int32_t next;
+            try {
+                next = sets.successor(cid, rq + 1);
+            } catch (const std::invalid_argument &ex) {
+                throw Failure(STCSP_ERR_UNSUPPORTED, ex.what());
+            }
+            cap_lookup[key] = next;
+            capmap_insert(cid, key, next);
+            added = true;
+        }
+        if (sets.dirty()) upload_model();
+        if (added) {
+            d_capmap.reserve(capmap.size(), 0, stream);
+            CK(cudaMemcpyAsync(d_capmap.p, capmap.data(), capmap.size() * sizeof(CapEntry), cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+            h2d += (long long)(capmap.size() * sizeof(CapEntry));
+        }
+        if (n_unres > 0) {
+            CK(cudaMemsetAsync(counters.p + C_UNRESOLVED, 0, sizeof(unsigned long long), stream));
+            RouteArgs ra{};
+            ra.leaves = leaves.p;
+            ra.list = unresolved.p;
+            ra.count = n_unres;
+            ra.capmap = d_capmap.p;
+            ra.capmap_mask = capmap.empty() ? -1 : (int32_t)capmap.size() - 1;
+            ra.unresolved = gathered.p;         // scratch: nothing may remain unresolved
+            ra.unresolved_cap = (long long)gathered.cap;
+            ra.counters = counters.p;
+            launch_route(dm, ra, (int)std::min<long long>((n_unres + 7) / 8, sm_count * 8), stream);
+            CK(cudaGetLastError());
+            read_counters();
+            t_launches++;
+            if (h_counters[C_UNRESOLVED] != 0)
+                throw Failure(STCSP_ERR_INVALID, "resolve: the request list did not cover every pending leaf of this rank");
+            n_unres = 0;
+        }
+        pending.clear();
+    }
+
+    void outbox(int32_t *outbox_dev, int64_t capacity, int64_t *counts) {
+        if (n_unres > 0) throw Failure(STCSP_ERR_INVALID, "outbox called with unresolved leaves pending");
+        long long off[2 * kMaxWorld] = {0};
+        long long total = 0;
+        for (int q = 0; q < world; q++) {
+            counts[q] = (int64_t)h_counters[C_OWNER0 + q];
+            off[q] = total;
+            total += counts[q];
+        }
+        if (total != n_leaves) throw Failure(STCSP_ERR_INVALID, "internal: owner counts do not add up to the leaf count");
+        if (total > capacity) throw Failure(STCSP_ERR_CAPACITY, "outbox too small");
+        if (total == 0) return;
+        CK(cudaMemcpyAsync(d_offsets.p, off, sizeof off, cudaMemcpyHostToDevice, stream));   // [world..2*world) stay 0: fill
+        launch_scatter(dm, leaves.p, n_leaves, d_offsets.p, reinterpret_cast<unsigned long long *>(d_offsets.p + kMaxWorld),
+                       outbox_dev, (int)std::min<long long>((n_leaves + 7) / 8, sm_count * 8), stream);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));
+        t_launches++;
+    }
+
+    void ingest(const int32_t *inbox, int64_t n, int64_t *frontier_next) {
+        if (n_unres > 0) throw Failure(STCSP_ERR_INVALID, "ingest called with unresolved leaves pending");
+        const int NW = dm.node_words, KW = dm.key_words, V = dm.V;
+        if (!inbox) n = n_leaves;
+        const int32_t *records = inbox ? inbox : leaves.p;
+        DBuf<int32_t> &out = frontier[cur ^ 1];
+        if (n > 0) {
+            out.reserve((size_t)(n_out + n) * NW, (size_t)n_out * NW, stream);
+            state_key.reserve((size_t)(n_states + n) * KW, (size_t)n_states * KW, stream);
+            edge_src.reserve((size_t)(n_edges + n), (size_t)n_edges, stream);
+            edge_dst.reserve((size_t)(n_edges + n), (size_t)n_edges, stream);
+            edge_label.reserve((size_t)(n_edges + n) * V, (size_t)n_edges * V, stream);
+            ensure_table(n_states + n);
+            IngestArgs ia{};
+            ia.records = records;
+            ia.count = n;
+            ia.table = table.p;
+            ia.table_mask = table_size - 1;
+            ia.state_key = state_key.p;
+            ia.state_cap = (long long)(state_key.cap / KW);
+            ia.edge_src = edge_src.p;
+            ia.edge_dst = edge_dst.p;
+            ia.edge_label = edge_label.p;
+            ia.edge_cap = (long long)std::min(edge_src.cap, edge_label.cap / (size_t)V);
+            ia.out_nodes = out.p;
+            ia.out_cap = (long long)(out.cap / NW);
+            ia.counters = counters.p;
+            launch_ingest(dm, ia, (int)std::min<long long>((n + 7) / 8, sm_count * 8), stream);
+            CK(cudaGetLastError());
+            read_counters();
+            t_launches++;
+            if (h_counters[C_OVERFLOW]) throw Failure(STCSP_ERR_CAPACITY, "internal: automaton pools overflowed during ingest");
+            n_out = (long long)h_counters[C_OUT];
+            n_states = (long long)h_counters[C_STATES];
+            n_edges = (long long)h_counters[C_EDGES];
+            t_dominance += (long long)h_counters[C_DOMINANCE];
+        }
+        cur ^= 1;
+        n_in = n_out;
+        n_out = 0;
+        n_leaves = 0;
+        if (frontier_next) *frontier_next = n_in;
+    }
+
+    void finish(stcsp_automaton_t *part) {
+        memset(part, 0, sizeof *part);
+        float ms = 0;
+        if (timing_open) {
+            CK(cudaEventRecord(ev1, stream));
+            CK(cudaEventSynchronize(ev1));
+            CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        }
+        const int KW = dm.key_words, V = dm.V, SL = dm.sig_len;
+        auto *st = new AutoStore();
+        std::vector<int32_t> keys((size_t)n_states * KW);
+        st->edge_src.resize((size_t)n_edges);
+        st->edge_dst.resize((size_t)n_edges);
+        st->edge_label.resize((size_t)n_edges * V);
+        try {
+            if (n_states) CK(cudaMemcpyAsync(keys.data(), state_key.p, keys.size() * 4, cudaMemcpyDeviceToHost, stream));
+            if (n_edges) {
+                CK(cudaMemcpyAsync(st->edge_src.data(), edge_src.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(st->edge_dst.data(), edge_dst.p, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(st->edge_label.data(), edge_label.p, (size_t)n_edges * V * 4, cudaMemcpyDeviceToHost, stream));
+            }
+            CK(cudaStreamSynchronize(stream));
+        } catch (...) {
+            delete st;
+            throw;
+        }
+        d2h += (long long)keys.size() * 4 + n_edges * (2 + V) * 4;
+        st->sig_vars = sets.sig_vars();
+        st->state_sig.assign((size_t)n_states * SL, 0);
+        st->state_cset.resize((size_t)n_states);
+        st->state_failed.assign((size_t)n_states, 0);
+        for (long long s = 0; s < n_states; s++) {
+            st->state_cset[s] = std::max(0, keys[s * KW]);
+            for (int j = 0; j < SL; j++) st->state_sig[s * SL + j] = keys[s * KW + 1 + j];
+        }
+        part->n_vars = V;
+        part->n_sig_vars = dm.n_sig;
+        part->n_until = sets.n_until();
+        part->n_until_vars = sets.n_until_vars();
+        part->sig_len = SL;
+        part->root_final = sets.n_until() == 0;
+        part->n_constraint_sets = sets.n_sets();
+        part->n_states = n_states;
+        part->n_edges = n_edges;
+        part->n_search_nodes = t_nodes;
+        part->n_fails = t_fails;
+        part->n_leaves = t_leaves;
+        part->n_dominance = t_dominance;
+        part->n_waves = t_waves;
+        part->n_tuples = t_tuples;
+        part->n_revisions = t_revisions;
+        part->n_kernel_launches = t_launches;
+        part->n_expand_launches = t_expand_launches;
+        part->solve_ms = ms;
+        part->expand_ms = expand_ms;
+        part->wall_ms = (now_s() - t_create) * 1e3;
+        part->h2d_bytes = h2d;
+        part->d2h_bytes = d2h;
+        // the reference's (lb, ub) int32 pairs per variable and offset
+        part->algorithmic_bytes = t_nodes * 2ll * V * dm.k * 8 + t_leaves * ((SL + 1) * 4ll + 8) +
+                                  n_states * ((SL + 1) * 4ll + 8) + n_edges * (V + 2) * 4ll;
+        bind_store(part, st);
+    }
+};
+
+namespace {
+
+int fail_with(const Failure &f) {
+    set_error(f.what());
+    return f.code;
+}
+
+template <class F>
+int guarded(F &&body) {
+    try {
+        body();
+        return STCSP_OK;
+    } catch (const Failure &f) {
+        return fail_with(f);
+    } catch (const std::bad_alloc &) {
+        set_error("out of host memory");
+        return STCSP_ERR_CAPACITY;
+    } catch (const std::exception &ex) {
+        set_error(ex.what());
+        return STCSP_ERR_INVALID;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int stcsp_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int stcsp_session_create(const stcsp_problem_t *problem, const stcsp_options_t *options, int32_t rank,
+                         int32_t world_size, stcsp_session_t **out) {
+    if (!problem || !out) { set_error("null argument"); return STCSP_ERR_INVALID; }
+    *out = nullptr;
+    stcsp_session *s = nullptr;
+    int rc = guarded([&] {
+        s = new stcsp_session();
+        s->init(problem, options, rank, world_size);
+    });
+    if (rc != STCSP_OK) {
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return STCSP_OK;
+}
+
+void stcsp_session_destroy(stcsp_session_t *s) { delete s; }
+
+int32_t stcsp_session_record_words(const stcsp_session_t *s) { return s->dm.rec_words; }
+int32_t stcsp_session_request_words(const stcsp_session_t *s) { return 1 + s->dm.V; }
+
+int stcsp_session_expand(stcsp_session_t *s, int64_t *n_leaves, int64_t *n_pending) {
+    return guarded([&] { s->expand(n_leaves, n_pending); });
+}
+
+int stcsp_session_pending(stcsp_session_t *s, int32_t *requests) {
+    if (!s->pending.empty()) memcpy(requests, s->pending.data(), s->pending.size() * 4);
+    return STCSP_OK;
+}
+
+int stcsp_session_resolve(stcsp_session_t *s, const int32_t *requests, int64_t n_requests) {
+    return guarded([&] { s->resolve(requests, n_requests); });
+}
+
+int stcsp_session_outbox(stcsp_session_t *s, int32_t *outbox, int64_t outbox_capacity, int64_t *counts_per_rank) {
+    return guarded([&] { s->outbox(outbox, outbox_capacity, counts_per_rank); });
+}
+
+int stcsp_session_ingest(stcsp_session_t *s, const int32_t *inbox, int64_t n_records, int64_t *frontier_next) {
+    return guarded([&] { s->ingest(inbox, n_records, frontier_next); });
+}
+
+int stcsp_session_finish(stcsp_session_t *s, stcsp_automaton_t *part) {
+    return guarded([&] { s->finish(part); });
+}
+
+int stcsp_automaton_assemble(const stcsp_automaton_t *parts, int32_t n_parts, stcsp_automaton_t *out) {
+    if (!parts || n_parts < 1 || !out) { set_error("null argument"); return STCSP_ERR_INVALID; }
+    return guarded([&] {
+        const stcsp_automaton_t &p0 = parts[0];
+        const int V = p0.n_vars, SL = p0.sig_len, W = n_parts;
+        int64_t total_states = 0, total_edges = 0, max_local = 0;
+        for (int r = 0; r < W; r++) {
+            if (parts[r].n_vars != V || parts[r].sig_len != SL) throw Failure(STCSP_ERR_INVALID, "assemble: parts disagree on the model");
+            total_states += parts[r].n_states;
+            total_edges += parts[r].n_edges;
+            max_local = std::max<int64_t>(max_local, parts[r].n_states);
+        }
+        if (p0.n_states < 1) throw Failure(STCSP_ERR_INVALID, "assemble: part 0 does not hold the root state");
+        // dense ids in ascending global-id order: global = local * W + rank
+        std::vector<int32_t> dense((size_t)max_local * W, -1);
+        int32_t next = 0;
+        for (int64_t l = 0; l < max_local; l++)
+            for (int r = 0; r < W; r++)
+                if (l < parts[r].n_states) dense[(size_t)l * W + r] = next++;
+        auto *st = new AutoStore();
+        memset(out, 0, sizeof *out);
+        st->sig_vars.assign(p0.sig_vars, p0.sig_vars + p0.n_sig_vars);
+        st->state_sig.assign((size_t)total_states * SL, 0);
+        st->state_cset.assign((size_t)total_states, 0);
+        st->state_failed.assign((size_t)total_states, 0);
+        for (int r = 0; r < W; r++)
+            for (int64_t l = 0; l < parts[r].n_states; l++) {
+                const int32_t d = dense[(size_t)l * W + r];
+                st->state_cset[d] = parts[r].state_cset[l];
+                if (parts[r].state_failed) st->state_failed[d] = parts[r].state_failed[l];
+                for (int j = 0; j < SL; j++) st->state_sig[(size_t)d * SL + j] = parts[r].state_sig[l * SL + j];
+            }
+        // counting sort of the edges by dense source id
+        std::vector<int64_t> first((size_t)total_states + 1, 0);
+        auto map_id = [&](int32_t g) -> int32_t {
+            if (g < 0 || (size_t)g >= dense.size() || dense[g] < 0) throw Failure(STCSP_ERR_INVALID, "assemble: edge names an unknown state");
+            return dense[g];
+        };
+        for (int r = 0; r < W; r++)
+            for (int64_t e = 0; e < parts[r].n_edges; e++) first[(size_t)map_id(parts[r].edge_src[e]) + 1]++;
+        for (int64_t s = 0; s < total_states; s++) first[s + 1] += first[s];
+        std::vector<int64_t> fillp(first.begin(), first.end() - 1);
+        st->edge_src.resize((size_t)total_edges);
+        st->edge_dst.resize((size_t)total_edges);
+        st->edge_label.resize((size_t)total_edges * V);
+        for (int r = 0; r < W; r++)
+            for (int64_t e = 0; e < parts[r].n_edges; e++) {
+                const int32_t s = map_id(parts[r].edge_src[e]);
+                const int64_t at = fillp[s]++;
+                st->edge_src[at] = s;
+                st->edge_dst[at] = map_id(parts[r].edge_dst[e]);
+                memcpy(&st->edge_label[(size_t)at * V], parts[r].edge_label + e * V, (size_t)V * 4);
+            }
+        out->n_vars = V;
+        out->n_sig_vars = p0.n_sig_vars;
+        out->n_until = p0.n_until;
+        out->n_until_vars = p0.n_until_vars;
+        out->sig_len = SL;
+        out->root_final = p0.root_final;
+        out->n_states = total_states;
+        out->n_edges = total_edges;
+        for (int r = 0; r < W; r++) {
+            const stcsp_automaton_t &p = parts[r];
+            out->n_constraint_sets = std::max(out->n_constraint_sets, p.n_constraint_sets);
+            out->n_search_nodes += p.n_search_nodes;
+            out->n_fails += p.n_fails;
+            out->n_leaves += p.n_leaves;
+            out->n_dominance += p.n_dominance;
+            out->n_tuples += p.n_tuples;
+            out->n_revisions += p.n_revisions;
+            out->n_kernel_launches += p.n_kernel_launches;
+            out->n_expand_launches += p.n_expand_launches;
+            out->algorithmic_bytes += p.algorithmic_bytes;
+            out->h2d_bytes += p.h2d_bytes;
+            out->d2h_bytes += p.d2h_bytes;
+            out->n_waves = std::max(out->n_waves, p.n_waves);
+            out->solve_ms = std::max(out->solve_ms, p.solve_ms);
+            out->wall_ms = std::max(out->wall_ms, p.wall_ms);
+            out->expand_ms = std::max(out->expand_ms, p.expand_ms);
+        }
+        bind_store(out, st);
+    });
+}
+
+int stcsp_automaton_trim(stcsp_automaton_t *a) {
+    if (!a || !a->impl) { set_error("trim needs a library-owned automaton"); return STCSP_ERR_INVALID; }
+    return guarded([&] {
+        auto *st = (AutoStore *)a->impl;
+        const int64_t n = a->n_states, m = a->n_edges;
+        const int V = a->n_vars;
+        std::vector<int64_t> outdeg((size_t)n, 0), in_first((size_t)n + 1, 0);
+        for (int64_t e = 0; e < m; e++) {
+            outdeg[st->edge_src[e]]++;
+            in_first[(size_t)st->edge_dst[e] + 1]++;
+        }
+        for (int64_t s = 0; s < n; s++) in_first[s + 1] += in_first[s];
+        std::vector<int64_t> in_edge((size_t)m), fillp(in_first.begin(), in_first.end() - 1);
+        for (int64_t e = 0; e < m; e++) in_edge[fillp[st->edge_dst[e]]++] = e;
+        std::vector<uint8_t> alive((size_t)m, 1);
+        std::vector<int32_t> todo;
+        for (int64_t s = 0; s < n; s++)
+            if (outdeg[s] == 0) { st->state_failed[s] = 1; todo.push_back((int32_t)s); }
+        while (!todo.empty()) {
+            const int32_t s = todo.back();
+            todo.pop_back();
+            for (int64_t i = in_first[s]; i < in_first[s + 1]; i++) {
+                const int64_t e = in_edge[i];
+                if (!alive[e]) continue;
+                alive[e] = 0;
+                const int32_t p = st->edge_src[e];
+                if (--outdeg[p] == 0 && !st->state_failed[p]) { st->state_failed[p] = 1; todo.push_back(p); }
+            }
+        }
+        int64_t w = 0;
+        for (int64_t e = 0; e < m; e++) {
+            if (!alive[e]) continue;
+            if (w != e) {
+                st->edge_src[w] = st->edge_src[e];
+                st->edge_dst[w] = st->edge_dst[e];
+                memmove(&st->edge_label[(size_t)w * V], &st->edge_label[(size_t)e * V], (size_t)V * 4);
+            }
+            w++;
+        }
+        st->edge_src.resize((size_t)w);
+        st->edge_dst.resize((size_t)w);
+        st->edge_label.resize((size_t)w * V);
+        a->n_edges = w;
+        bind_store(a, st);
+    });
+}
+
+int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *options, stcsp_automaton_t *out) {
+    if (!problem || !out) { set_error("null argument"); return STCSP_ERR_INVALID; }
+    memset(out, 0, sizeof *out);
+    const double t0 = now_s();
+    stcsp_session *s = nullptr;
+    stcsp_automaton_t part;
+    memset(&part, 0, sizeof part);
+    int rc = guarded([&] {
+        s = new stcsp_session();
+        s->init(problem, options, 0, 1);
+        const double deadline = s->opt.time_limit_s > 0 ? t0 + s->opt.time_limit_s : 0;
+        int64_t frontier = s->n_in;
+        std::vector<int32_t> req;
+        while (frontier > 0) {
+            if (deadline > 0 && now_s() > deadline) throw Failure(STCSP_ERR_TIMEOUT, "time limit reached");
+            int64_t n_leaves = 0, n_pending = 0;
+            s->expand(&n_leaves, &n_pending);
+            if (n_pending > 0) {
+                req = s->pending;
+                s->resolve(req.data(), n_pending);
+            }
+            s->ingest(nullptr, 0, &frontier);
+        }
+        s->finish(&part);
+    });
+    delete s;
+    if (rc == STCSP_OK) rc = stcsp_automaton_assemble(&part, 1, out);
+    stcsp_automaton_free(&part);
+    if (rc == STCSP_OK && !(options && options->no_trim)) rc = stcsp_automaton_trim(out);
+    if (rc == STCSP_OK) out->wall_ms = (now_s() - t0) * 1e3;
+    else stcsp_automaton_free(out);
+    return rc;
+}
+
+void stcsp_automaton_free(stcsp_automaton_t *a) {
+    if (!a) return;
+    delete (AutoStore *)a->impl;
+    memset(a, 0, sizeof *a);
+}
+
+}  // extern "C"
