@@ -268,8 +268,6 @@ void SetTable::compile_set(int32_t s) {
     ds.next_off = (int32_t)dev_aux.size();
     ds.n_next = (int32_t)next_pairs.size() / 2;
     dev_aux.insert(dev_aux.end(), next_pairs.begin(), next_pairs.end());
-    if ((int)hs.cap_vars.size() > Limits::kMaxCap)
-        throw std::invalid_argument("unsupported: `first` captures more than 12 variables in one constraint set");
     ds.n_cap = (int32_t)hs.cap_vars.size();
     ds.cap_off = (int32_t)dev_aux.size();
     dev_aux.insert(dev_aux.end(), hs.cap_vars.begin(), hs.cap_vars.end());

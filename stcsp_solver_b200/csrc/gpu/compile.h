@@ -78,7 +78,6 @@ struct HostSet {
 struct Limits {
     static constexpr int kMaxScope = 32;        // variables per POINT constraint
     static constexpr int kMaxStack = 24;        // evaluator stack depth
-    static constexpr int kMaxCap = 12;          // captured variables per set
     static constexpr int kMaxUntil = 30;        // until constraints (flags packed in one word)
     static constexpr int kMaxWidth = 64;        // values per domain (one 64-bit word)
 };

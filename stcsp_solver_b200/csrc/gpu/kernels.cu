@@ -419,13 +419,18 @@ __host__ __device__ __forceinline__ uint32_t key_word_hash(int32_t word, int j) 
 
 __host__ __device__ inline uint32_t owner_hash(uint32_t h) { return mix32(h ^ 0x5bd1e995u); }
 
-__host__ __device__ inline uint32_t cap_hash(int cid, const int32_t *vals, int n) {
-    uint32_t h = 0x9e3779b9u * (uint32_t)(cid + 1);
-    for (int i = 0; i < n; i++) {
-        h ^= (uint32_t)vals[i] + 0x9e3779b9u + (h << 6) + (h >> 2);
-    }
+__host__ __device__ inline uint32_t cap_hash_begin(int cid) { return 0x9e3779b9u * (uint32_t)(cid + 1); }
+__host__ __device__ inline uint32_t cap_hash_step(uint32_t h, int32_t v) {
+    return h ^ ((uint32_t)v + 0x9e3779b9u + (h << 6) + (h >> 2));
+}
+__host__ __device__ inline uint32_t cap_hash_end(uint32_t h) {
     h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
     return h;
+}
+__host__ __device__ inline uint32_t cap_hash(int cid, const int32_t *vals, int n) {
+    uint32_t h = cap_hash_begin(cid);
+    for (int i = 0; i < n; i++) h = cap_hash_step(h, vals[i]);
+    return cap_hash_end(h);
 }
 
 // word j of the state key of the successor described by a routed record
@@ -454,14 +459,15 @@ __global__ void __launch_bounds__(256) route_kernel(const DevModel M, const Rout
             // the successor set depends on the values captured by `first`: host-filled map
             int found = -1;
             if (lane == 0 && P.capmap_mask >= 0) {
-                int32_t vals[Limits::kMaxCap];
-                for (int i = 0; i < S.n_cap; i++) vals[i] = rec[4 + M.aux[S.cap_off + i]];
-                uint32_t h = cap_hash(cid, vals, S.n_cap) & (uint32_t)P.capmap_mask;
+                const int32_t *cap = M.aux + S.cap_off;
+                uint32_t h = cap_hash_begin(cid);
+                for (int i = 0; i < S.n_cap; i++) h = cap_hash_step(h, rec[4 + cap[i]]);
+                h = cap_hash_end(h) & (uint32_t)P.capmap_mask;
                 for (;;) {
-                    const CapEntry &e = P.capmap[h];
+                    const CapEntry e = P.capmap[h];
                     if (e.cid == -1) break;
                     bool eq = e.cid == cid;
-                    for (int i = 0; eq && i < S.n_cap; i++) eq = e.vals[i] == vals[i];
+                    for (int i = 0; eq && i < S.n_cap; i++) eq = P.capvals[e.off + i] == rec[4 + cap[i]];
                     if (eq) { found = e.next; break; }
                     h = (h + 1) & (uint32_t)P.capmap_mask;
                 }

@@ -59,7 +59,8 @@ struct DevModel {
 struct CapEntry {          // (constraint set, captured values) -> successor set; host-filled
     int32_t cid;           // -1 = empty slot
     int32_t next;
-    int32_t vals[Limits::kMaxCap];
+    int32_t off;           // captured values at capvals[off .. off + n_cap of the set)
+    int32_t pad;
 };
 
 struct ExpandArgs {
@@ -77,6 +78,7 @@ struct RouteArgs {
     const int32_t *list;        // nullptr: leaves [0, C_LEAVES); else the leaves list[0 .. count)
     long long count;
     const CapEntry *capmap;
+    const int32_t *capvals;
     int32_t capmap_mask;
     int32_t *unresolved;        // leaf indices that need the host
     long long unresolved_cap;

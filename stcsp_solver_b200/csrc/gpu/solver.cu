@@ -114,6 +114,8 @@ struct stcsp_session {
     int expand_grid_max = 148;
     // constraint-set transitions resolved so far
     std::vector<CapEntry> capmap;
+    std::vector<int32_t> capvals;
+    DBuf<int32_t> d_capvals;
     long long capmap_used = 0;
     std::map<std::vector<int32_t>, int32_t> cap_lookup;
     std::vector<int32_t> pending;                   // flat requests [cid, values[V]]
@@ -318,6 +320,7 @@ struct stcsp_session {
                 ra.leaves = leaves.p;
                 ra.list = nullptr;
                 ra.capmap = d_capmap.p;
+                ra.capvals = d_capvals.p;
                 ra.capmap_mask = capmap.empty() ? -1 : (int32_t)capmap.size() - 1;
                 ra.unresolved = unresolved.p;
                 ra.unresolved_cap = (long long)unresolved.cap;
@@ -399,12 +402,13 @@ struct stcsp_session {
         CapEntry e{};
         e.cid = cid;
         e.next = next;
-        for (size_t i = 1; i < key.size(); i++) e.vals[i - 1] = key[i];
+        e.off = (int32_t)capvals.size();
+        capvals.insert(capvals.end(), key.begin() + 1, key.end());
         place(e);
     }
     void place(const CapEntry &e) {
         const int n = (int)sets.host_set(e.cid).cap_vars.size();
-        uint32_t h = capmap_hash(e.cid, e.vals, n) & (uint32_t)(capmap.size() - 1);
+        uint32_t h = capmap_hash(e.cid, capvals.data() + e.off, n) & (uint32_t)(capmap.size() - 1);
         while (capmap[h].cid != -1) h = (h + 1) & (uint32_t)(capmap.size() - 1);
         capmap[h] = e;
         capmap_used++;
@@ -433,6 +437,7 @@ struct stcsp_session {
         if (added) {
             d_capmap.reserve(capmap.size(), 0, stream);
             CK(cudaMemcpyAsync(d_capmap.p, capmap.data(), capmap.size() * sizeof(CapEntry), cudaMemcpyHostToDevice, stream));
+            upload(d_capvals, capvals);
             CK(cudaStreamSynchronize(stream));
             h2d += (long long)(capmap.size() * sizeof(CapEntry));
         }
@@ -443,6 +448,7 @@ struct stcsp_session {
             ra.list = unresolved.p;
             ra.count = n_unres;
             ra.capmap = d_capmap.p;
+            ra.capvals = d_capvals.p;
             ra.capmap_mask = capmap.empty() ? -1 : (int32_t)capmap.size() - 1;
             ra.unresolved = gathered.p;         // scratch: nothing may remain unresolved
             ra.unresolved_cap = (long long)gathered.cap;
