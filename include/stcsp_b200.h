@@ -214,7 +214,7 @@ int stcsp_session_resolve(stcsp_session_t *s, const int32_t *requests, int64_t n
  * start at record index sum(counts_per_rank[0..q)). */
 int stcsp_session_outbox(stcsp_session_t *s, int32_t *outbox, int64_t outbox_capacity, int64_t *counts_per_rank);
 /* Insert `n_records` routed leaf records (device memory) owned by this rank and end the wave.
- * inbox == NULL: ingest this rank's own leaves (world_size == 1).  *frontier_next = local search
+ * inbox == NULL: world_size == 1 ingests this rank's own leaves in place; otherwise nothing was received.  *frontier_next = local search
  * nodes waiting for the next wave. */
 int stcsp_session_ingest(stcsp_session_t *s, const int32_t *inbox, int64_t n_records, int64_t *frontier_next);
 /* Local part of the automaton: the states this rank owns (rows in local-index order, global id =

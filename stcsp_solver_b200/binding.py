@@ -112,6 +112,20 @@ def lib() -> C.CDLL:
         L.stcsp_solution_canonical.argtypes = [C.POINTER(Problem), C.POINTER(SolutionC)]
         L.stcsp_solution_canonical.restype = C.c_void_p
         L.stcsp_gpu_device_count.restype = C.c_int
+        L.stcsp_session_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.c_int32, C.c_int32,
+                                           C.POINTER(C.c_void_p)]
+        L.stcsp_session_destroy.argtypes = [C.c_void_p]
+        L.stcsp_session_record_words.argtypes = [C.c_void_p]
+        L.stcsp_session_record_words.restype = C.c_int32
+        L.stcsp_session_request_words.argtypes = [C.c_void_p]
+        L.stcsp_session_request_words.restype = C.c_int32
+        L.stcsp_session_expand.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.stcsp_session_pending.argtypes = [C.c_void_p, C.c_void_p]
+        L.stcsp_session_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.stcsp_session_outbox.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.stcsp_session_ingest.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.stcsp_session_finish.argtypes = [C.c_void_p, C.POINTER(AutomatonC)]
+        L.stcsp_automaton_assemble.argtypes = [C.POINTER(AutomatonC), C.c_int32, C.POINTER(AutomatonC)]
         _lib = L
     return _lib
 
@@ -255,3 +269,93 @@ def solve_text(text: str, flags: Sequence[str] = (), options: Optional[Options] 
     model = Model(text, k)
     automaton = solve(model, options)
     return model, automaton, Solution(model, automaton, "-a" in flags, "-z" in flags)
+
+
+class Session:
+    """Step-wise search on one GPU (one rank of a multi-GPU solve); see include/stcsp_b200.h."""
+
+    def __init__(self, model: Model, options: Optional[Options], rank: int, world_size: int):
+        self.model = model
+        self._h = C.c_void_p()
+        opts = options if options is not None else default_options()
+        _check(lib().stcsp_session_create(model.problem, C.byref(opts), rank, world_size, C.byref(self._h)))
+        self.rank, self.world_size = rank, world_size
+        self.record_words = lib().stcsp_session_record_words(self._h)
+        self.request_words = lib().stcsp_session_request_words(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().stcsp_session_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def expand(self):
+        n_leaves, n_pending = C.c_int64(), C.c_int64()
+        _check(lib().stcsp_session_expand(self._h, C.byref(n_leaves), C.byref(n_pending)))
+        return n_leaves.value, n_pending.value
+
+    def pending(self, n_pending: int) -> np.ndarray:
+        out = np.zeros((n_pending, self.request_words), dtype=np.int32)
+        if n_pending:
+            _check(lib().stcsp_session_pending(self._h, out.ctypes.data))
+        return out
+
+    def resolve(self, requests: np.ndarray) -> None:
+        requests = np.ascontiguousarray(requests, dtype=np.int32)
+        _check(lib().stcsp_session_resolve(self._h, requests.ctypes.data, requests.shape[0]))
+
+    def outbox(self, device_ptr: int, capacity: int) -> np.ndarray:
+        counts = (C.c_int64 * self.world_size)()
+        _check(lib().stcsp_session_outbox(self._h, device_ptr, capacity, counts))
+        return np.array(list(counts), dtype=np.int64)
+
+    def ingest(self, device_ptr: Optional[int], n_records: int) -> int:
+        nxt = C.c_int64()
+        _check(lib().stcsp_session_ingest(self._h, device_ptr, n_records, C.byref(nxt)))
+        return nxt.value
+
+    def finish(self) -> Automaton:
+        out = AutomatonC()
+        _check(lib().stcsp_session_finish(self._h, C.byref(out)))
+        return Automaton(out, lib().stcsp_automaton_free)
+
+
+_PART_STATS = ("n_constraint_sets", "n_search_nodes", "n_fails", "n_leaves", "n_dominance", "n_waves", "n_tuples",
+               "n_revisions", "n_kernel_launches", "n_expand_launches", "algorithmic_bytes", "h2d_bytes", "d2h_bytes")
+_PART_TIMES = ("solve_ms", "wall_ms", "expand_ms")
+
+
+def part_to_arrays(a: Automaton) -> dict:
+    """Plain-numpy form of one rank's part (what travels between ranks)."""
+    c = a.c
+    head = np.array([c.n_vars, c.n_sig_vars, c.n_until, c.n_until_vars, c.sig_len, c.root_final, c.n_states, c.n_edges]
+                    + [getattr(c, k) for k in _PART_STATS], dtype=np.int64)
+    times = np.array([getattr(c, k) for k in _PART_TIMES], dtype=np.float64)
+    return {"head": head, "times": times, "sig_vars": a.sig_vars, "state_sig": a.state_sig.reshape(-1),
+            "state_cset": a.state_cset, "edge_src": a.edge_src, "edge_dst": a.edge_dst,
+            "edge_label": a.edge_label.reshape(-1)}
+
+
+def assemble(parts: Sequence[dict], trim: bool = True) -> Automaton:
+    """stcsp_automaton_assemble (+ trim) over per-rank parts given as numpy arrays (rank order)."""
+    arr = (AutomatonC * len(parts))()
+    keep = []
+    for i, p in enumerate(parts):
+        h = [int(x) for x in p["head"]]
+        c = arr[i]
+        c.n_vars, c.n_sig_vars, c.n_until, c.n_until_vars, c.sig_len, c.root_final, c.n_states, c.n_edges = h[:8]
+        for k, v in zip(_PART_STATS, h[8:]):
+            setattr(c, k, v)
+        for k, v in zip(_PART_TIMES, p["times"]):
+            setattr(c, k, float(v))
+        for name in ("sig_vars", "state_sig", "state_cset", "edge_src", "edge_dst", "edge_label"):
+            a = np.ascontiguousarray(p[name], dtype=np.int32)
+            keep.append(a)
+            setattr(c, name, a.ctypes.data_as(C.POINTER(C.c_int32)))
+        c.state_failed = None
+    out = AutomatonC()
+    _check(lib().stcsp_automaton_assemble(arr, len(parts), C.byref(out)))
+    if trim:
+        _check(lib().stcsp_automaton_trim(C.byref(out)))
+    return Automaton(out, lib().stcsp_automaton_free)

@@ -487,7 +487,7 @@ struct stcsp_session {
     void ingest(const int32_t *inbox, int64_t n, int64_t *frontier_next) {
         if (n_unres > 0) throw Failure(STCSP_ERR_INVALID, "ingest called with unresolved leaves pending");
         const int NW = dm.node_words, KW = dm.key_words, V = dm.V;
-        if (!inbox) n = n_leaves;
+        if (!inbox) n = world == 1 ? n_leaves : 0;       // single rank: this rank's own leaves, in place
         const int32_t *records = inbox ? inbox : leaves.p;
         DBuf<int32_t> &out = frontier[cur ^ 1];
         if (n > 0) {

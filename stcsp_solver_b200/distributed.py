@@ -1,0 +1,132 @@
+"""Multi-GPU solve: one process per GPU, states sharded by the hash of their signature.
+
+Each rank runs the same C-ABI session (include/stcsp_b200.h) on its own GPU.  Per frontier wave:
+local expand -> leaves grouped by owner rank (device) -> counts all-to-all -> payload all-to-all
+(NCCL over NVLink when the backend is nccl) -> owners dedup/insert -> all-reduce of the frontier
+sizes for termination.  Constraint-set ids are kept identical on every rank by resolving the
+union of all ranks' requests in one sorted order.  Rank 0 gathers the per-rank parts and
+assembles + trims the automaton (reference fail rule, src/solveralgorithm.cpp:904-910).
+
+The collective plumbing (``WaveExchange``) is device-agnostic so that it is covered by
+world_size-2 gloo tests on CPU; the sessions themselves need CUDA.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import binding
+
+
+class WaveExchange:
+    """The collectives of one solve, over CPU tensors (gloo) or CUDA tensors (nccl)."""
+
+    def __init__(self, group=None, device: Optional[torch.device] = None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+                else torch.device("cpu")
+        self.device = device
+
+    def total(self, value: int) -> int:
+        t = torch.tensor([value], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
+
+    def exchange_counts(self, counts: np.ndarray) -> np.ndarray:
+        """counts[q] = records this rank sends to q  ->  records this rank receives from each rank."""
+        send = torch.as_tensor(np.asarray(counts, dtype=np.int64)).to(self.device)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv.cpu().numpy()
+
+    def exchange_records(self, outbox: torch.Tensor, send_counts: np.ndarray, recv_counts: np.ndarray) -> torch.Tensor:
+        """outbox [n_send, words] grouped by destination rank -> inbox [n_recv, words] grouped by source rank."""
+        inbox = torch.empty((int(recv_counts.sum()), outbox.shape[1]), dtype=outbox.dtype, device=outbox.device)
+        dist.all_to_all_single(inbox, outbox, output_split_sizes=[int(c) for c in recv_counts],
+                               input_split_sizes=[int(c) for c in send_counts], group=self.group)
+        return inbox
+
+    def union_rows(self, rows: np.ndarray) -> np.ndarray:
+        """Sorted union over all ranks of the int32 rows each rank holds (same result on every rank)."""
+        width = rows.shape[1]
+        n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=self.device)
+        sizes = [torch.empty_like(n) for _ in range(self.world)]
+        dist.all_gather(sizes, n, group=self.group)
+        sizes = [int(s.item()) for s in sizes]
+        cap = max(max(sizes), 1)
+        mine = torch.zeros((cap, width), dtype=torch.int32, device=self.device)
+        if rows.shape[0]:
+            mine[: rows.shape[0]] = torch.as_tensor(np.ascontiguousarray(rows, dtype=np.int32)).to(self.device)
+        got = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(got, mine, group=self.group)
+        allrows = torch.cat([g[:s] for g, s in zip(got, sizes)], dim=0).cpu().numpy()
+        if allrows.shape[0] == 0:
+            return allrows
+        return np.unique(allrows, axis=0)
+
+    def gather_arrays(self, arrays: dict) -> Optional[List[dict]]:
+        """Every rank's dict of numpy arrays, in rank order, on rank 0 (None elsewhere)."""
+        names = sorted(arrays)
+        sizes = torch.tensor([arrays[k].size for k in names], dtype=torch.int64, device=self.device)
+        all_sizes = [torch.empty_like(sizes) for _ in range(self.world)]
+        dist.all_gather(all_sizes, sizes, group=self.group)
+        all_sizes = [s.cpu().numpy() for s in all_sizes]
+        out = [dict() for _ in range(self.world)] if self.rank == 0 else None
+        for i, k in enumerate(names):
+            dtype = arrays[k].dtype
+            tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+                   np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+            if self.rank == 0:
+                out[0][k] = arrays[k]
+                for r in range(1, self.world):
+                    buf = torch.empty(int(all_sizes[r][i]), dtype=tdt, device=self.device)
+                    if buf.numel():
+                        dist.recv(buf, src=r, group=self.group)
+                    out[r][k] = buf.cpu().numpy()
+            elif arrays[k].size:
+                dist.send(torch.as_tensor(np.ascontiguousarray(arrays[k])).to(self.device), dst=0, group=self.group)
+        return out
+
+
+def solve_distributed(model: binding.Model, options: Optional[binding.Options] = None, group=None,
+                      trim: bool = True):
+    """Solve on all ranks of `group` (default: the world).  Returns the merged Automaton on rank 0, None elsewhere.
+
+    The caller has initialised torch.distributed (backend nccl) and set the CUDA device of this process.
+    """
+    ex = WaveExchange(group)
+    opts = options if options is not None else binding.default_options()
+    opts.use_current_device = 1
+    session = binding.Session(model, opts, ex.rank, ex.world)
+    words = session.record_words
+    stats = {"waves": 0, "records_sent": 0}
+    try:
+        while True:
+            n_leaves, n_pending = session.expand()
+            if ex.total(n_pending) > 0:
+                session.resolve(ex.union_rows(session.pending(n_pending)))
+            outbox = torch.empty((max(n_leaves, 1), words), dtype=torch.int32, device=ex.device)
+            send_counts = session.outbox(outbox.data_ptr(), n_leaves)
+            recv_counts = ex.exchange_counts(send_counts)
+            inbox = ex.exchange_records(outbox[:n_leaves], send_counts, recv_counts)
+            torch.cuda.synchronize()
+            frontier = session.ingest(inbox.data_ptr() if inbox.shape[0] else None, int(inbox.shape[0]))
+            stats["waves"] += 1
+            stats["records_sent"] += int(send_counts.sum())
+            if ex.total(frontier) == 0:
+                break
+        part = session.finish()
+        parts = ex.gather_arrays(binding.part_to_arrays(part))
+    finally:
+        session.close()
+    if ex.rank != 0:
+        return None
+    automaton = binding.assemble(parts, trim=trim)
+    automaton.exchange_stats = stats
+    return automaton
