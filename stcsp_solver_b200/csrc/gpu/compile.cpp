@@ -229,6 +229,7 @@ void SetTable::compile_set(int32_t s) {
         int32_t ci = (int32_t)dev_cons.size();
         if (c.kind == ConKind::Next) {
             dc.kind = DK_NEXT;
+            dc.pivot = -1;
             dc.x = c.root->kid[0]->arg;
             dc.y = c.root->kid[1]->kid[0]->arg;
             next_pairs.push_back(dc.x);
@@ -237,6 +238,7 @@ void SetTable::compile_set(int32_t s) {
             dev_props.push_back(DevProp{ci, 0});
         } else if (c.kind == ConKind::Until) {
             dc.kind = DK_UNTIL;
+            dc.pivot = -1;
             dc.x = c.root->kid[0]->arg;
             dc.y = c.root->kid[1]->arg;
             dc.until_idx = until_idx;
@@ -252,6 +254,7 @@ void SetTable::compile_set(int32_t s) {
             dc.code_off = (int32_t)dev_code.size();
             int depth = compile_expr(*c.root, c.scope, dev_code);
             dc.code_len = (int32_t)dev_code.size() - dc.code_off;
+            assign_table(dc, c);
             if (depth > Limits::kMaxStack) throw std::invalid_argument("unsupported: expression nesting needs a deeper evaluator stack");
             max_stack_ = std::max(max_stack_, (int32_t)depth);
             ds.max_stack = std::max(ds.max_stack, (int32_t)depth);
@@ -273,6 +276,15 @@ void SetTable::compile_set(int32_t s) {
     dev_aux.insert(dev_aux.end(), hs.cap_vars.begin(), hs.cap_vars.end());
 
     ds.n_prop = (int32_t)dev_props.size() - ds.prop_off;
+    // the propagation loop runs the lowest dirty index first: cheap propagators before expensive ones
+    auto cost = [&](const DevProp &pr) -> long long {
+        const DevCon &dc = dev_cons[pr.con];
+        if (dc.kind != DK_POINT) return 0;
+        if (dc.pivot >= 0) return 1 + dc.table_entries;
+        return (1ll << 40) + dc.n_scope;
+    };
+    std::stable_sort(dev_props.begin() + ds.prop_off, dev_props.end(),
+                     [&](const DevProp &a, const DevProp &b) { return cost(a) < cost(b); });
     ds.n_words = std::max(1, (ds.n_prop + 31) / 32);
     max_props_ = std::max(max_props_, ds.n_prop);
     ds.wake_off = (int32_t)dev_wake.size();
@@ -294,6 +306,53 @@ void SetTable::compile_set(int32_t s) {
     }
     ds.static_next = -1;
     dev_sets[s] = ds;
+}
+
+// Relation table of a pointwise constraint: allocated here, filled on the device.
+void SetTable::assign_table(DevCon &dc, const Constraint &c) {
+    dc.pivot = -1;
+    dc.table_entries = 0;
+    dc.table_off = 0;
+    const int n = dc.n_scope;
+    dev_stride.resize(dev_scope.size(), 0);
+    if (n < 1) return;
+    std::vector<stcsp_tok_t> toks;
+    flatten_expr(*c.root, toks);
+    std::string key((const char *)toks.data(), toks.size() * sizeof(stcsp_tok_t));
+    auto it = table_cache_.find(key);
+    if (it == table_cache_.end()) {
+        int pivot = 0;
+        for (int i = 1; i < n; i++)
+            if (width_[c.scope[i]] > width_[c.scope[pivot]]) pivot = i;
+        long long entries = 1;
+        for (int i = 0; i < n && entries <= Limits::kMaxTableEntries; i++)
+            if (i != pivot) entries *= width_[c.scope[i]];
+        if (entries > Limits::kMaxTableEntries || table_words + entries > Limits::kMaxTableWords) return;
+        TableRef ref;
+        ref.off = table_words;
+        ref.entries = (int32_t)entries;
+        ref.pivot = pivot;
+        ref.strides.assign(n, 0);
+        int32_t stride = 1;
+        for (int i = 0; i < n; i++) {
+            if (i == pivot) continue;
+            ref.strides[i] = stride;
+            stride *= width_[c.scope[i]];
+        }
+        table_words += entries;
+        it = table_cache_.emplace(key, ref).first;
+        dc.pivot = ref.pivot;
+        dc.table_entries = ref.entries;
+        dc.table_off = ref.off;
+        for (int i = 0; i < n; i++) dev_stride[dc.scope_off + i] = ref.strides[i];
+        table_jobs.push_back(TableJob{(int32_t)dev_cons.size()});      // dc is appended right after this call
+        return;
+    }
+    const TableRef &ref = it->second;
+    dc.pivot = ref.pivot;
+    dc.table_entries = ref.entries;
+    dc.table_off = ref.off;
+    for (int i = 0; i < n; i++) dev_stride[dc.scope_off + i] = ref.strides[i];
 }
 
 void SetTable::resolve_static(int32_t s) {

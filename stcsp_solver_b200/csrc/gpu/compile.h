@@ -49,6 +49,11 @@ struct DevCon {            // one enforceable constraint of one constraint set
     int32_t code_len;
     int32_t x, y;          // NEXT: x == next y.  UNTIL: x until y
     int32_t until_idx;     // UNTIL: index among the set's until constraints
+    // POINT with a relation table (small product of declared widths): entry [sum bitpos(slot) * stride(slot)]
+    // over the non-pivot slots = bitmask of the pivot variable's values completing a satisfying tuple
+    int32_t pivot;         // scope slot of the pivot variable, -1: no table (bytecode enumeration)
+    int32_t table_entries;
+    long long table_off;   // into the table pool (u64 words)
 };
 
 struct DevProp {           // propagator = (constraint, time offset); NEXT/UNTIL use offset 0
@@ -80,6 +85,12 @@ struct Limits {
     static constexpr int kMaxStack = 24;        // evaluator stack depth
     static constexpr int kMaxUntil = 30;        // until constraints (flags packed in one word)
     static constexpr int kMaxWidth = 64;        // values per domain (one 64-bit word)
+    static constexpr int kMaxTableEntries = 1 << 16;    // per relation table (512 KiB)
+    static constexpr long long kMaxTableWords = 1ll << 25;   // whole pool (256 MiB)
+};
+
+struct TableJob {          // a relation table the device still has to fill (build_tables_kernel)
+    int32_t con;           // absolute constraint index
 };
 
 class SetTable {
@@ -111,7 +122,10 @@ class SetTable {
     std::vector<DevCon> dev_cons;
     std::vector<DevProp> dev_props;
     std::vector<int32_t> dev_scope;
+    std::vector<int32_t> dev_stride;        // parallel to dev_scope: table stride of each scope slot (0 for the pivot)
     std::vector<Instr> dev_code;
+    std::vector<TableJob> table_jobs;       // tables allocated since the last take_table_jobs()
+    long long table_words = 0;              // size of the device table pool in u64 words
     std::vector<uint32_t> dev_wake;
     std::vector<int32_t> dev_aux;
     std::vector<int32_t> arr_off, arr_val;
@@ -120,8 +134,11 @@ class SetTable {
     int32_t add_set(std::vector<Constraint> cons);
     int32_t find_or_add(std::vector<Constraint> cons);
     void compile_set(int32_t s);
+    void assign_table(DevCon &dc, const Constraint &c);
     void resolve_static(int32_t s);
 
+    struct TableRef { long long off; int32_t entries, pivot; std::vector<int32_t> strides; };
+    std::map<std::string, TableRef> table_cache_;      // structurally equal constraints share one table
     int32_t k_ = 2;
     std::vector<int32_t> lb_, width_;
     std::vector<Array> arrays_;

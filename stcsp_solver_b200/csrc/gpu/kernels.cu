@@ -22,6 +22,8 @@
 // leaf every constraint has exactly one tuple, so every leaf is checked exactly.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace stcsp {
@@ -85,6 +87,7 @@ __device__ __forceinline__ u64 shift_bits(u64 v, int s) {
 }
 
 // ---- bytecode evaluator: one tuple per lane (reference solverValidateRe) --------------------------
+template <int LS>   // LS = distance between consecutive stack/scope slots of one lane (32: warp-interleaved, 1: private)
 __device__ __forceinline__ int eval_tuple(const Instr *__restrict__ code, const int32_t *cur, int32_t *stk, int lane,
                                           const DevModel &M) {
     int pc = 0, sp = 0, tos = 0;
@@ -96,8 +99,8 @@ __device__ __forceinline__ int eval_tuple(const Instr *__restrict__ code, const 
         int l;
         switch (in.x) {
             case BC_END: return tos != 0;
-            case BC_PUSHC: stk[sp * 32 + lane] = tos; sp++; tos = arg; break;
-            case BC_PUSHV: stk[sp * 32 + lane] = tos; sp++; tos = cur[arg * 32 + lane]; break;
+            case BC_PUSHC: stk[sp * LS + lane] = tos; sp++; tos = arg; break;
+            case BC_PUSHV: stk[sp * LS + lane] = tos; sp++; tos = cur[arg * LS + lane]; break;
             case BC_ARR: {
                 const int lo = M.arr_off[arg], n = M.arr_off[arg + 1] - lo;
                 if (tos < 0 || tos >= n) { valid = false; tos = 0; }
@@ -106,28 +109,28 @@ __device__ __forceinline__ int eval_tuple(const Instr *__restrict__ code, const 
             }
             case BC_ABS: tos = tos < 0 ? (int)(0u - (unsigned)tos) : tos; break;
             case BC_NOT: tos = (tos == 0); break;
-            case BC_LT: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l < tos) : 0; break;
-            case BC_GT: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l > tos) : 0; break;
-            case BC_LE: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l <= tos) : 0; break;
-            case BC_GE: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l >= tos) : 0; break;
-            case BC_EQ: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l == tos) : 0; break;
-            case BC_NE: sp--; l = stk[sp * 32 + lane]; tos = valid ? (l != tos) : 0; break;
-            case BC_ADD: sp--; l = stk[sp * 32 + lane]; tos = valid ? (int)((unsigned)l + (unsigned)tos) : 0; break;
-            case BC_SUB: sp--; l = stk[sp * 32 + lane]; tos = valid ? (int)((unsigned)l - (unsigned)tos) : 0; break;
-            case BC_MUL: sp--; l = stk[sp * 32 + lane]; tos = valid ? (int)((unsigned)l * (unsigned)tos) : 0; break;
+            case BC_LT: sp--; l = stk[sp * LS + lane]; tos = valid ? (l < tos) : 0; break;
+            case BC_GT: sp--; l = stk[sp * LS + lane]; tos = valid ? (l > tos) : 0; break;
+            case BC_LE: sp--; l = stk[sp * LS + lane]; tos = valid ? (l <= tos) : 0; break;
+            case BC_GE: sp--; l = stk[sp * LS + lane]; tos = valid ? (l >= tos) : 0; break;
+            case BC_EQ: sp--; l = stk[sp * LS + lane]; tos = valid ? (l == tos) : 0; break;
+            case BC_NE: sp--; l = stk[sp * LS + lane]; tos = valid ? (l != tos) : 0; break;
+            case BC_ADD: sp--; l = stk[sp * LS + lane]; tos = valid ? (int)((unsigned)l + (unsigned)tos) : 0; break;
+            case BC_SUB: sp--; l = stk[sp * LS + lane]; tos = valid ? (int)((unsigned)l - (unsigned)tos) : 0; break;
+            case BC_MUL: sp--; l = stk[sp * LS + lane]; tos = valid ? (int)((unsigned)l * (unsigned)tos) : 0; break;
             case BC_DIV:
             case BC_MOD:
-                sp--; l = stk[sp * 32 + lane];
+                sp--; l = stk[sp * LS + lane];
                 if (!valid) tos = 0;
                 else if (tos == 0 || (l == (int)0x80000000 && tos == -1)) { valid = false; tos = 0; }
                 else tos = in.x == BC_DIV ? l / tos : l % tos;
                 break;
-            case BC_JZ: l = tos; sp--; tos = stk[sp * 32 + lane]; if (l == 0) pc = arg; break;
+            case BC_JZ: l = tos; sp--; tos = stk[sp * LS + lane]; if (l == 0) pc = arg; break;
             case BC_JMP: pc = arg; break;
-            case BC_AND_SC: if (tos == 0) pc = arg; else { sp--; tos = stk[sp * 32 + lane]; } break;
-            case BC_OR_SC: if (tos != 0) { tos = 1; pc = arg; } else { sp--; tos = stk[sp * 32 + lane]; } break;
+            case BC_AND_SC: if (tos == 0) pc = arg; else { sp--; tos = stk[sp * LS + lane]; } break;
+            case BC_OR_SC: if (tos != 0) { tos = 1; pc = arg; } else { sp--; tos = stk[sp * LS + lane]; } break;
             case BC_IMPLY_SC: if (tos == 0) { tos = 1; pc = arg; } break;
-            case BC_IMPLY_FIN: sp--; l = stk[sp * 32 + lane]; tos = (l <= tos); break;
+            case BC_IMPLY_FIN: sp--; l = stk[sp * LS + lane]; tos = (l <= tos); break;
             default: return 0;
         }
     }
@@ -165,13 +168,31 @@ __device__ bool revise_point(NodeCtx &c, const DevCon &con, int off) {
     const int myvar = lane < n ? M.scope[con.scope_off + lane] : 0;
     const u64 myd = lane < n ? c.dom[myvar * k + off] : 1ull;
     const int dsz = __popcll(myd);
-    u64 prod = (u64)dsz;
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) prod = sat_mul(prod, __shfl_xor_sync(0xffffffffu, prod, s));
-    const long long limit = off == 0 ? M.enum_now : M.enum_ahead;
-    if ((long long)prod > limit) return true;           // skipped: re-armed when a domain of the scope shrinks
+    if (__any_sync(0xffffffffu, myd == 0ull)) return false;
     const unsigned fmask = __ballot_sync(0xffffffffu, lane < n && dsz > 1);
     const int nf = __popc(fmask);
+    if (nf == 0) {
+        // every variable bound: one tuple, evaluated by lane 0 (the exact check every leaf gets)
+        if (lane < n) wm.cur[lane * 32] = M.lb[myvar] + __ffsll((long long)myd) - 1;
+        __syncwarp();
+        int ok = 0;
+        if (lane == 0) ok = eval_tuple<32>(M.code + con.code_off, wm.cur, wm.stk, 0, M);
+        c.tuples += 1;
+        return __shfl_sync(0xffffffffu, ok, 0) != 0;
+    }
+    float pf = (float)dsz;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) pf *= __shfl_xor_sync(0xffffffffu, pf, s);
+    const long long limit = off == 0 ? M.enum_now : M.enum_ahead;
+    if (pf > (float)limit) return true;                 // skipped: re-armed when a domain of the scope shrinks
+    u64 prod;
+    if (pf < 16777216.0f) {
+        prod = (u64)pf;                                 // exact below 2^24
+    } else {
+        prod = (u64)dsz;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) prod = sat_mul(prod, __shfl_xor_sync(0xffffffffu, prod, s));
+    }
     if (lane < n) {
         int j = 0;
         for (u64 w = myd; w; w &= w - 1) wm.vals[lane * 64 + j++] = (uint8_t)(__ffsll((long long)w) - 1);
@@ -211,7 +232,7 @@ __device__ bool revise_point(NodeCtx &c, const DevCon &con, int off) {
     for (u64 tbase = 0; tbase < prod; tbase += 32) {
         const bool active = tbase + lane < prod;
         int ok = 0;
-        if (active) ok = eval_tuple(code, wm.cur, wm.stk, lane, M);
+        if (active) ok = eval_tuple<32>(code, wm.cur, wm.stk, lane, M);
         if (ok) {
             for (int r = 0; r < nf; r++) {
                 const int i = wm.fl[r];
@@ -243,6 +264,175 @@ __device__ bool revise_point(NodeCtx &c, const DevCon &con, int off) {
         const u64 nd = wm.supp[wm.fl[lane]];
         cvar_idx = wm.fdi[lane];
         if (nd != c.dom[cvar_idx]) { c.dom[cvar_idx] = nd; changed = true; }
+    }
+    unsigned cm = __ballot_sync(0xffffffffu, changed);
+    __syncwarp();
+    while (cm) {
+        const int r = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const int idx = __shfl_sync(0xffffffffu, cvar_idx, r);
+        mark_changed(c, idx / k, idx % k);
+    }
+    return true;
+}
+
+// Pointwise constraint with a relation table: the pivot variable's values are handled 64 at a time by one
+// table word per prefix tuple; the lanes walk the prefix tuples over the current domains of the other variables.
+__device__ bool revise_table(NodeCtx &c, const DevCon &con, int off) {
+    const DevModel &M = c.M;
+    WarpMem &wm = c.wm;
+    const int lane = c.lane, n = con.n_scope, k = M.k, pv = con.pivot;
+    const int myvar = lane < n ? M.scope[con.scope_off + lane] : 0;
+    const int mystride = lane < n ? M.stride[con.scope_off + lane] : 0;
+    const u64 myd = lane < n ? c.dom[myvar * k + off] : 1ull;
+    const int dsz = __popcll(myd);
+    const u64 Dp = __shfl_sync(0xffffffffu, myd, pv);
+    if (__any_sync(0xffffffffu, myd == 0ull)) return false;
+    const bool is_pref = lane < n && lane != pv;
+    const bool is_free = is_pref && dsz > 1;
+    const unsigned fmask = __ballot_sync(0xffffffffu, is_free);
+    const int nf = __popc(fmask);
+    // bound prefix variables contribute a constant to the table index
+    const int base = __reduce_add_sync(0xffffffffu, (is_pref && dsz == 1) ? (__ffsll((long long)myd) - 1) * mystride : 0);
+    const u64 *T = M.tables + con.table_off;
+    const int pidx = __shfl_sync(0xffffffffu, myvar, pv) * k + off;
+
+    if (nf <= 2) {
+        // Fast paths: no enumeration state.  The lanes stand for the bit positions of one free variable (two
+        // passes when it is wider than 32); a second free variable is walked value by value, uniformly.
+        int ly = -1, lz = -1;                   // scope slots: y = outer (uniform) variable, z = lane variable
+        if (nf >= 1) lz = __ffs(fmask) - 1;
+        if (nf == 2) {
+            ly = 31 - __clz(fmask);
+            if (__shfl_sync(0xffffffffu, dsz, ly) > __shfl_sync(0xffffffffu, dsz, lz)) { const int t = ly; ly = lz; lz = t; }
+        }
+        const u64 Dz = nf >= 1 ? __shfl_sync(0xffffffffu, myd, lz) : 1ull;
+        const int sz = nf >= 1 ? __shfl_sync(0xffffffffu, mystride, lz) : 0;
+        const u64 Dy = nf == 2 ? __shfl_sync(0xffffffffu, myd, ly) : 1ull;
+        const int sy = nf == 2 ? __shfl_sync(0xffffffffu, mystride, ly) : 0;
+        const int passes = (Dz >> 32) ? 2 : 1;
+        u64 pm = 0ull, supp_z = 0ull, supp_y = 0ull;
+        unsigned long long looked = 0;
+        for (u64 wy = Dy; wy; wy &= wy - 1) {
+            const int py = __ffsll((long long)wy) - 1;
+            bool any_y = false;
+            for (int h = 0; h < passes; h++) {
+                const int pos = lane + 32 * h;
+                u64 m = 0ull;
+                if ((Dz >> pos) & 1ull) m = __ldg(T + base + py * sy + pos * sz) & Dp;
+                const unsigned b = __ballot_sync(0xffffffffu, m != 0ull);
+                supp_z |= (u64)b << (32 * h);
+                any_y |= b != 0u;
+                pm |= m;
+            }
+            if (any_y) supp_y |= 1ull << py;
+            looked += __popcll(Dz);
+        }
+        c.tuples += looked;
+        pm = ((u64)__reduce_or_sync(0xffffffffu, (unsigned)(pm >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (unsigned)pm);
+        if (pm == 0ull) return false;
+        if (pm != Dp) {
+            if (lane == 0) c.dom[pidx] = pm;
+            mark_changed(c, pidx / k, off);
+        }
+        if (nf >= 1 && supp_z != Dz) {
+            const int zi = __shfl_sync(0xffffffffu, myvar, lz);
+            if (lane == 0) c.dom[zi * k + off] = supp_z;
+            mark_changed(c, zi, off);
+        }
+        if (nf == 2 && supp_y != Dy) {
+            const int yi = __shfl_sync(0xffffffffu, myvar, ly);
+            if (lane == 0) c.dom[yi * k + off] = supp_y;
+            mark_changed(c, yi, off);
+        }
+        return true;
+    }
+
+    // General path: mixed-radix walk over the prefix tuples, 32 per step.
+    float pf = is_free ? (float)dsz : 1.0f;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) pf *= __shfl_xor_sync(0xffffffffu, pf, s);
+    const long long limit = off == 0 ? M.enum_now : M.enum_ahead;
+    if (pf > (float)limit) return true;             // skipped: re-armed when a domain of the scope shrinks
+    u64 prod;
+    if (pf < 16777216.0f) {
+        prod = (u64)pf;                             // exact below 2^24
+    } else {
+        prod = is_free ? (u64)dsz : 1ull;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) prod = sat_mul(prod, __shfl_xor_sync(0xffffffffu, prod, s));
+    }
+    if (is_free) {
+        int j = 0;
+        for (u64 w = myd; w; w &= w - 1) wm.vals[lane * 64 + j++] = (uint8_t)(__ffsll((long long)w) - 1);
+        const int r = __popc(fmask & ((1u << lane) - 1u));
+        wm.fl[r] = (uint8_t)lane;
+        wm.fd[r] = (uint8_t)dsz;
+        wm.flb[r] = mystride;
+        wm.fdi[r] = myvar * k + off;
+        wm.supp[r] = 0ull;
+    }
+    __syncwarp();
+    {
+        int t = lane, t32 = 32;
+        for (int r = 0; r < nf; r++) {
+            const int f = wm.fd[r];
+            wm.dig[r * 32 + lane] = (uint8_t)(t % f);
+            t /= f;
+            if (lane == 0) wm.sd[r] = (uint8_t)(t32 % f);
+            t32 /= f;
+        }
+    }
+    __syncwarp();
+    u64 pm = 0ull;
+    bool any = false;
+    u64 done = 0;
+    for (u64 tbase = 0; tbase < prod; tbase += 32) {
+        u64 m = 0ull;
+        if (tbase + lane < prod) {
+            int idx = base;
+            for (int r = 0; r < nf; r++) idx += (int)wm.vals[wm.fl[r] * 64 + wm.dig[r * 32 + lane]] * wm.flb[r];
+            m = __ldg(T + idx) & Dp;
+        }
+        if (m) {
+            pm |= m;
+            for (int r = 0; r < nf; r++) {
+                const u64 bit = 1ull << wm.vals[wm.fl[r] * 64 + wm.dig[r * 32 + lane]];
+                if (!(wm.supp[r] & bit)) atomicOr(&wm.supp[r], bit);
+            }
+        }
+        any |= __ballot_sync(0xffffffffu, m != 0ull) != 0u;
+        done = tbase + 32;
+        if (done >= prod) break;
+        __syncwarp();
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)pm), hi = __reduce_or_sync(0xffffffffu, (unsigned)(pm >> 32));
+        const bool full = lane < nf ? (wm.supp[lane] == c.dom[wm.fdi[lane]]) : true;
+        if ((((u64)hi << 32) | lo) == Dp && __all_sync(0xffffffffu, full)) break;
+        int carry = 0;
+        for (int r = 0; r < nf; r++) {
+            const int f = wm.fd[r];
+            int d = wm.dig[r * 32 + lane] + wm.sd[r] + carry;
+            carry = d >= f;
+            if (carry) d -= f;
+            wm.dig[r * 32 + lane] = (uint8_t)d;
+        }
+    }
+    c.tuples += done < prod ? done : prod;
+    if (!any) return false;
+    __syncwarp();
+    {
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)pm), hi = __reduce_or_sync(0xffffffffu, (unsigned)(pm >> 32));
+        pm = ((u64)hi << 32) | lo;
+    }
+    bool changed = false;
+    int cvar_idx = 0;
+    if (lane < nf) {
+        const u64 nd = wm.supp[lane];
+        cvar_idx = wm.fdi[lane];
+        if (nd != c.dom[cvar_idx]) { c.dom[cvar_idx] = nd; changed = true; }
+    } else if (lane == nf) {
+        cvar_idx = pidx;
+        if (pm != Dp) { c.dom[pidx] = pm; changed = true; }
     }
     unsigned cm = __ballot_sync(0xffffffffu, changed);
     __syncwarp();
@@ -341,7 +531,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const DevMode
             const DevProp pr = M.props[S.prop_off + q];
             const DevCon con = M.cons[pr.con];
             bool ok;
-            if (con.kind == DK_POINT) ok = revise_point(ctx, con, pr.offset);
+            if (con.kind == DK_POINT) ok = con.pivot >= 0 ? revise_table(ctx, con, pr.offset) : revise_point(ctx, con, pr.offset);
             else if (con.kind == DK_NEXT) ok = revise_next(ctx, con);
             else ok = revise_until(ctx, con);
             __syncwarp();
@@ -648,6 +838,32 @@ __global__ void __launch_bounds__(256) rehash_kernel(const DevModel M, int32_t *
     }
 }
 
+// Fill one relation table: thread per entry (prefix tuple over the DECLARED domains), loop over the pivot's values.
+__global__ void __launch_bounds__(128) build_table_kernel(const DevModel M, int32_t con_idx, int32_t entries, u64 *tables) {
+    const DevCon con = M.cons[con_idx];
+    const int n = con.n_scope, pv = con.pivot;
+    int32_t cur[Limits::kMaxScope];
+    int32_t stk[Limits::kMaxStack + 2];
+    const Instr *code = M.code + con.code_off;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < entries; e += gridDim.x * blockDim.x) {
+        int rest = e;
+        for (int i = 0; i < n; i++) {
+            if (i == pv) continue;
+            const int v = M.scope[con.scope_off + i];
+            const int w = M.width[v];
+            cur[i] = M.lb[v] + rest % w;
+            rest /= w;
+        }
+        const int vp = M.scope[con.scope_off + pv];
+        u64 mask = 0ull;
+        for (int b = 0; b < M.width[vp]; b++) {
+            cur[pv] = M.lb[vp] + b;
+            if (eval_tuple<1>(code, cur, stk, 0, M)) mask |= 1ull << b;
+        }
+        tables[con.table_off + e] = mask;
+    }
+}
+
 __global__ void fill_kernel(int32_t *ptr, long long n, int32_t value) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         ptr[i] = value;
@@ -716,6 +932,12 @@ void launch_rehash(const DevModel &m, int32_t *table, long long table_mask, cons
                    long long n_states, int grid, cudaStream_t stream) {
     if (n_states <= 0) return;
     rehash_kernel<<<grid, 256, 0, stream>>>(m, table, table_mask, state_key, n_states);
+}
+
+void launch_build_table(const DevModel &m, int32_t con, int32_t entries, unsigned long long *tables, cudaStream_t stream) {
+    if (entries <= 0) return;
+    const int grid = std::min((entries + 127) / 128, 148 * 8);
+    build_table_kernel<<<grid, 128, 0, stream>>>(m, con, entries, tables);
 }
 
 void launch_fill(int32_t *ptr, long long n, int32_t value, cudaStream_t stream) {

@@ -11,8 +11,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -38,33 +40,121 @@ struct Failure : std::runtime_error {
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// Process-wide cache of device blocks (power-of-two size classes, per device).  cudaMalloc / cudaFree cost
+// 0.3-0.6 ms each on B200 and the stream-ordered pool showed 5-350 ms stalls when it had to grow, so blocks
+// released by one solve are kept and handed to the next: in steady state a solve allocates nothing.
+struct DeviceCache {
+    std::mutex mu;
+    std::map<std::pair<int, size_t>, std::vector<void *>> free_blocks;
+    static size_t size_class(size_t bytes) {
+        size_t c = 4096;
+        while (c < bytes) c <<= 1;
+        return c;
+    }
+    void *acquire(int device, size_t bytes) {       // bytes must be a size class
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = free_blocks.find({device, bytes});
+            if (it != free_blocks.end() && !it->second.empty()) {
+                void *p = it->second.back();
+                it->second.pop_back();
+                return p;
+            }
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {                     // give the cached blocks back to the driver and retry once
+            cudaGetLastError();
+            trim(device);
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            throw Failure(STCSP_ERR_CAPACITY, "device allocation of " + std::to_string(bytes) + " bytes failed: " +
+                                                  cudaGetErrorString(e));
+        }
+        return p;
+    }
+    void give_back(int device, size_t bytes, void *p) {
+        std::lock_guard<std::mutex> g(mu);
+        free_blocks[{device, bytes}].push_back(p);
+    }
+    void trim(int device) {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &kv : free_blocks)
+            if (kv.first.first == device) {
+                for (void *p : kv.second) cudaFree(p);
+                kv.second.clear();
+            }
+    }
+};
+DeviceCache &device_cache() {
+    static DeviceCache *c = new DeviceCache();      // leaked on purpose (no CUDA calls during static destruction)
+    return *c;
+}
+
 template <class T>
 struct DBuf {
     T *p = nullptr;
     size_t cap = 0;     // elements
+    size_t bytes = 0;   // size class of the block
+    int device = 0;
     DBuf() = default;
     DBuf(const DBuf &) = delete;
     DBuf &operator=(const DBuf &) = delete;
-    ~DBuf() { if (p) cudaFree(p); }
+    ~DBuf() { release(); }
+    // The caller guarantees that no work using the block is in flight (the session synchronises its stream first).
+    void release() {
+        if (p) device_cache().give_back(device, bytes, p);
+        p = nullptr;
+        cap = bytes = 0;
+    }
     // at least `need` elements; the first `keep` elements survive a reallocation
     bool reserve(size_t need, size_t keep, cudaStream_t st) {
         if (need <= cap) return false;
-        size_t ncap = std::max(need, cap + cap / 2);
-        T *np = nullptr;
-        cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
-        if (e != cudaSuccess)
-            throw Failure(STCSP_ERR_CAPACITY, "device allocation of " + std::to_string(ncap * sizeof(T)) +
-                                                  " bytes failed: " + cudaGetErrorString(e));
-        if (keep) CK(cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        const size_t nbytes = DeviceCache::size_class(std::max(need, 2 * cap) * sizeof(T));
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        T *np = (T *)device_cache().acquire(dev, nbytes);
         if (p) {
-            CK(cudaStreamSynchronize(st));
-            cudaFree(p);
+            if (keep) CK(cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));          // nothing in flight may still touch the old block
+            device_cache().give_back(device, bytes, p);
         }
         p = np;
-        cap = ncap;
+        cap = nbytes / sizeof(T);
+        bytes = nbytes;
+        device = dev;
         return true;
     }
 };
+
+// Pinned host blocks for the counter read-back, cached per process (cudaMallocHost costs ~1 ms).
+struct PinnedCache {
+    std::mutex mu;
+    std::vector<unsigned long long *> free_blocks;
+    unsigned long long *acquire() {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!free_blocks.empty()) {
+                unsigned long long *b = free_blocks.back();
+                free_blocks.pop_back();
+                return b;
+            }
+        }
+        unsigned long long *b = nullptr;
+        CK(cudaMallocHost(&b, C_COUNT * sizeof(unsigned long long)));
+        return b;
+    }
+    void give_back(unsigned long long *b) {
+        std::lock_guard<std::mutex> g(mu);
+        free_blocks.push_back(b);
+    }
+};
+PinnedCache &pinned_cache() {
+    static PinnedCache *c = new PinnedCache();      // leaked on purpose: outlives the CUDA context teardown order
+    return *c;
+}
 
 struct AutoStore {      // backing storage of a library-owned stcsp_automaton_t
     std::vector<int32_t> sig_vars, state_sig, state_cset, edge_src, edge_dst, edge_label;
@@ -95,7 +185,9 @@ struct stcsp_session {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     DevModel dm{};
     // model pools
-    DBuf<int32_t> d_lb, d_width, d_sigvars, d_scope, d_aux, d_arr_off, d_arr_val;
+    DBuf<int32_t> d_lb, d_width, d_sigvars, d_scope, d_stride, d_aux, d_arr_off, d_arr_val;
+    DBuf<unsigned long long> d_tables;
+    long long tables_built = 0;     // u64 words of the table pool already filled
     DBuf<DevSet> d_sets;
     DBuf<DevCon> d_cons;
     DBuf<DevProp> d_props;
@@ -126,12 +218,23 @@ struct stcsp_session {
     bool timing_open = false;
 
     ~stcsp_session() {
-        if (h_counters) cudaFreeHost(h_counters);
+        if (stream) cudaStreamSynchronize(stream);
+        if (h_counters) pinned_cache().give_back(h_counters);
+        release_all();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (evk0) cudaEventDestroy(evk0);
         if (evk1) cudaEventDestroy(evk1);
         if (stream) cudaStreamDestroy(stream);
+    }
+
+    void release_all() {
+        d_lb.release(); d_width.release(); d_sigvars.release(); d_scope.release(); d_stride.release(); d_aux.release();
+        d_arr_off.release(); d_arr_val.release(); d_tables.release(); d_sets.release(); d_cons.release();
+        d_props.release(); d_code.release(); d_wake.release(); frontier[0].release(); frontier[1].release();
+        leaves.release(); unresolved.release(); gathered.release(); table.release(); state_key.release();
+        edge_src.release(); edge_dst.release(); edge_label.release(); d_capmap.release(); d_capvals.release();
+        counters.release(); d_offsets.release();
     }
 
     template <class T>
@@ -151,6 +254,9 @@ struct stcsp_session {
         upload(d_cons, sets.dev_cons);
         upload(d_props, sets.dev_props);
         upload(d_scope, sets.dev_scope);
+        sets.dev_stride.resize(sets.dev_scope.size(), 0);
+        upload(d_stride, sets.dev_stride);
+        d_tables.reserve((size_t)std::max<long long>(sets.table_words, 1), (size_t)tables_built, stream);
         upload(d_code, sets.dev_code);
         upload(d_wake, sets.dev_wake);
         upload(d_aux, sets.dev_aux);
@@ -178,6 +284,8 @@ struct stcsp_session {
         dm.cons = d_cons.p;
         dm.props = d_props.p;
         dm.scope = d_scope.p;
+        dm.stride = d_stride.p;
+        dm.tables = d_tables.p;
         dm.code = d_code.p;
         dm.wake = d_wake.p;
         dm.aux = d_aux.p;
@@ -186,6 +294,14 @@ struct stcsp_session {
         if (expand_smem_bytes(dm) > 200 * 1024)
             throw Failure(STCSP_ERR_UNSUPPORTED, "model needs more shared memory per CTA than an SM has");
         expand_grid_max = expand_max_grid(dm, sm_count);
+        // fill the relation tables of constraints seen for the first time
+        for (const TableJob &job : sets.table_jobs) {
+            launch_build_table(dm, job.con, sets.dev_cons[job.con].table_entries, d_tables.p, stream);
+            t_launches++;
+        }
+        if (!sets.table_jobs.empty()) CK(cudaGetLastError());
+        sets.table_jobs.clear();
+        tables_built = sets.table_words;
         sets.clear_dirty();
     }
 
@@ -211,9 +327,11 @@ struct stcsp_session {
             launch_rehash(dm, fresh.p, want - 1, state_key.p, n_states, sm_count * 4, stream);
             t_launches++;
         }
-        CK(cudaStreamSynchronize(stream));
         std::swap(table.p, fresh.p);
         std::swap(table.cap, fresh.cap);
+        std::swap(table.bytes, fresh.bytes);
+        std::swap(table.device, fresh.device);
+        CK(cudaStreamSynchronize(stream));      // the old table returns to the cache when `fresh` goes out of scope
         table_size = want;
     }
     void init(const stcsp_problem_t *problem, const stcsp_options_t *options, int r, int w) {
@@ -250,7 +368,7 @@ struct stcsp_session {
         upload_model();
         counters.reserve(C_COUNT, 0, stream);
         CK(cudaMemsetAsync(counters.p, 0, C_COUNT * sizeof(unsigned long long), stream));
-        CK(cudaMallocHost(&h_counters, C_COUNT * sizeof(unsigned long long)));
+        h_counters = pinned_cache().acquire();
         d_offsets.reserve(2 * kMaxWorld, 0, stream);
 
         const int NW = dm.node_words, KW = dm.key_words;
@@ -299,10 +417,15 @@ struct stcsp_session {
         zero_wave_counters();
         if (n_in > 0) {
             const int NW = dm.node_words, RW = dm.rec_words;
+            const double te0 = now_s();
             leaves.reserve((size_t)n_in * RW, 0, stream);
             unresolved.reserve((size_t)n_in, 0, stream);
             DBuf<int32_t> &out = frontier[cur ^ 1];
             out.reserve((size_t)std::max<long long>(2 * n_in, 4096) * NW, 0, stream);
+            if (opt.verbosity > 1) {
+                CK(cudaStreamSynchronize(stream));
+                fprintf(stderr, "[stcsp r%d]   expand reserve %.1f us\n", rank, (now_s() - te0) * 1e6);
+            }
             for (;;) {
                 ExpandArgs ea{};
                 ea.in_nodes = frontier[cur].p;
@@ -325,15 +448,24 @@ struct stcsp_session {
                 ra.unresolved = unresolved.p;
                 ra.unresolved_cap = (long long)unresolved.cap;
                 ra.counters = counters.p;
+                const double te1 = now_s();
+                if (opt.verbosity > 1) CK(cudaStreamSynchronize(stream));
+                const double te2 = now_s();
                 launch_route(dm, ra, (int)std::min<long long>((n_in + 7) / 8, sm_count * 8), stream);
                 CK(cudaGetLastError());
                 read_counters();
+                if (opt.verbosity > 1)
+                    fprintf(stderr, "[stcsp r%d]   expand kernel wall %.1f us, route+read %.1f us\n", rank, (te2 - te1) * 1e6, (now_s() - te2) * 1e6);
                 t_launches += 2;
                 t_expand_launches++;
                 if (opt.profile_kernels) {
                     float ms = 0;
                     CK(cudaEventElapsedTime(&ms, evk0, evk1));
                     expand_ms += ms;
+                    if (opt.verbosity > 0)
+                        fprintf(stderr, "[stcsp r%d] t=%.3f ms wave %lld: in %lld out %llu leaves %llu fails %llu tuples %llu revisions %llu expand %.1f us grid %d\n",
+                                rank, (now_s() - t_create) * 1e3, t_waves, n_in, h_counters[C_OUT], h_counters[C_LEAVES], h_counters[C_FAILS],
+                                h_counters[C_TUPLES], h_counters[C_REVISIONS], ms * 1e3, grid);
                 }
                 const unsigned long long ov = h_counters[C_OVERFLOW];
                 if (ov & 1ull) {        // frontier buffer too small: nothing but scratch was written, run the wave again
@@ -490,6 +622,8 @@ struct stcsp_session {
         if (!inbox) n = world == 1 ? n_leaves : 0;       // single rank: this rank's own leaves, in place
         const int32_t *records = inbox ? inbox : leaves.p;
         DBuf<int32_t> &out = frontier[cur ^ 1];
+        const double tw0 = now_s();
+        double tw1 = tw0, tw2 = tw0;
         if (n > 0) {
             out.reserve((size_t)(n_out + n) * NW, (size_t)n_out * NW, stream);
             state_key.reserve((size_t)(n_states + n) * KW, (size_t)n_states * KW, stream);
@@ -497,6 +631,7 @@ struct stcsp_session {
             edge_dst.reserve((size_t)(n_edges + n), (size_t)n_edges, stream);
             edge_label.reserve((size_t)(n_edges + n) * V, (size_t)n_edges * V, stream);
             ensure_table(n_states + n);
+            tw1 = now_s();
             IngestArgs ia{};
             ia.records = records;
             ia.count = n;
@@ -520,7 +655,11 @@ struct stcsp_session {
             n_states = (long long)h_counters[C_STATES];
             n_edges = (long long)h_counters[C_EDGES];
             t_dominance += (long long)h_counters[C_DOMINANCE];
+            tw2 = now_s();
         }
+        if (opt.verbosity > 1)
+            fprintf(stderr, "[stcsp r%d]   ingest %lld records: reserve %.1f us, kernel+sync %.1f us, states %lld edges %lld table %lld\n",
+                    rank, (long long)n, (tw1 - tw0) * 1e6, (tw2 - tw1) * 1e6, n_states, n_edges, table_size);
         cur ^= 1;
         n_in = n_out;
         n_out = 0;
