@@ -61,7 +61,7 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons while the timed region runs (NVML, 50 ms period)."""
+    """SM clock and throttle reasons while the timed region runs (NVML, 2 ms period)."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -77,13 +77,15 @@ class ClockSampler(threading.Thread):
                      nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
-            while not self.stop_flag:
+            while True:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                if self.stop_flag:
+                    break
+                time.sleep(0.002)
         except Exception as e:      # NVML missing: report it instead of inventing numbers
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 

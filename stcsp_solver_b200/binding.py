@@ -155,9 +155,12 @@ class Model:
             return cls(f.read(), prefix_k)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().stcsp_model_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().stcsp_model_free(self._h)
+                self._h = None
+        except Exception:       # interpreter shutdown: module globals are already gone
+            pass
 
     @property
     def var_names(self) -> List[str]:
@@ -208,9 +211,12 @@ class Automaton:
             "h2d_bytes", "d2h_bytes")}
 
     def __del__(self):
-        if getattr(self, "_free", None):
-            self._free(C.byref(self.c))
-            self._free = None
+        try:
+            if getattr(self, "_free", None):
+                self._free(C.byref(self.c))
+                self._free = None
+        except Exception:
+            pass
 
 
 class Solution:
@@ -240,8 +246,11 @@ class Solution:
         return canonical.parse_dot(self.dot())
 
     def __del__(self):
-        if getattr(self, "c", None) is not None and self.c.impl:
-            lib().stcsp_solution_free(C.byref(self.c))
+        try:
+            if getattr(self, "c", None) is not None and self.c.impl:
+                lib().stcsp_solution_free(C.byref(self.c))
+        except Exception:
+            pass
 
 
 def default_options(**kw) -> Options:
@@ -284,9 +293,12 @@ class Session:
         self.request_words = lib().stcsp_session_request_words(self._h)
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().stcsp_session_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().stcsp_session_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
     __del__ = close
 

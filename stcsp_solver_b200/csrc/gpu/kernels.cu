@@ -481,7 +481,7 @@ __device__ bool revise_until(NodeCtx &c, const DevCon &con) {
     return true;
 }
 
-__global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const DevModel M, const ExpandArgs P) {
+__global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevModel M, const ExpandArgs P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpMem wm = carve(smem + (size_t)warp * warp_bytes(M), M);
@@ -838,10 +838,11 @@ __global__ void __launch_bounds__(256) rehash_kernel(const DevModel M, int32_t *
     }
 }
 
-// Fill one relation table: thread per entry (prefix tuple over the DECLARED domains), loop over the pivot's values.
-__global__ void __launch_bounds__(128) build_table_kernel(const DevModel M, int32_t con_idx, int32_t entries, u64 *tables) {
-    const DevCon con = M.cons[con_idx];
-    const int n = con.n_scope, pv = con.pivot;
+// Fill relation tables: blockIdx.y = job (constraint), thread per entry (prefix tuple over the DECLARED domains),
+// loop over the pivot's values.
+__global__ void __launch_bounds__(128) build_table_kernel(const DevModel M, const int32_t *jobs, u64 *tables) {
+    const DevCon con = M.cons[jobs[blockIdx.y]];
+    const int n = con.n_scope, pv = con.pivot, entries = con.table_entries;
     int32_t cur[Limits::kMaxScope];
     int32_t stk[Limits::kMaxStack + 2];
     const Instr *code = M.code + con.code_off;
@@ -885,8 +886,9 @@ size_t expand_smem_bytes(const DevModel &m) { return warp_bytes(m) * kExpandWarp
 
 static void configure_expand(size_t smem) {
     static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > configured) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(expand_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = smem;
     }
 }
@@ -934,10 +936,11 @@ void launch_rehash(const DevModel &m, int32_t *table, long long table_mask, cons
     rehash_kernel<<<grid, 256, 0, stream>>>(m, table, table_mask, state_key, n_states);
 }
 
-void launch_build_table(const DevModel &m, int32_t con, int32_t entries, unsigned long long *tables, cudaStream_t stream) {
-    if (entries <= 0) return;
-    const int grid = std::min((entries + 127) / 128, 148 * 8);
-    build_table_kernel<<<grid, 128, 0, stream>>>(m, con, entries, tables);
+void launch_build_tables(const DevModel &m, const int32_t *dev_jobs, int n_jobs, int max_entries, unsigned long long *tables,
+                         cudaStream_t stream) {
+    if (n_jobs <= 0) return;
+    dim3 grid((unsigned)std::min((max_entries + 127) / 128, 256), (unsigned)n_jobs);
+    build_table_kernel<<<grid, 128, 0, stream>>>(m, dev_jobs, tables);
 }
 
 void launch_fill(int32_t *ptr, long long n, int32_t value, cudaStream_t stream) {

@@ -118,8 +118,9 @@ void launch_gather(const int32_t *src, const int32_t *list, long long count, int
 void launch_rehash(const DevModel &m, int32_t *table, long long table_mask, const int32_t *state_key,
                    long long n_states, int grid, cudaStream_t stream);
 void launch_fill(int32_t *ptr, long long n, int32_t value, cudaStream_t stream);
-// fill the relation table of constraint `con` (absolute index) by evaluating its bytecode on every tuple
-void launch_build_table(const DevModel &m, int32_t con, int32_t entries, unsigned long long *tables, cudaStream_t stream);
+// fill the relation tables of the constraints dev_jobs[0 .. n_jobs) (absolute indices) by evaluating their bytecode
+void launch_build_tables(const DevModel &m, const int32_t *dev_jobs, int n_jobs, int max_entries, unsigned long long *tables,
+                         cudaStream_t stream);
 
 uint32_t capmap_hash(int cid, const int32_t *vals, int n);
 uint32_t state_key_hash(const int32_t *key, int key_words);

@@ -187,6 +187,7 @@ struct stcsp_session {
     // model pools
     DBuf<int32_t> d_lb, d_width, d_sigvars, d_scope, d_stride, d_aux, d_arr_off, d_arr_val;
     DBuf<unsigned long long> d_tables;
+    DBuf<int32_t> d_jobs;
     long long tables_built = 0;     // u64 words of the table pool already filled
     DBuf<DevSet> d_sets;
     DBuf<DevCon> d_cons;
@@ -230,7 +231,7 @@ struct stcsp_session {
 
     void release_all() {
         d_lb.release(); d_width.release(); d_sigvars.release(); d_scope.release(); d_stride.release(); d_aux.release();
-        d_arr_off.release(); d_arr_val.release(); d_tables.release(); d_sets.release(); d_cons.release();
+        d_arr_off.release(); d_arr_val.release(); d_tables.release(); d_jobs.release(); d_sets.release(); d_cons.release();
         d_props.release(); d_code.release(); d_wake.release(); frontier[0].release(); frontier[1].release();
         leaves.release(); unresolved.release(); gathered.release(); table.release(); state_key.release();
         edge_src.release(); edge_dst.release(); edge_label.release(); d_capmap.release(); d_capvals.release();
@@ -275,8 +276,8 @@ struct stcsp_session {
         dm.max_scope = sets.max_scope();
         dm.max_stack = sets.max_stack();
         dm.max_words = (sets.max_props() + 31) / 32;
-        dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : (1ll << 12);
-        dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : (1ll << 9);
+        dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : 512;
+        dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : 8;
         dm.lb = d_lb.p;
         dm.width = d_width.p;
         dm.sig_vars = d_sigvars.p;
@@ -295,11 +296,19 @@ struct stcsp_session {
             throw Failure(STCSP_ERR_UNSUPPORTED, "model needs more shared memory per CTA than an SM has");
         expand_grid_max = expand_max_grid(dm, sm_count);
         // fill the relation tables of constraints seen for the first time
-        for (const TableJob &job : sets.table_jobs) {
-            launch_build_table(dm, job.con, sets.dev_cons[job.con].table_entries, d_tables.p, stream);
+        if (!sets.table_jobs.empty()) {
+            std::vector<int32_t> jobs;
+            int max_entries = 1;
+            for (const TableJob &job : sets.table_jobs) {
+                jobs.push_back(job.con);
+                max_entries = std::max(max_entries, sets.dev_cons[job.con].table_entries);
+            }
+            upload(d_jobs, jobs);
+            launch_build_tables(dm, d_jobs.p, (int)jobs.size(), max_entries, d_tables.p, stream);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(stream));
             t_launches++;
         }
-        if (!sets.table_jobs.empty()) CK(cudaGetLastError());
         sets.table_jobs.clear();
         tables_built = sets.table_words;
         sets.clear_dirty();
@@ -415,6 +424,7 @@ struct stcsp_session {
         n_leaves = n_unres = 0;
         n_out = 0;
         zero_wave_counters();
+        for (int i = C_OUT; i < C_COUNT; i++) h_counters[i] = 0;       // host mirror of the wave counters
         if (n_in > 0) {
             const int NW = dm.node_words, RW = dm.rec_words;
             const double te0 = now_s();
