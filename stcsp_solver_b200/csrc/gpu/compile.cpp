@@ -285,6 +285,9 @@ void SetTable::compile_set(int32_t s) {
     };
     std::stable_sort(dev_props.begin() + ds.prop_off, dev_props.end(),
                      [&](const DevProp &a, const DevProp &b) { return cost(a) < cost(b); });
+    ds.n_cheap = 0;
+    for (int32_t q = 0; q < ds.n_prop; q++)
+        if (cost(dev_props[ds.prop_off + q]) < (1ll << 40)) ds.n_cheap = q + 1;
     ds.n_words = std::max(1, (ds.n_prop + 31) / 32);
     max_props_ = std::max(max_props_, ds.n_prop);
     ds.wake_off = (int32_t)dev_wake.size();

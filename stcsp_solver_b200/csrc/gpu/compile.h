@@ -70,7 +70,7 @@ struct DevSet {            // one constraint set
     int32_t n_until, until_off;    // right-hand variable of each until constraint (into aux pool)
     int32_t n_next, next_off;      // (x, y) pairs of the NEXT constraints (into aux pool)
     int32_t max_stack;
-    int32_t pad;
+    int32_t n_cheap;       // propagators [0, n_cheap) are NEXT / UNTIL / relation tables, the rest enumerate bytecode
 };
 
 struct HostSet {

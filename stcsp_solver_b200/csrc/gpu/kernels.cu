@@ -33,10 +33,14 @@ namespace {
 typedef unsigned long long u64;
 
 struct WarpMem {
+    // node-group state: private to a warp (warp-per-node mode) or shared by the CTA (CTA-per-node mode)
     int32_t *nodew;     // node words (header + domains)
-    uint32_t *dirty;    // propagator bitmask
+    uint32_t *dirty;    // propagator bitmask: to be revised
+    uint32_t *dcur;     // CTA mode: the propagators of the current round
+    int32_t *flag;      // [0] wipe-out, [1] propagators in the current round, [2..3] broadcast of the child base index
+    // per-warp scratch of the revision in flight
     u64 *supp;          // [max_scope] support sets of the constraint being revised
-    int32_t *flb;       // [max_scope] lb of free variable r
+    int32_t *flb;       // [max_scope] lb (bytecode) / table stride of free variable r
     int32_t *fdi;       // [max_scope] domain index (var*k+off) of free variable r
     int32_t *cur;       // [max_scope][32] current tuple values per lane
     int32_t *stk;       // [max_stack+1][32] evaluator stack per lane
@@ -47,10 +51,12 @@ struct WarpMem {
 
 __host__ __device__ inline size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
 
-__host__ __device__ inline size_t warp_bytes(const DevModel &m) {
+__host__ __device__ inline size_t node_bytes(const DevModel &m) {
+    return align8((size_t)m.node_words * 4) + 2 * align8((size_t)m.max_words * 4) + 16;
+}
+
+__host__ __device__ inline size_t scratch_bytes(const DevModel &m) {
     size_t b = 0;
-    b += align8((size_t)m.node_words * 4);
-    b += align8((size_t)m.max_words * 4);
     b += (size_t)m.max_scope * 8;
     b += align8((size_t)m.max_scope * 4) * 2;
     b += (size_t)m.max_scope * 32 * 4;
@@ -61,11 +67,15 @@ __host__ __device__ inline size_t warp_bytes(const DevModel &m) {
     return align8(b);
 }
 
-__device__ inline WarpMem carve(unsigned char *base, const DevModel &m) {
+// layout of a CTA's dynamic shared memory: kExpandWarps node blocks, then kExpandWarps scratch blocks
+__device__ inline WarpMem carve(unsigned char *smem, const DevModel &m, int node_slot, int warp) {
     WarpMem w;
-    unsigned char *p = base;
+    unsigned char *p = smem + (size_t)node_slot * node_bytes(m);
     w.nodew = (int32_t *)p; p += align8((size_t)m.node_words * 4);
     w.dirty = (uint32_t *)p; p += align8((size_t)m.max_words * 4);
+    w.dcur = (uint32_t *)p; p += align8((size_t)m.max_words * 4);
+    w.flag = (int32_t *)p;
+    p = smem + (size_t)kExpandWarps * node_bytes(m) + (size_t)warp * scratch_bytes(m);
     w.supp = (u64 *)p; p += (size_t)m.max_scope * 8;
     w.flb = (int32_t *)p; p += align8((size_t)m.max_scope * 4);
     w.fdi = (int32_t *)p; p += align8((size_t)m.max_scope * 4);
@@ -144,6 +154,10 @@ __device__ __forceinline__ u64 sat_mul(u64 a, u64 b) {
     return p > cap ? cap : p;
 }
 
+__device__ __forceinline__ u64 reduce_or64(u64 v) {
+    return ((u64)__reduce_or_sync(0xffffffffu, (unsigned)(v >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (unsigned)v);
+}
+
 struct NodeCtx {
     const DevModel &M;
     const DevSet &S;
@@ -154,13 +168,67 @@ struct NodeCtx {
     unsigned long long tuples;
 };
 
+// A domain of (var, off) shrank: every propagator watching it must run (again).
+template <bool CTA>
 __device__ __forceinline__ void mark_changed(NodeCtx &c, int var, int off) {
     const uint32_t *wk = c.M.wake + c.S.wake_off + ((size_t)var * c.M.k + off) * c.S.n_words;
-    for (int w = c.lane; w < c.S.n_words; w += 32) c.wm.dirty[w] |= wk[w];
+    for (int w = c.lane; w < c.S.n_words; w += 32) {
+        const uint32_t m = wk[w];
+        if (CTA) { if (m) atomicOr(&c.wm.dirty[w], m); }
+        else c.wm.dirty[w] |= m;
+    }
     __syncwarp();
 }
 
-// Pointwise constraint at one time offset.  Returns false on wipe-out.
+// Intersect domain `idx` with `nd` (warp-uniform arguments).  Domains only ever shrink, and they are only
+// written through atomicAnd, so warps of one CTA may revise different propagators of the same node at once:
+// a revision that read a stale (larger) domain merely prunes less, and the shrink that it missed re-arms it.
+// Returns false on wipe-out.
+template <bool CTA>
+__device__ __forceinline__ bool shrink_dom(NodeCtx &c, int idx, u64 nd) {
+    u64 old;
+    if (CTA) {
+        old = 0ull;
+        if (c.lane == 0) old = atomicAnd(&c.dom[idx], nd);
+        old = __shfl_sync(0xffffffffu, old, 0);
+    } else {                                            // the warp owns the node: plain read-modify-write
+        old = c.dom[idx];
+        __syncwarp();
+        if (c.lane == 0) c.dom[idx] = old & nd;
+    }
+    const u64 now = old & nd;
+    if (now == 0ull) return false;
+    if (now != old) mark_changed<CTA>(c, idx / c.M.k, idx % c.M.k);
+    else __syncwarp();
+    return true;
+}
+
+// Per-lane variant: lanes with `mine` set hold (idx, nd) of different domains.  Returns false on wipe-out.
+template <bool CTA>
+__device__ __forceinline__ bool shrink_doms(NodeCtx &c, bool mine, int idx, u64 nd) {
+    bool changed = false, wiped = false;
+    if (mine) {
+        u64 old;
+        if (CTA) old = atomicAnd(&c.dom[idx], nd);
+        else { old = c.dom[idx]; c.dom[idx] = old & nd; }       // distinct domains per lane
+        const u64 now = old & nd;
+        wiped = now == 0ull;
+        changed = now != old;
+    }
+    if (__any_sync(0xffffffffu, wiped)) return false;
+    unsigned cm = __ballot_sync(0xffffffffu, changed);
+    while (cm) {
+        const int r = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const int i = __shfl_sync(0xffffffffu, idx, r);
+        mark_changed<CTA>(c, i / c.M.k, i % c.M.k);
+    }
+    __syncwarp();
+    return true;
+}
+
+// Pointwise constraint at one time offset, bytecode enumeration.  Returns false on wipe-out.
+template <bool CTA>
 __device__ bool revise_point(NodeCtx &c, const DevCon &con, int off) {
     const DevModel &M = c.M;
     WarpMem &wm = c.wm;
@@ -229,6 +297,9 @@ __device__ bool revise_point(NodeCtx &c, const DevCon &con, int off) {
     const Instr *code = M.code + con.code_off;
     bool any = false;
     u64 done = 0;
+    // the domains as this revision saw them (another warp may shrink them meanwhile)
+    const u64 seen_sh = __shfl_sync(0xffffffffu, myd, wm.fl[lane < nf ? lane : 0]);
+    const u64 seen = lane < nf ? seen_sh : 0ull;
     for (u64 tbase = 0; tbase < prod; tbase += 32) {
         const bool active = tbase + lane < prod;
         int ok = 0;
@@ -243,7 +314,7 @@ __device__ bool revise_point(NodeCtx &c, const DevCon &con, int off) {
         any |= __ballot_sync(0xffffffffu, ok) != 0u;
         done = tbase + 32;
         __syncwarp();
-        const bool full = lane < nf ? (wm.supp[wm.fl[lane]] == c.dom[wm.fdi[lane]]) : true;
+        const bool full = lane < nf ? (wm.supp[wm.fl[lane]] == seen) : true;
         if (any && __all_sync(0xffffffffu, full)) break;    // every value already supported: nothing to prune
         int carry = 0;
         for (int r = 0; r < nf; r++) {
@@ -258,26 +329,13 @@ __device__ bool revise_point(NodeCtx &c, const DevCon &con, int off) {
     }
     c.tuples += done < prod ? done : prod;
     if (!any) return false;
-    bool changed = false;
-    int cvar_idx = 0;
-    if (lane < nf) {
-        const u64 nd = wm.supp[wm.fl[lane]];
-        cvar_idx = wm.fdi[lane];
-        if (nd != c.dom[cvar_idx]) { c.dom[cvar_idx] = nd; changed = true; }
-    }
-    unsigned cm = __ballot_sync(0xffffffffu, changed);
     __syncwarp();
-    while (cm) {
-        const int r = __ffs(cm) - 1;
-        cm &= cm - 1;
-        const int idx = __shfl_sync(0xffffffffu, cvar_idx, r);
-        mark_changed(c, idx / k, idx % k);
-    }
-    return true;
+    return shrink_doms<CTA>(c, lane < nf, lane < nf ? wm.fdi[lane] : 0, lane < nf ? wm.supp[wm.fl[lane]] : 0ull);
 }
 
 // Pointwise constraint with a relation table: the pivot variable's values are handled 64 at a time by one
 // table word per prefix tuple; the lanes walk the prefix tuples over the current domains of the other variables.
+template <bool CTA>
 __device__ bool revise_table(NodeCtx &c, const DevCon &con, int off) {
     const DevModel &M = c.M;
     WarpMem &wm = c.wm;
@@ -329,22 +387,11 @@ __device__ bool revise_table(NodeCtx &c, const DevCon &con, int off) {
             looked += __popcll(Dz);
         }
         c.tuples += looked;
-        pm = ((u64)__reduce_or_sync(0xffffffffu, (unsigned)(pm >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (unsigned)pm);
+        pm = reduce_or64(pm);
         if (pm == 0ull) return false;
-        if (pm != Dp) {
-            if (lane == 0) c.dom[pidx] = pm;
-            mark_changed(c, pidx / k, off);
-        }
-        if (nf >= 1 && supp_z != Dz) {
-            const int zi = __shfl_sync(0xffffffffu, myvar, lz);
-            if (lane == 0) c.dom[zi * k + off] = supp_z;
-            mark_changed(c, zi, off);
-        }
-        if (nf == 2 && supp_y != Dy) {
-            const int yi = __shfl_sync(0xffffffffu, myvar, ly);
-            if (lane == 0) c.dom[yi * k + off] = supp_y;
-            mark_changed(c, yi, off);
-        }
+        if (pm != Dp && !shrink_dom<CTA>(c, pidx, pm)) return false;
+        if (nf >= 1 && supp_z != Dz && !shrink_dom<CTA>(c, __shfl_sync(0xffffffffu, myvar, lz) * k + off, supp_z)) return false;
+        if (nf == 2 && supp_y != Dy && !shrink_dom<CTA>(c, __shfl_sync(0xffffffffu, myvar, ly) * k + off, supp_y)) return false;
         return true;
     }
 
@@ -373,6 +420,8 @@ __device__ bool revise_table(NodeCtx &c, const DevCon &con, int off) {
         wm.supp[r] = 0ull;
     }
     __syncwarp();
+    const u64 seen_sh = __shfl_sync(0xffffffffu, myd, wm.fl[lane < nf ? lane : 0]);
+    const u64 seen = lane < nf ? seen_sh : 0ull;
     {
         int t = lane, t32 = 32;
         for (int r = 0; r < nf; r++) {
@@ -405,9 +454,8 @@ __device__ bool revise_table(NodeCtx &c, const DevCon &con, int off) {
         done = tbase + 32;
         if (done >= prod) break;
         __syncwarp();
-        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)pm), hi = __reduce_or_sync(0xffffffffu, (unsigned)(pm >> 32));
-        const bool full = lane < nf ? (wm.supp[lane] == c.dom[wm.fdi[lane]]) : true;
-        if ((((u64)hi << 32) | lo) == Dp && __all_sync(0xffffffffu, full)) break;
+        const bool full = lane < nf ? (wm.supp[lane] == seen) : true;
+        if (reduce_or64(pm) == Dp && __all_sync(0xffffffffu, full)) break;
         int carry = 0;
         for (int r = 0; r < nf; r++) {
             const int f = wm.fd[r];
@@ -420,33 +468,16 @@ __device__ bool revise_table(NodeCtx &c, const DevCon &con, int off) {
     c.tuples += done < prod ? done : prod;
     if (!any) return false;
     __syncwarp();
-    {
-        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)pm), hi = __reduce_or_sync(0xffffffffu, (unsigned)(pm >> 32));
-        pm = ((u64)hi << 32) | lo;
-    }
-    bool changed = false;
-    int cvar_idx = 0;
-    if (lane < nf) {
-        const u64 nd = wm.supp[lane];
-        cvar_idx = wm.fdi[lane];
-        if (nd != c.dom[cvar_idx]) { c.dom[cvar_idx] = nd; changed = true; }
-    } else if (lane == nf) {
-        cvar_idx = pidx;
-        if (pm != Dp) { c.dom[pidx] = pm; changed = true; }
-    }
-    unsigned cm = __ballot_sync(0xffffffffu, changed);
-    __syncwarp();
-    while (cm) {
-        const int r = __ffs(cm) - 1;
-        cm &= cm - 1;
-        const int idx = __shfl_sync(0xffffffffu, cvar_idx, r);
-        mark_changed(c, idx / k, idx % k);
-    }
-    return true;
+    pm = reduce_or64(pm);
+    const bool mine = lane <= nf;
+    const int idx = lane < nf ? wm.fdi[lane] : pidx;
+    const u64 nd = lane < nf ? wm.supp[lane] : pm;
+    return shrink_doms<CTA>(c, mine, idx, nd);
 }
 
 // x == next y: values of y at offset p+1 are the values of x at offset p (reference
 // enforceNextConsistency, src/solveralgorithm.cpp:544-593).
+template <bool CTA>
 __device__ bool revise_next(NodeCtx &c, const DevCon &con) {
     const DevModel &M = c.M;
     const int k = M.k, x = con.x, y = con.y;
@@ -456,15 +487,8 @@ __device__ bool revise_next(NodeCtx &c, const DevCon &con) {
         const u64 nX = X & shift_bits(Y, -s) & width_mask(M.width[x]);
         const u64 nY = Y & shift_bits(X, s) & width_mask(M.width[y]);
         if (nX == 0ull || nY == 0ull) return false;
-        __syncwarp();
-        if (nX != X) {
-            if (c.lane == 0) c.dom[x * k + p] = nX;
-            mark_changed(c, x, p);
-        }
-        if (nY != Y) {
-            if (c.lane == 0) c.dom[y * k + p + 1] = nY;
-            mark_changed(c, y, p + 1);
-        }
+        if (nX != X && !shrink_dom<CTA>(c, x * k + p, nX)) return false;
+        if (nY != Y && !shrink_dom<CTA>(c, y * k + p + 1, nY)) return false;
     }
     return true;
 }
@@ -481,19 +505,39 @@ __device__ bool revise_until(NodeCtx &c, const DevCon &con) {
     return true;
 }
 
+template <bool CTA>
+__device__ __forceinline__ bool revise(NodeCtx &c, int q) {
+    const DevProp pr = c.M.props[c.S.prop_off + q];
+    const DevCon con = c.M.cons[pr.con];
+    if (con.kind == DK_POINT)
+        return con.pivot >= 0 ? revise_table<CTA>(c, con, pr.offset) : revise_point<CTA>(c, con, pr.offset);
+    if (con.kind == DK_NEXT) return revise_next<CTA>(c, con);
+    return revise_until(c, con);
+}
+
+// CTA = true : one CTA per search node, its warps revise different dirty propagators of the node concurrently
+//              (narrow waves: fewer nodes than resident CTAs, the latency of one node is the wave's duration).
+// CTA = false: one warp per search node (wide waves: throughput).
+template <bool CTA>
 __global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevModel M, const ExpandArgs P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpMem wm = carve(smem + (size_t)warp * warp_bytes(M), M);
+    WarpMem wm = carve(smem, M, CTA ? 0 : warp, warp);
     const long long n_in = P.n_in;
-    const long long total_warps = (long long)gridDim.x * kExpandWarps;
+    const long long first = CTA ? (long long)blockIdx.x : (long long)blockIdx.x * kExpandWarps + warp;
+    const long long step = CTA ? (long long)gridDim.x : (long long)gridDim.x * kExpandWarps;
     const int V = M.V, k = M.k, NW = M.node_words;
+    const int gwarps = CTA ? kExpandWarps : 1;          // warps working on one node
+    const int gw = CTA ? warp : 0;                      // this warp's index among them
+    const int gtid = CTA ? threadIdx.x : lane, gthreads = gwarps * 32;
     unsigned long long st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0;
 
-    for (long long ni = (long long)blockIdx.x * kExpandWarps + warp; ni < n_in; ni += total_warps) {
+    for (long long ni = first; ni < n_in; ni += step) {
         const int32_t *src = P.in_nodes + ni * NW;
-        for (int w = lane; w < NW; w += 32) wm.nodew[w] = src[w];
-        __syncwarp();
+        if (CTA) __syncthreads();                       // the previous node's shared state is no longer in use
+        for (int w = gtid; w < NW; w += gthreads) wm.nodew[w] = src[w];
+        if (gtid == 0) wm.flag[0] = 0;
+        if (CTA) __syncthreads(); else __syncwarp();
         const int cid = wm.nodew[1], bvar = wm.nodew[3];
         const DevSet S = M.sets[cid];
         NodeCtx ctx{M, S, wm, reinterpret_cast<u64 *>(wm.nodew + 4), lane, wm.nodew[2], 0ull};
@@ -503,7 +547,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevM
         for (int i = lane; i < V * k; i += 32) empty |= dom[i] == 0ull;
         bool fail = __any_sync(0xffffffffu, empty);
 
-        for (int w = lane; w < S.n_words; w += 32) {
+        for (int w = gtid; w < S.n_words; w += gthreads) {
             uint32_t m;
             if (bvar < 0) {
                 const int left = S.n_prop - w * 32;
@@ -513,36 +557,75 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevM
             }
             wm.dirty[w] = m;
         }
-        __syncwarp();
+        if (CTA) __syncthreads(); else __syncwarp();
 
-        while (!fail) {
-            int q = -1;
-            for (int base = 0; base < S.n_words; base += 32) {
-                const uint32_t w = base + lane < S.n_words ? wm.dirty[base + lane] : 0u;
-                const unsigned b = __ballot_sync(0xffffffffu, w != 0u);
-                if (b) {
-                    const int l = __ffs(b) - 1;
-                    const uint32_t ww = __shfl_sync(0xffffffffu, w, l);
-                    q = (base + l) * 32 + __ffs(ww) - 1;
-                    break;
+        if (!CTA) {
+            // Gauss-Seidel: always the cheapest dirty propagator next
+            while (!fail) {
+                int q = -1;
+                for (int base = 0; base < S.n_words; base += 32) {
+                    const uint32_t w = base + lane < S.n_words ? wm.dirty[base + lane] : 0u;
+                    const unsigned b = __ballot_sync(0xffffffffu, w != 0u);
+                    if (b) {
+                        const int l = __ffs(b) - 1;
+                        const uint32_t ww = __shfl_sync(0xffffffffu, w, l);
+                        q = (base + l) * 32 + __ffs(ww) - 1;
+                        break;
+                    }
                 }
+                if (q < 0) break;
+                const bool ok = revise<false>(ctx, q);
+                __syncwarp();
+                if (lane == 0) wm.dirty[q >> 5] &= ~(1u << (q & 31));                // revisions are idempotent
+                __syncwarp();
+                st_rev++;
+                fail = !ok;
             }
-            if (q < 0) break;
-            const DevProp pr = M.props[S.prop_off + q];
-            const DevCon con = M.cons[pr.con];
-            bool ok;
-            if (con.kind == DK_POINT) ok = con.pivot >= 0 ? revise_table(ctx, con, pr.offset) : revise_point(ctx, con, pr.offset);
-            else if (con.kind == DK_NEXT) ok = revise_next(ctx, con);
-            else ok = revise_until(ctx, con);
-            __syncwarp();
-            if (lane == 0) wm.dirty[q >> 5] &= ~(1u << (q & 31));   // revisions are idempotent
-            __syncwarp();
-            st_rev++;
-            fail = !ok;
+        } else {
+            // Rounds: the dirty propagators of one cost class are dealt to the warps; whatever they wake runs in a
+            // later round.  Cheap propagators (NEXT, UNTIL, relation tables) always go before bytecode enumerations.
+            while (!fail) {         // `fail` is uniform over the CTA here (every warp looked at the same domains)
+                if (threadIdx.x == 0) {
+                    bool cheap = false;
+                    for (int w = 0; w < S.n_words; w++) {
+                        const int left = S.n_cheap - w * 32;
+                        const uint32_t cm = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+                        cheap |= (wm.dirty[w] & cm) != 0u;
+                    }
+                    int total = 0;
+                    for (int w = 0; w < S.n_words; w++) {
+                        const int left = S.n_cheap - w * 32;
+                        const uint32_t cm = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+                        const uint32_t take = cheap ? (wm.dirty[w] & cm) : wm.dirty[w];
+                        wm.dcur[w] = take;
+                        wm.dirty[w] &= ~take;
+                        total += __popc(take);
+                    }
+                    wm.flag[1] = total;
+                }
+                __syncthreads();
+                if (wm.flag[1] == 0 || wm.flag[0] != 0) break;
+                int seen_bits = 0;
+                bool ok = true;
+                for (int w = 0; ok && w < S.n_words; w++) {
+                    uint32_t bits = wm.dcur[w];
+                    while (ok && bits) {
+                        const int b = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        if ((seen_bits++ % kExpandWarps) != gw) continue;
+                        ok = revise<true>(ctx, w * 32 + b);
+                        __syncwarp();
+                        st_rev++;
+                    }
+                }
+                if (!ok && lane == 0) wm.flag[0] = 1;
+                __syncthreads();
+            }
+            fail = fail || wm.flag[0] != 0;
         }
-        st_nodes++;
         st_tuples += ctx.tuples;
-        if (fail) { st_fails++; continue; }
+        if (gw == 0) st_nodes++;
+        if (fail) { if (gw == 0) st_fails++; continue; }
 
         int bv = -1;
         for (int base = 0; base < V; base += 32) {
@@ -553,6 +636,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevM
         }
         if (bv < 0) {
             // leaf: every variable bound at the current time point
+            if (gw != 0) continue;
             unsigned long long li = 0;
             if (lane == 0) li = atomicAdd(&P.counters[C_LEAVES], 1ull);
             li = __shfl_sync(0xffffffffu, li, 0);
@@ -567,15 +651,26 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevM
             const u64 D = dom[bv * k];
             const int d = __popcll(D);
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&P.counters[C_OUT], (unsigned long long)d);
-            base = __shfl_sync(0xffffffffu, base, 0);
+            if (CTA) {
+                if (threadIdx.x == 0) {
+                    const unsigned long long b0 = atomicAdd(&P.counters[C_OUT], (unsigned long long)d);
+                    wm.flag[2] = (int)(b0 & 0xffffffffull);
+                    wm.flag[3] = (int)(b0 >> 32);
+                }
+                __syncthreads();
+                base = ((unsigned long long)(unsigned)wm.flag[3] << 32) | (unsigned)wm.flag[2];
+            } else {
+                if (lane == 0) base = atomicAdd(&P.counters[C_OUT], (unsigned long long)d);
+                base = __shfl_sync(0xffffffffu, base, 0);
+            }
             if ((long long)(base + d) > P.out_cap) {
-                if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
+                if (gtid == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
                 continue;
             }
             const int dw = 4 + 2 * (bv * k);
             int j = 0;
             for (u64 w = D; w; w &= w - 1, j++) {
+                if ((j % gwarps) != gw) continue;
                 const u64 one = w & (~w + 1ull);
                 int32_t *dst = P.out_nodes + (base + j) * NW;
                 for (int i = lane; i < NW; i += 32) {
@@ -588,8 +683,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevM
             }
         }
     }
-    if (lane == 0 && st_nodes) {
-        atomicAdd(&P.counters[C_NODES], st_nodes);
+    if (lane == 0 && (st_nodes | st_tuples | st_rev)) {
+        if (st_nodes) atomicAdd(&P.counters[C_NODES], st_nodes);
         if (st_fails) atomicAdd(&P.counters[C_FAILS], st_fails);
         if (st_tuples) atomicAdd(&P.counters[C_TUPLES], st_tuples);
         if (st_rev) atomicAdd(&P.counters[C_REVISIONS], st_rev);
@@ -882,13 +977,17 @@ uint32_t state_key_hash(const int32_t *key, int key_words) {
 
 int32_t owner_of_hash(uint32_t h, int32_t world) { return world > 1 ? (int32_t)(owner_hash(h) % (uint32_t)world) : 0; }
 
-size_t expand_smem_bytes(const DevModel &m) { return warp_bytes(m) * kExpandWarps; }
+size_t expand_smem_bytes(const DevModel &m) { return (node_bytes(m) + scratch_bytes(m)) * kExpandWarps; }
 
 static void configure_expand(size_t smem) {
     static size_t configured = 0;
     if (smem > configured) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(expand_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (smem > 48 * 1024) {
+            cudaFuncSetAttribute(expand_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(expand_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        cudaFuncSetAttribute(expand_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(expand_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = smem;
     }
 }
@@ -897,16 +996,17 @@ int expand_max_grid(const DevModel &m, int sm_count) {
     const size_t smem = expand_smem_bytes(m);
     configure_expand(smem);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_kernel, kExpandWarps * 32, smem) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_kernel<false>, kExpandWarps * 32, smem) != cudaSuccess ||
         per_sm < 1)
         per_sm = 1;
     return per_sm * sm_count;
 }
 
-void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, cudaStream_t stream) {
+void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, bool cta_per_node, cudaStream_t stream) {
     const size_t smem = expand_smem_bytes(m);
     configure_expand(smem);
-    expand_kernel<<<grid, kExpandWarps * 32, smem, stream>>>(m, a);
+    if (cta_per_node) expand_kernel<true><<<grid, kExpandWarps * 32, smem, stream>>>(m, a);
+    else expand_kernel<false><<<grid, kExpandWarps * 32, smem, stream>>>(m, a);
 }
 
 void launch_route(const DevModel &m, const RouteArgs &a, int grid, cudaStream_t stream) {

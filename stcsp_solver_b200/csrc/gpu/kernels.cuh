@@ -105,7 +105,8 @@ constexpr int kExpandWarps = 8;      // warps per CTA of the expand kernel
 
 size_t expand_smem_bytes(const DevModel &m);
 int expand_max_grid(const DevModel &m, int sm_count);      // resident CTAs of the expand kernel on this device
-void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, cudaStream_t stream);
+// cta_per_node: one CTA (8 warps) per search node instead of one warp -- for waves narrower than the GPU
+void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, bool cta_per_node, cudaStream_t stream);
 void launch_route(const DevModel &m, const RouteArgs &a, int grid, cudaStream_t stream);
 void launch_ingest(const DevModel &m, const IngestArgs &a, int grid, cudaStream_t stream);
 // group the routed local leaves by owner rank into `outbox` (dev_offsets = exclusive prefix of the owner counts)

@@ -445,9 +445,12 @@ struct stcsp_session {
                 ea.leaves = leaves.p;
                 ea.leaf_cap = (long long)(leaves.cap / RW);
                 ea.counters = counters.p;
-                const int grid = (int)std::min<long long>((n_in + kExpandWarps - 1) / kExpandWarps, expand_grid_max);
+                // narrow wave: a whole CTA per node (intra-node parallelism); wide wave: a warp per node
+                const bool cta_mode = n_in <= 3ll * expand_grid_max;
+                const int grid = cta_mode ? (int)std::min<long long>(n_in, expand_grid_max)
+                                          : (int)std::min<long long>((n_in + kExpandWarps - 1) / kExpandWarps, expand_grid_max);
                 if (opt.profile_kernels) CK(cudaEventRecord(evk0, stream));
-                launch_expand(dm, ea, grid, stream);
+                launch_expand(dm, ea, grid, cta_mode, stream);
                 if (opt.profile_kernels) CK(cudaEventRecord(evk1, stream));
                 RouteArgs ra{};
                 ra.leaves = leaves.p;
