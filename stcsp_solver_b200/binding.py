@@ -179,28 +179,30 @@ class Model:
         return _take_string(lib().stcsp_model_dump(self._h))
 
 
-def _np(ptr, n, dtype):
+def _np(ptr, n, dtype, copy=True):
     if n == 0:
         return np.zeros(0, dtype=dtype)
-    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+    a = np.ctypeslib.as_array(ptr, shape=(n,))
+    return a.astype(dtype, copy=True) if copy else a
 
 
 class Automaton:
     """Owner of one ``stcsp_automaton_t`` plus numpy copies of its arrays."""
 
-    def __init__(self, c_struct: AutomatonC, free_fn):
+    def __init__(self, c_struct: AutomatonC, free_fn, copy: bool = False):
+        """`copy=False`: the numpy arrays are views into the library-owned automaton (valid while this object lives)."""
         self.c = c_struct
         self._free = free_fn
         a = c_struct
         self.n_vars, self.sig_len = a.n_vars, a.sig_len
         self.n_states, self.n_edges = a.n_states, a.n_edges
-        self.sig_vars = _np(a.sig_vars, a.n_sig_vars, np.int32)
-        self.state_sig = _np(a.state_sig, a.n_states * a.sig_len, np.int32).reshape(a.n_states, a.sig_len)
-        self.state_cset = _np(a.state_cset, a.n_states, np.int32)
-        self.state_failed = _np(a.state_failed, a.n_states, np.uint8)
-        self.edge_src = _np(a.edge_src, a.n_edges, np.int32)
-        self.edge_dst = _np(a.edge_dst, a.n_edges, np.int32)
-        self.edge_label = _np(a.edge_label, a.n_edges * a.n_vars, np.int32).reshape(a.n_edges, a.n_vars)
+        self.sig_vars = _np(a.sig_vars, a.n_sig_vars, np.int32, copy)
+        self.state_sig = _np(a.state_sig, a.n_states * a.sig_len, np.int32, copy).reshape(a.n_states, a.sig_len)
+        self.state_cset = _np(a.state_cset, a.n_states, np.int32, copy)
+        self.state_failed = _np(a.state_failed, a.n_states, np.uint8, copy)
+        self.edge_src = _np(a.edge_src, a.n_edges, np.int32, copy)
+        self.edge_dst = _np(a.edge_dst, a.n_edges, np.int32, copy)
+        self.edge_label = _np(a.edge_label, a.n_edges * a.n_vars, np.int32, copy).reshape(a.n_edges, a.n_vars)
 
     def stats(self) -> dict:
         a = self.c

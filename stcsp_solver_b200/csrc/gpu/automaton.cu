@@ -1,0 +1,152 @@
+// Device-side finishing of the automaton (single-rank path): group the edges by source state, apply the fail
+// rule as a greatest fixpoint, and compact -- so that the host receives the final arrays in one copy.
+//
+//   reference                                              here
+//   vertexAddEdge (src/graph.cpp:33-38): per-vertex lists   counting sort of the edge store by source id
+//   fail marking  (src/solveralgorithm.cpp:865-868,904-910) trim_step_kernel iterated to a fixpoint: a state is
+//       failed iff it has no edge into a non-failed state;   failed without live out-edges; edges into failed
+//       no edge into a failed state is ever kept             states die, which may fail their sources in turn
+#include <cuda_runtime.h>
+
+#include <cub/device/device_scan.cuh>
+
+#include "kernels.cuh"
+
+namespace stcsp {
+
+namespace {
+
+__global__ void __launch_bounds__(256) edge_count_kernel(const int32_t *src, long long n, int32_t *deg) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&deg[src[e]], 1);
+}
+
+// one warp per edge: claim a slot in the source's range, copy (src, dst, label)
+__global__ void __launch_bounds__(256) edge_scatter_kernel(const int32_t *src, const int32_t *dst, const int32_t *label,
+                                                           long long n, int V, const int32_t *first, int32_t *fill,
+                                                           int32_t *osrc, int32_t *odst, int32_t *olabel) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long e = warp_id; e < n; e += total_warps) {
+        const int s = src[e];
+        int pos = 0;
+        if (lane == 0) pos = first[s] + atomicAdd(&fill[s], 1);
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (lane == 0) { osrc[pos] = s; odst[pos] = dst[e]; }
+        for (int v = lane; v < V; v += 32) olabel[(long long)pos * V + v] = label[e * V + v];
+    }
+}
+
+__global__ void __launch_bounds__(256) trim_init_kernel(const int32_t *deg, long long n_states, int32_t *outdeg,
+                                                        uint8_t *failed, int32_t *changed) {
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_states; s += (long long)gridDim.x * blockDim.x) {
+        const int d = deg[s];
+        outdeg[s] = d;
+        failed[s] = d == 0;
+        if (d == 0) *changed = 1;
+    }
+}
+
+// one pass: every live edge into a failed state dies; a source that loses its last live edge fails
+__global__ void __launch_bounds__(256) trim_step_kernel(const int32_t *src, const int32_t *dst, long long n, uint8_t *alive,
+                                                        int32_t *outdeg, uint8_t *failed, int32_t *changed, int32_t *dead) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        if (!alive[e] || !failed[dst[e]]) continue;
+        alive[e] = 0;
+        atomicAdd(dead, 1);
+        if (atomicSub(&outdeg[src[e]], 1) == 1) {
+            failed[src[e]] = 1;
+            *changed = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) alive_to_int_kernel(const uint8_t *alive, long long n, int32_t *flag) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        flag[e] = alive[e];
+}
+
+__global__ void __launch_bounds__(256) edge_compact_kernel(const int32_t *src, const int32_t *dst, const int32_t *label,
+                                                           const uint8_t *alive, const int32_t *pos, long long n, int V,
+                                                           int32_t *osrc, int32_t *odst, int32_t *olabel) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long e = warp_id; e < n; e += total_warps) {
+        if (!alive[e]) continue;
+        const long long p = pos[e];
+        if (lane == 0) { osrc[p] = src[e]; odst[p] = dst[e]; }
+        for (int v = lane; v < V; v += 32) olabel[p * V + v] = label[e * V + v];
+    }
+}
+
+// state rows from state keys: cset = max(0, key[0]) (the root's key starts with -1), sig = key[1..]
+__global__ void __launch_bounds__(256) state_rows_kernel(const int32_t *keys, long long n_states, int KW, int32_t *cset,
+                                                         int32_t *sig) {
+    const long long total = n_states * KW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / KW;
+        const int j = (int)(i % KW);
+        const int32_t v = keys[i];
+        if (j == 0) cset[s] = v < 0 ? 0 : v;
+        else sig[s * (KW - 1) + (j - 1)] = v;
+    }
+}
+
+int grid_for(long long n, int per_block, int sm_count) {
+    long long g = (n + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > (long long)sm_count * 8) g = (long long)sm_count * 8;
+    return (int)g;
+}
+
+}  // namespace
+
+size_t scan_temp_bytes(long long n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n);
+    return bytes;
+}
+
+void launch_exclusive_scan(void *temp, size_t temp_bytes, const int32_t *in, int32_t *out, long long n, cudaStream_t stream) {
+    cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, stream);
+}
+
+void launch_edge_count(const int32_t *src, long long n, int32_t *deg, int sm_count, cudaStream_t stream) {
+    if (n > 0) edge_count_kernel<<<grid_for(n, 256, sm_count), 256, 0, stream>>>(src, n, deg);
+}
+
+void launch_edge_scatter(const int32_t *src, const int32_t *dst, const int32_t *label, long long n, int V, const int32_t *first,
+                         int32_t *fill, int32_t *osrc, int32_t *odst, int32_t *olabel, int sm_count, cudaStream_t stream) {
+    if (n > 0)
+        edge_scatter_kernel<<<grid_for(n, 8, sm_count), 256, 0, stream>>>(src, dst, label, n, V, first, fill, osrc, odst, olabel);
+}
+
+void launch_trim_init(const int32_t *deg, long long n_states, int32_t *outdeg, uint8_t *failed, int32_t *changed, int sm_count,
+                      cudaStream_t stream) {
+    if (n_states > 0) trim_init_kernel<<<grid_for(n_states, 256, sm_count), 256, 0, stream>>>(deg, n_states, outdeg, failed, changed);
+}
+
+void launch_trim_step(const int32_t *src, const int32_t *dst, long long n, uint8_t *alive, int32_t *outdeg, uint8_t *failed,
+                      int32_t *changed, int32_t *dead, int sm_count, cudaStream_t stream) {
+    if (n > 0) trim_step_kernel<<<grid_for(n, 256, sm_count), 256, 0, stream>>>(src, dst, n, alive, outdeg, failed, changed, dead);
+}
+
+void launch_alive_to_int(const uint8_t *alive, long long n, int32_t *flag, int sm_count, cudaStream_t stream) {
+    if (n > 0) alive_to_int_kernel<<<grid_for(n, 256, sm_count), 256, 0, stream>>>(alive, n, flag);
+}
+
+void launch_edge_compact(const int32_t *src, const int32_t *dst, const int32_t *label, const uint8_t *alive, const int32_t *pos,
+                         long long n, int V, int32_t *osrc, int32_t *odst, int32_t *olabel, int sm_count, cudaStream_t stream) {
+    if (n > 0)
+        edge_compact_kernel<<<grid_for(n, 8, sm_count), 256, 0, stream>>>(src, dst, label, alive, pos, n, V, osrc, odst, olabel);
+}
+
+void launch_state_rows(const int32_t *keys, long long n_states, int KW, int32_t *cset, int32_t *sig, int sm_count,
+                       cudaStream_t stream) {
+    if (n_states > 0)
+        state_rows_kernel<<<grid_for(n_states * KW, 256, sm_count), 256, 0, stream>>>(keys, n_states, KW, cset, sig);
+}
+
+}  // namespace stcsp

@@ -123,6 +123,22 @@ void launch_fill(int32_t *ptr, long long n, int32_t value, cudaStream_t stream);
 void launch_build_tables(const DevModel &m, const int32_t *dev_jobs, int n_jobs, int max_entries, unsigned long long *tables,
                          cudaStream_t stream);
 
+// automaton.cu: device-side finishing (group edges by source, fail-rule fixpoint, compaction)
+size_t scan_temp_bytes(long long n);
+void launch_exclusive_scan(void *temp, size_t temp_bytes, const int32_t *in, int32_t *out, long long n, cudaStream_t stream);
+void launch_edge_count(const int32_t *src, long long n, int32_t *deg, int sm_count, cudaStream_t stream);
+void launch_edge_scatter(const int32_t *src, const int32_t *dst, const int32_t *label, long long n, int V, const int32_t *first,
+                         int32_t *fill, int32_t *osrc, int32_t *odst, int32_t *olabel, int sm_count, cudaStream_t stream);
+void launch_trim_init(const int32_t *deg, long long n_states, int32_t *outdeg, uint8_t *failed, int32_t *changed, int sm_count,
+                      cudaStream_t stream);
+void launch_trim_step(const int32_t *src, const int32_t *dst, long long n, uint8_t *alive, int32_t *outdeg, uint8_t *failed,
+                      int32_t *changed, int32_t *dead, int sm_count, cudaStream_t stream);
+void launch_alive_to_int(const uint8_t *alive, long long n, int32_t *flag, int sm_count, cudaStream_t stream);
+void launch_edge_compact(const int32_t *src, const int32_t *dst, const int32_t *label, const uint8_t *alive, const int32_t *pos,
+                         long long n, int V, int32_t *osrc, int32_t *odst, int32_t *olabel, int sm_count, cudaStream_t stream);
+void launch_state_rows(const int32_t *keys, long long n_states, int KW, int32_t *cset, int32_t *sig, int sm_count,
+                       cudaStream_t stream);
+
 uint32_t capmap_hash(int cid, const int32_t *vals, int n);
 uint32_t state_key_hash(const int32_t *key, int key_words);
 int32_t owner_of_hash(uint32_t h, int32_t world);

@@ -156,13 +156,17 @@ PinnedCache &pinned_cache() {
     return *c;
 }
 
-struct AutoStore {      // backing storage of a library-owned stcsp_automaton_t
+struct Store {          // backing storage of a library-owned stcsp_automaton_t
+    virtual ~Store() {}
+};
+
+struct AutoStore : Store {      // host vectors (assembled / multi-rank automata)
     std::vector<int32_t> sig_vars, state_sig, state_cset, edge_src, edge_dst, edge_label;
     std::vector<uint8_t> state_failed;
 };
 
 void bind_store(stcsp_automaton_t *a, AutoStore *st) {
-    a->impl = st;
+    a->impl = static_cast<Store *>(st);
     a->sig_vars = st->sig_vars.data();
     a->state_sig = st->state_sig.data();
     a->state_cset = st->state_cset.data();
@@ -171,6 +175,63 @@ void bind_store(stcsp_automaton_t *a, AutoStore *st) {
     a->edge_dst = st->edge_dst.data();
     a->edge_label = st->edge_label.data();
 }
+
+// Pinned host blocks, cached per process by size class: the automaton is copied device -> host once, at PCIe speed,
+// into memory the caller reads in place (fresh pageable memory costs ~2.5 GB/s in page faults + staging).
+struct HostCache {
+    std::mutex mu;
+    std::map<size_t, std::vector<void *>> free_blocks;
+    static constexpr size_t kMaxPinned = (size_t)4 << 30;      // larger blocks are plain malloc
+    void *acquire(size_t bytes, bool &pinned) {
+        pinned = bytes <= kMaxPinned;
+        if (!pinned) {
+            void *p = malloc(bytes);
+            if (!p) throw std::bad_alloc();
+            return p;
+        }
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = free_blocks.find(bytes);
+            if (it != free_blocks.end() && !it->second.empty()) {
+                void *p = it->second.back();
+                it->second.pop_back();
+                return p;
+            }
+        }
+        void *p = nullptr;
+        if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            pinned = false;
+            p = malloc(bytes);
+            if (!p) throw std::bad_alloc();
+        }
+        return p;
+    }
+    void give_back(void *p, size_t bytes, bool pinned) {
+        if (!pinned) { free(p); return; }
+        std::lock_guard<std::mutex> g(mu);
+        free_blocks[bytes].push_back(p);
+    }
+};
+HostCache &host_cache() {
+    static HostCache *c = new HostCache();
+    return *c;
+}
+
+struct HostBlock {
+    void *p = nullptr;
+    size_t bytes = 0;
+    bool pinned = false;
+    void alloc(size_t need) {
+        bytes = DeviceCache::size_class(std::max<size_t>(need, 1));
+        p = host_cache().acquire(bytes, pinned);
+    }
+    ~HostBlock() { if (p) host_cache().give_back(p, bytes, pinned); }
+};
+
+struct PinnedStore : Store {    // single-rank automata finished on the device
+    HostBlock sig_vars, state_sig, state_cset, state_failed, edge_src, edge_dst, edge_label;
+};
 
 }  // namespace
 }  // namespace stcsp
@@ -715,6 +776,12 @@ struct stcsp_session {
             st->state_cset[s] = std::max(0, keys[s * KW]);
             for (int j = 0; j < SL; j++) st->state_sig[s * SL + j] = keys[s * KW + 1 + j];
         }
+        fill_header(part, ms);
+        bind_store(part, st);
+    }
+
+    void fill_header(stcsp_automaton_t *part, float ms) {
+        const int V = dm.V, SL = dm.sig_len;
         part->n_vars = V;
         part->n_sig_vars = dm.n_sig;
         part->n_until = sets.n_until();
@@ -722,8 +789,8 @@ struct stcsp_session {
         part->sig_len = SL;
         part->root_final = sets.n_until() == 0;
         part->n_constraint_sets = sets.n_sets();
-        part->n_states = n_states;
-        part->n_edges = n_edges;
+        if (part->n_states == 0) part->n_states = n_states;
+        if (part->n_edges == 0) part->n_edges = n_edges;
         part->n_search_nodes = t_nodes;
         part->n_fails = t_fails;
         part->n_leaves = t_leaves;
@@ -741,7 +808,125 @@ struct stcsp_session {
         // the reference's (lb, ub) int32 pairs per variable and offset
         part->algorithmic_bytes = t_nodes * 2ll * V * dm.k * 8 + t_leaves * ((SL + 1) * 4ll + 8) +
                                   n_states * ((SL + 1) * 4ll + 8) + n_edges * (V + 2) * 4ll;
-        bind_store(part, st);
+    }
+
+    // Single-rank finish: edges grouped by source and the fail rule applied ON THE DEVICE, then one copy into pinned
+    // host memory.  State ids are already dense (world == 1: global id == local index, root == 0).
+    void finish_device(stcsp_automaton_t *out, bool trim) {
+        memset(out, 0, sizeof *out);
+        const int KW = dm.key_words, V = dm.V, SL = dm.sig_len;
+        const long long ns = n_states, ne = n_edges;
+        DBuf<int32_t> deg, first, fill, s_src, s_dst, s_label, outdeg, flags, rows_cset, rows_sig;
+        DBuf<uint8_t> failed, alive, scan_tmp;
+        struct Release {        // return the scratch blocks only after the stream drained
+            cudaStream_t st;
+            ~Release() { cudaStreamSynchronize(st); }
+        };
+        int32_t *f_src = edge_src.p, *f_dst = edge_dst.p, *f_label = edge_label.p;
+        long long n_final = ne;
+        {
+            deg.reserve((size_t)ns + 1, 0, stream);
+            first.reserve((size_t)ns + 1, 0, stream);
+            fill.reserve((size_t)ns + 1, 0, stream);
+            failed.reserve((size_t)ns + 1, 0, stream);
+            CK(cudaMemsetAsync(deg.p, 0, ((size_t)ns + 1) * 4, stream));
+            CK(cudaMemsetAsync(fill.p, 0, ((size_t)ns + 1) * 4, stream));
+            CK(cudaMemsetAsync(failed.p, 0, (size_t)ns + 1, stream));
+            launch_edge_count(edge_src.p, ne, deg.p, sm_count, stream);
+            const size_t tmp = scan_temp_bytes(std::max<long long>(ns + 1, ne + 1));
+            scan_tmp.reserve(tmp + 16, 0, stream);
+            launch_exclusive_scan(scan_tmp.p, tmp, deg.p, first.p, ns + 1, stream);
+            if (ne > 0) {
+                s_src.reserve((size_t)ne, 0, stream);
+                s_dst.reserve((size_t)ne, 0, stream);
+                s_label.reserve((size_t)ne * V, 0, stream);
+                launch_edge_scatter(edge_src.p, edge_dst.p, edge_label.p, ne, V, first.p, fill.p, s_src.p, s_dst.p, s_label.p,
+                                    sm_count, stream);
+                f_src = s_src.p; f_dst = s_dst.p; f_label = s_label.p;
+                t_launches += 3;
+            }
+            if (trim) {
+                outdeg.reserve((size_t)ns + 1, 0, stream);
+                alive.reserve((size_t)ne + 1, 0, stream);
+                CK(cudaMemsetAsync(alive.p, 1, (size_t)ne + 1, stream));
+                unsigned long long *ctl = counters.p + C_OUT;         // two scratch words: [0] changed, [1] dead edges
+                CK(cudaMemsetAsync(ctl, 0, 16, stream));
+                launch_trim_init(deg.p, ns, outdeg.p, failed.p, (int32_t *)ctl, sm_count, stream);
+                t_launches++;
+                for (;;) {
+                    CK(cudaMemcpyAsync(h_counters, ctl, 16, cudaMemcpyDeviceToHost, stream));
+                    CK(cudaStreamSynchronize(stream));
+                    if ((int32_t)h_counters[0] == 0) break;
+                    CK(cudaMemsetAsync(ctl, 0, 4, stream));
+                    launch_trim_step(f_src, f_dst, ne, alive.p, outdeg.p, failed.p, (int32_t *)ctl, (int32_t *)(ctl + 1),
+                                     sm_count, stream);
+                    t_launches++;
+                }
+                const long long dead = (long long)(int32_t)h_counters[1];
+                if (dead > 0) {
+                    // compact the live edges back into the (now free) append-order buffers; order within a source is kept
+                    flags.reserve((size_t)ne + 1, 0, stream);
+                    launch_alive_to_int(alive.p, ne, flags.p, sm_count, stream);
+                    const size_t tmp2 = scan_temp_bytes(ne + 1);
+                    scan_tmp.reserve(tmp2 + 16, 0, stream);
+                    launch_exclusive_scan(scan_tmp.p, tmp2, flags.p, flags.p, ne, stream);
+                    launch_edge_compact(f_src, f_dst, f_label, alive.p, flags.p, ne, V, edge_src.p, edge_dst.p, edge_label.p,
+                                        sm_count, stream);
+                    f_src = edge_src.p; f_dst = edge_dst.p; f_label = edge_label.p;
+                    n_final = ne - dead;
+                    t_launches += 3;
+                }
+            }
+            rows_cset.reserve((size_t)ns + 1, 0, stream);
+            rows_sig.reserve((size_t)ns * std::max(SL, 1) + 1, 0, stream);
+            launch_state_rows(state_key.p, ns, KW, rows_cset.p, rows_sig.p, sm_count, stream);
+            t_launches++;
+            CK(cudaGetLastError());
+        }
+        float ms = 0;
+        if (timing_open) {
+            CK(cudaEventRecord(ev1, stream));
+        }
+        auto *st = new PinnedStore();
+        Release guard{stream};
+        try {
+            st->sig_vars.alloc(sets.sig_vars().size() * 4);
+            st->state_sig.alloc((size_t)ns * SL * 4);
+            st->state_cset.alloc((size_t)ns * 4);
+            st->state_failed.alloc((size_t)ns);
+            st->edge_src.alloc((size_t)n_final * 4);
+            st->edge_dst.alloc((size_t)n_final * 4);
+            st->edge_label.alloc((size_t)n_final * V * 4);
+            if (!sets.sig_vars().empty()) memcpy(st->sig_vars.p, sets.sig_vars().data(), sets.sig_vars().size() * 4);
+            if (ns) {
+                if (SL) CK(cudaMemcpyAsync(st->state_sig.p, rows_sig.p, (size_t)ns * SL * 4, cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(st->state_cset.p, rows_cset.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(st->state_failed.p, failed.p, (size_t)ns, cudaMemcpyDeviceToHost, stream));
+            }
+            if (n_final) {
+                CK(cudaMemcpyAsync(st->edge_src.p, f_src, (size_t)n_final * 4, cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(st->edge_dst.p, f_dst, (size_t)n_final * 4, cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(st->edge_label.p, f_label, (size_t)n_final * V * 4, cudaMemcpyDeviceToHost, stream));
+            }
+            CK(cudaStreamSynchronize(stream));
+            if (timing_open) CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        } catch (...) {
+            delete st;
+            throw;
+        }
+        d2h += ns * (SL + 1) * 4 + ns + n_final * (2 + V) * 4;
+        out->n_states = ns;
+        out->n_edges = n_final;
+        fill_header(out, ms);
+        out->n_edges = n_final;
+        out->impl = static_cast<Store *>(st);
+        out->sig_vars = (int32_t *)st->sig_vars.p;
+        out->state_sig = (int32_t *)st->state_sig.p;
+        out->state_cset = (int32_t *)st->state_cset.p;
+        out->state_failed = (uint8_t *)st->state_failed.p;
+        out->edge_src = (int32_t *)st->edge_src.p;
+        out->edge_dst = (int32_t *)st->edge_dst.p;
+        out->edge_label = (int32_t *)st->edge_label.p;
     }
 };
 
@@ -913,23 +1098,22 @@ int stcsp_automaton_assemble(const stcsp_automaton_t *parts, int32_t n_parts, st
 }
 
 int stcsp_automaton_trim(stcsp_automaton_t *a) {
-    if (!a || !a->impl) { set_error("trim needs a library-owned automaton"); return STCSP_ERR_INVALID; }
+    if (!a) { set_error("null argument"); return STCSP_ERR_INVALID; }
     return guarded([&] {
-        auto *st = (AutoStore *)a->impl;
         const int64_t n = a->n_states, m = a->n_edges;
         const int V = a->n_vars;
         std::vector<int64_t> outdeg((size_t)n, 0), in_first((size_t)n + 1, 0);
         for (int64_t e = 0; e < m; e++) {
-            outdeg[st->edge_src[e]]++;
-            in_first[(size_t)st->edge_dst[e] + 1]++;
+            outdeg[a->edge_src[e]]++;
+            in_first[(size_t)a->edge_dst[e] + 1]++;
         }
         for (int64_t s = 0; s < n; s++) in_first[s + 1] += in_first[s];
         std::vector<int64_t> in_edge((size_t)m), fillp(in_first.begin(), in_first.end() - 1);
-        for (int64_t e = 0; e < m; e++) in_edge[fillp[st->edge_dst[e]]++] = e;
+        for (int64_t e = 0; e < m; e++) in_edge[fillp[a->edge_dst[e]]++] = e;
         std::vector<uint8_t> alive((size_t)m, 1);
         std::vector<int32_t> todo;
         for (int64_t s = 0; s < n; s++)
-            if (outdeg[s] == 0) { st->state_failed[s] = 1; todo.push_back((int32_t)s); }
+            if (outdeg[s] == 0) { a->state_failed[s] = 1; todo.push_back((int32_t)s); }
         while (!todo.empty()) {
             const int32_t s = todo.back();
             todo.pop_back();
@@ -937,25 +1121,21 @@ int stcsp_automaton_trim(stcsp_automaton_t *a) {
                 const int64_t e = in_edge[i];
                 if (!alive[e]) continue;
                 alive[e] = 0;
-                const int32_t p = st->edge_src[e];
-                if (--outdeg[p] == 0 && !st->state_failed[p]) { st->state_failed[p] = 1; todo.push_back(p); }
+                const int32_t p = a->edge_src[e];
+                if (--outdeg[p] == 0 && !a->state_failed[p]) { a->state_failed[p] = 1; todo.push_back(p); }
             }
         }
         int64_t w = 0;
-        for (int64_t e = 0; e < m; e++) {
+        for (int64_t e = 0; e < m; e++) {       // in place: the arrays keep their capacity, n_edges shrinks
             if (!alive[e]) continue;
             if (w != e) {
-                st->edge_src[w] = st->edge_src[e];
-                st->edge_dst[w] = st->edge_dst[e];
-                memmove(&st->edge_label[(size_t)w * V], &st->edge_label[(size_t)e * V], (size_t)V * 4);
+                a->edge_src[w] = a->edge_src[e];
+                a->edge_dst[w] = a->edge_dst[e];
+                memmove(a->edge_label + (size_t)w * V, a->edge_label + (size_t)e * V, (size_t)V * 4);
             }
             w++;
         }
-        st->edge_src.resize((size_t)w);
-        st->edge_dst.resize((size_t)w);
-        st->edge_label.resize((size_t)w * V);
         a->n_edges = w;
-        bind_store(a, st);
     });
 }
 
@@ -964,11 +1144,12 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
     memset(out, 0, sizeof *out);
     const double t0 = now_s();
     stcsp_session *s = nullptr;
-    stcsp_automaton_t part;
-    memset(&part, 0, sizeof part);
+    double t_init = 0, t_loop = 0, t_finish = 0;
+    const bool verbose = options && options->verbosity > 0;
     int rc = guarded([&] {
         s = new stcsp_session();
         s->init(problem, options, 0, 1);
+        t_init = now_s();
         const double deadline = s->opt.time_limit_s > 0 ? t0 + s->opt.time_limit_s : 0;
         int64_t frontier = s->n_in;
         std::vector<int32_t> req;
@@ -982,12 +1163,17 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
             }
             s->ingest(nullptr, 0, &frontier);
         }
-        s->finish(&part);
+        t_loop = now_s();
+        s->finish_device(out, !(options && options->no_trim));
+        t_finish = now_s();
     });
     delete s;
-    if (rc == STCSP_OK) rc = stcsp_automaton_assemble(&part, 1, out);
-    stcsp_automaton_free(&part);
-    if (rc == STCSP_OK && !(options && options->no_trim)) rc = stcsp_automaton_trim(out);
+    const double t_del = now_s();
+    const double t_asm = now_s();
+    if (verbose)
+        fprintf(stderr, "[stcsp] wall: init %.2f ms, waves %.2f ms, download %.2f ms, release %.2f ms, assemble %.2f ms, trim %.2f ms\n",
+                (t_init - t0) * 1e3, (t_loop - t_init) * 1e3, (t_finish - t_loop) * 1e3, (t_del - t_finish) * 1e3,
+                (t_asm - t_del) * 1e3, (now_s() - t_asm) * 1e3);
     if (rc == STCSP_OK) out->wall_ms = (now_s() - t0) * 1e3;
     else stcsp_automaton_free(out);
     return rc;
@@ -995,7 +1181,7 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
 
 void stcsp_automaton_free(stcsp_automaton_t *a) {
     if (!a) return;
-    delete (AutoStore *)a->impl;
+    delete (Store *)a->impl;
     memset(a, 0, sizeof *a);
 }
 
