@@ -85,8 +85,8 @@ struct Limits {
     static constexpr int kMaxStack = 24;        // evaluator stack depth
     static constexpr int kMaxUntil = 30;        // until constraints (flags packed in one word)
     static constexpr int kMaxWidth = 64;        // values per domain (one 64-bit word)
-    static constexpr int kMaxTableEntries = 1 << 16;    // per relation table (512 KiB)
-    static constexpr long long kMaxTableWords = 1ll << 25;   // whole pool (256 MiB)
+    static constexpr int kMaxTableEntries = 1 << 22;    // per relation table (32 MiB: still L2-resident on B200)
+    static constexpr long long kMaxTableWords = 1ll << 27;   // whole pool (1 GiB)
 };
 
 struct TableJob {          // a relation table the device still has to fill (build_tables_kernel)
@@ -130,6 +130,13 @@ class SetTable {
     std::vector<int32_t> dev_aux;
     std::vector<int32_t> arr_off, arr_val;
 
+    // Relation tables already resident on the device (from an earlier solve of the same model): seeding them
+    // before init() means no table is rebuilt.  export_tables() hands the directory back.
+    struct TableRef { long long off; int32_t entries, pivot; std::vector<int32_t> strides; };
+    typedef std::map<std::string, TableRef> TableDirectory;
+    void seed_tables(const TableDirectory &dir, long long words) { table_cache_ = dir; table_words = words; }
+    const TableDirectory &export_tables() const { return table_cache_; }
+
   private:
     int32_t add_set(std::vector<Constraint> cons);
     int32_t find_or_add(std::vector<Constraint> cons);
@@ -137,8 +144,7 @@ class SetTable {
     void assign_table(DevCon &dc, const Constraint &c);
     void resolve_static(int32_t s);
 
-    struct TableRef { long long off; int32_t entries, pivot; std::vector<int32_t> strides; };
-    std::map<std::string, TableRef> table_cache_;      // structurally equal constraints share one table
+    TableDirectory table_cache_;      // structurally equal constraints share one table
     int32_t k_ = 2;
     std::vector<int32_t> lb_, width_;
     std::vector<Array> arrays_;

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -110,6 +111,12 @@ struct DBuf {
         cap = bytes = 0;
     }
     // at least `need` elements; the first `keep` elements survive a reallocation
+    void swap(DBuf &o) {
+        std::swap(p, o.p);
+        std::swap(cap, o.cap);
+        std::swap(bytes, o.bytes);
+        std::swap(device, o.device);
+    }
     bool reserve(size_t need, size_t keep, cudaStream_t st) {
         if (need <= cap) return false;
         const size_t nbytes = DeviceCache::size_class(std::max(need, 2 * cap) * sizeof(T));
@@ -128,6 +135,61 @@ struct DBuf {
         return true;
     }
 };
+
+// Relation tables of recently solved models stay resident on the device (take / put: one session at a time owns
+// an entry, a concurrent solve of the same model simply builds its own).
+struct ModelCache {
+    struct Entry {
+        DBuf<unsigned long long> tables;
+        long long words = 0;
+        SetTable::TableDirectory dir;
+    };
+    std::mutex mu;
+    std::map<std::string, std::unique_ptr<Entry>> entries;
+    std::vector<std::string> order;
+    std::unique_ptr<Entry> take(const std::string &key) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = entries.find(key);
+        if (it == entries.end()) return nullptr;
+        std::unique_ptr<Entry> e = std::move(it->second);
+        entries.erase(it);
+        order.erase(std::remove(order.begin(), order.end(), key), order.end());
+        return e;
+    }
+    void put(const std::string &key, std::unique_ptr<Entry> e) {
+        std::lock_guard<std::mutex> g(mu);
+        if (entries.count(key)) return;
+        entries[key] = std::move(e);
+        order.push_back(key);
+        while (order.size() > 8) {          // oldest out (its blocks go back to the device cache)
+            entries.erase(order.front());
+            order.erase(order.begin());
+        }
+    }
+};
+ModelCache &model_cache() {
+    static ModelCache *c = new ModelCache();
+    return *c;
+}
+
+std::string model_key(const stcsp_problem_t &p, int device) {
+    std::string k;
+    auto add = [&](const void *ptr, size_t n) { k.append((const char *)ptr, n); };
+    add(&device, sizeof device);
+    add(&p.prefix_k, sizeof p.prefix_k);
+    add(&p.n_vars, sizeof p.n_vars);
+    add(p.var_lb, sizeof(int32_t) * p.n_vars);
+    add(p.var_ub, sizeof(int32_t) * p.n_vars);
+    add(&p.n_arrays, sizeof p.n_arrays);
+    if (p.n_arrays > 0) {
+        add(p.arr_offsets, sizeof(int32_t) * (p.n_arrays + 1));
+        add(p.arr_values, sizeof(int32_t) * p.arr_offsets[p.n_arrays]);
+    }
+    add(&p.n_constraints, sizeof p.n_constraints);
+    add(p.con_offsets, sizeof(int32_t) * (p.n_constraints + 1));
+    add(p.con_tokens, sizeof(stcsp_tok_t) * p.con_offsets[p.n_constraints]);
+    return k;
+}
 
 // Pinned host blocks for the counter read-back, cached per process (cudaMallocHost costs ~1 ms).
 struct PinnedCache {
@@ -250,6 +312,7 @@ struct stcsp_session {
     DBuf<unsigned long long> d_tables;
     DBuf<int32_t> d_jobs;
     long long tables_built = 0;     // u64 words of the table pool already filled
+    std::string cache_key;
     DBuf<DevSet> d_sets;
     DBuf<DevCon> d_cons;
     DBuf<DevProp> d_props;
@@ -282,6 +345,13 @@ struct stcsp_session {
     ~stcsp_session() {
         if (stream) cudaStreamSynchronize(stream);
         if (h_counters) pinned_cache().give_back(h_counters);
+        if (!cache_key.empty() && sets.table_jobs.empty() && tables_built == sets.table_words && d_tables.p) {
+            std::unique_ptr<ModelCache::Entry> e(new ModelCache::Entry());      // keep the relation tables resident
+            e->tables.swap(d_tables);
+            e->words = sets.table_words;
+            e->dir = sets.export_tables();
+            model_cache().put(cache_key, std::move(e));
+        }
         release_all();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -429,6 +499,12 @@ struct stcsp_session {
         CK(cudaEventCreate(&evk0));
         CK(cudaEventCreate(&evk1));
         try {
+            cache_key = model_key(*problem, device);
+            if (std::unique_ptr<ModelCache::Entry> e = model_cache().take(cache_key)) {
+                sets.seed_tables(e->dir, e->words);
+                d_tables.swap(e->tables);
+                tables_built = e->words;
+            }
             sets.init(*problem);
         } catch (const std::invalid_argument &ex) {
             throw Failure(STCSP_ERR_UNSUPPORTED, ex.what());
