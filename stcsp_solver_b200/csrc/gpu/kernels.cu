@@ -21,6 +21,7 @@
 // skipped (sound: a skipped propagator only prunes less) and re-armed when a domain shrinks; at a
 // leaf every constraint has exactly one tuple, so every leaf is checked exactly.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include <algorithm>
 
@@ -519,8 +520,7 @@ __device__ __forceinline__ bool revise(NodeCtx &c, int q) {
 //              (narrow waves: fewer nodes than resident CTAs, the latency of one node is the wave's duration).
 // CTA = false: one warp per search node (wide waves: throughput).
 template <bool CTA>
-__global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevModel M, const ExpandArgs P) {
-    extern __shared__ __align__(16) unsigned char smem[];
+__device__ __forceinline__ void expand_body(const DevModel &M, const ExpandArgs &P, unsigned char *smem) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpMem wm = carve(smem, M, CTA ? 0 : warp, warp);
     const long long n_in = P.n_in;
@@ -691,6 +691,12 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevM
     }
 }
 
+template <bool CTA>
+__global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevModel M, const ExpandArgs P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    expand_body<CTA>(M, P, smem);
+}
+
 // ---- hashing ---------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
@@ -727,7 +733,7 @@ __device__ __forceinline__ int key_word(const DevModel &M, const int32_t *rec, i
 
 // ---- route: successor constraint set, until flags and state-key hash of every leaf --------------------
 // (reference src/solveralgorithm.cpp:755-837: constraint rewriting -> constraintID, signature)
-__global__ void __launch_bounds__(256) route_kernel(const DevModel M, const RouteArgs P) {
+__device__ __forceinline__ void route_body(const DevModel &M, const RouteArgs &P) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -790,6 +796,8 @@ __global__ void __launch_bounds__(256) route_kernel(const DevModel M, const Rout
     }
 }
 
+__global__ void __launch_bounds__(256) route_kernel(const DevModel M, const RouteArgs P) { route_body(M, P); }
+
 // ---- scatter: group routed leaves by owner rank (multi-GPU only) ---------------------------------------
 __global__ void __launch_bounds__(256) scatter_kernel(const DevModel M, const int32_t *leaves, long long n,
                                                       const long long *offsets, unsigned long long *fill,
@@ -823,7 +831,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const int32_t *src, const i
 // ---- ingest: state dedup, edge append, first search node of every new state ------------------------------
 // One warp per routed leaf record (reference vertexTableGetVertex/AddVertex src/graph.cpp:108-123,
 // edgeNew src/graph.cpp:78-89, variableAdvanceOneTimeStep src/variable.cpp:94-108).
-__global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const IngestArgs P) {
+__device__ __forceinline__ void ingest_body(const DevModel &M, const IngestArgs &P) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -919,6 +927,119 @@ __global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const Ing
     if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
 }
 
+__global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const IngestArgs P) { ingest_body(M, P); }
+
+// ---- the whole wave loop in one cooperative launch -------------------------------------------------------
+// Waves of a small or deep search cost more in launches and host synchronisation than in work.  search_kernel
+// runs expand -> route -> ingest -> bookkeeping for wave after wave with grid-wide barriers in between and
+// returns to the host only when it is done or needs it (buffers to grow, an unseen constraint-set transition).
+__global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevModel M, SearchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    volatile SearchCtl *ctl = A.ctl;                    // written by one thread, read by all after a grid barrier
+    volatile unsigned long long *cnt = A.counters;
+    const bool tracer = A.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long wave = 0;
+    auto stamp = [&](int k) {
+        if (tracer && wave < A.trace_cap) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            A.trace[wave * 5 + k] = t;
+        }
+    };
+    for (;;) {
+        // ---- wave start: can this wave run without the host?
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const long long n_in = ctl->n_in;
+            const long long states = (long long)cnt[C_STATES], edges = (long long)cnt[C_EDGES];
+            int st = SEARCH_RUN;
+            if (n_in == 0) st = SEARCH_DONE;
+            else if (ctl->waves_left <= 0) st = SEARCH_YIELD;
+            else if (n_in > A.leaf_cap || n_in > A.unresolved_cap || states + n_in > A.state_cap ||
+                     edges + n_in > A.edge_cap || 2 * (states + n_in) > A.table_mask + 1 || 2 * n_in > A.out_cap)
+                st = SEARCH_GROW;
+            ctl->status = st;
+        }
+        grid.sync();
+        if (ctl->status != SEARCH_RUN) return;
+        stamp(0);
+        const long long n_in = ctl->n_in;
+        const int cur = ctl->cur;
+        ExpandArgs ea;
+        ea.in_nodes = A.frontier[cur];
+        ea.n_in = n_in;
+        ea.out_nodes = A.frontier[cur ^ 1];
+        ea.out_cap = A.out_cap;
+        ea.leaves = A.leaves;
+        ea.leaf_cap = A.leaf_cap;
+        ea.counters = A.counters;
+        if (n_in <= 3ll * gridDim.x) expand_body<true>(M, ea, smem);
+        else expand_body<false>(M, ea, smem);
+        grid.sync();
+        stamp(1);
+        // ---- the frontier buffer overflowed: only scratch was written, the host grows it and the wave runs again
+        if (cnt[C_OVERFLOW] & 1ull) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->status = SEARCH_RETRY;
+            return;
+        }
+        RouteArgs ra;
+        ra.leaves = A.leaves;
+        ra.list = nullptr;
+        ra.count = 0;
+        ra.capmap = A.capmap;
+        ra.capvals = A.capvals;
+        ra.capmap_mask = A.capmap_mask;
+        ra.unresolved = A.unresolved;
+        ra.unresolved_cap = A.unresolved_cap;
+        ra.counters = A.counters;
+        route_body(M, ra);
+        grid.sync();
+        stamp(2);
+        const long long n_leaves = (long long)cnt[C_LEAVES];
+        if (cnt[C_UNRESOLVED] != 0ull || (long long)cnt[C_OUT] + n_leaves > A.out_cap) {
+            // the host finishes this wave (resolve + ingest) and relaunches
+            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->status = SEARCH_INGEST;
+            return;
+        }
+        IngestArgs ia;
+        ia.records = A.leaves;
+        ia.count = n_leaves;
+        ia.table = A.table;
+        ia.table_mask = A.table_mask;
+        ia.state_key = A.state_key;
+        ia.state_cap = A.state_cap;
+        ia.edge_src = A.edge_src;
+        ia.edge_dst = A.edge_dst;
+        ia.edge_label = A.edge_label;
+        ia.edge_cap = A.edge_cap;
+        ia.out_nodes = A.frontier[cur ^ 1];
+        ia.out_cap = A.out_cap;
+        ia.counters = A.counters;
+        ingest_body(M, ia);
+        grid.sync();
+        stamp(3);
+        // ---- wave end: totals, swap, reset the wave counters
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            ctl->t_nodes += (long long)cnt[C_NODES];
+            ctl->t_fails += (long long)cnt[C_FAILS];
+            ctl->t_tuples += (long long)cnt[C_TUPLES];
+            ctl->t_revisions += (long long)cnt[C_REVISIONS];
+            ctl->t_dominance += (long long)cnt[C_DOMINANCE];
+            ctl->t_leaves += n_leaves;
+            ctl->t_waves += 1;
+            ctl->waves_left -= 1;
+            ctl->overflow |= (int)cnt[C_OVERFLOW];
+            ctl->n_in = (long long)cnt[C_OUT];
+            ctl->cur = cur ^ 1;
+            for (int i = C_OUT; i < C_COUNT; i++) cnt[i] = 0ull;
+            __threadfence();
+        }
+        stamp(4);
+        wave++;
+        // the barrier at the top of the loop publishes the new control block
+    }
+}
+
 // Re-insert every state into a fresh table after growth (one thread per state).
 __global__ void __launch_bounds__(256) rehash_kernel(const DevModel M, int32_t *table, long long mask,
                                                      const int32_t *state_key, long long n_states) {
@@ -1007,6 +1128,28 @@ void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, bool cta_pe
     configure_expand(smem);
     if (cta_per_node) expand_kernel<true><<<grid, kExpandWarps * 32, smem, stream>>>(m, a);
     else expand_kernel<false><<<grid, kExpandWarps * 32, smem, stream>>>(m, a);
+}
+
+int search_max_grid(const DevModel &m, int sm_count) {
+    const size_t smem = expand_smem_bytes(m);
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = smem;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel, kExpandWarps * 32, smem) != cudaSuccess || per_sm < 1)
+        return 0;
+    return per_sm * sm_count;
+}
+
+cudaError_t launch_search(const DevModel &m, const SearchArgs &a, int grid, cudaStream_t stream) {
+    const size_t smem = expand_smem_bytes(m);
+    DevModel mm = m;
+    SearchArgs aa = a;
+    void *params[] = {&mm, &aa};
+    return cudaLaunchCooperativeKernel((const void *)search_kernel, dim3(grid), dim3(kExpandWarps * 32), params, smem, stream);
 }
 
 void launch_route(const DevModel &m, const RouteArgs &a, int grid, cudaStream_t stream) {

@@ -101,12 +101,52 @@ struct IngestArgs {
     unsigned long long *counters;
 };
 
+// Control block of the persistent search kernel (device memory, mirrored to the host when the kernel returns).
+enum SearchStatus : int {
+    SEARCH_RUN = 0,
+    SEARCH_DONE = 1,       // frontier empty
+    SEARCH_GROW = 2,       // a pool is too small for the next wave: the host grows it, nothing of the wave has run
+    SEARCH_RETRY = 3,      // the output frontier overflowed during expand: grow it, run the wave again
+    SEARCH_INGEST = 4,     // expand + route done; the host resolves constraint-set transitions / grows, then ingests
+    SEARCH_YIELD = 5       // wave budget used up (time-limit checks)
+};
+struct SearchCtl {
+    long long n_in;
+    int cur, status, overflow, pad;
+    long long waves_left;
+    long long t_nodes, t_fails, t_tuples, t_revisions, t_dominance, t_leaves, t_waves;
+};
+struct SearchArgs {
+    SearchCtl *ctl;
+    unsigned long long *counters;
+    int32_t *frontier[2];
+    long long out_cap;                  // capacity of EACH frontier buffer, in nodes
+    int32_t *leaves;
+    long long leaf_cap;
+    int32_t *unresolved;
+    long long unresolved_cap;
+    const CapEntry *capmap;
+    const int32_t *capvals;
+    int32_t capmap_mask;
+    int32_t *table;
+    long long table_mask;
+    int32_t *state_key;
+    long long state_cap;
+    int32_t *edge_src, *edge_dst, *edge_label;
+    long long edge_cap;
+    unsigned long long *trace;          // optional: 5 %globaltimer stamps per wave (start, expanded, routed, ingested, end)
+    long long trace_cap;                // in waves
+};
+
 constexpr int kExpandWarps = 8;      // warps per CTA of the expand kernel
 
 size_t expand_smem_bytes(const DevModel &m);
 int expand_max_grid(const DevModel &m, int sm_count);      // resident CTAs of the expand kernel on this device
 // cta_per_node: one CTA (8 warps) per search node instead of one warp -- for waves narrower than the GPU
 void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, bool cta_per_node, cudaStream_t stream);
+// persistent wave loop (cooperative launch); search_max_grid = co-resident CTAs, 0 if unavailable
+int search_max_grid(const DevModel &m, int sm_count);
+cudaError_t launch_search(const DevModel &m, const SearchArgs &a, int grid, cudaStream_t stream);
 void launch_route(const DevModel &m, const RouteArgs &a, int grid, cudaStream_t stream);
 void launch_ingest(const DevModel &m, const IngestArgs &a, int grid, cudaStream_t stream);
 // group the routed local leaves by owner rank into `outbox` (dev_offsets = exclusive prefix of the owner counts)

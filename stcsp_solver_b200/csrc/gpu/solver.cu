@@ -143,6 +143,8 @@ struct ModelCache {
         DBuf<unsigned long long> tables;
         long long words = 0;
         SetTable::TableDirectory dir;
+        // pool sizes the last solve of this model ended with: the next one starts there and never has to grow
+        long long cap_frontier = 0, cap_states = 0, cap_edges = 0, cap_table = 0;
     };
     std::mutex mu;
     std::map<std::string, std::unique_ptr<Entry>> entries;
@@ -205,7 +207,7 @@ struct PinnedCache {
             }
         }
         unsigned long long *b = nullptr;
-        CK(cudaMallocHost(&b, C_COUNT * sizeof(unsigned long long)));
+        CK(cudaMallocHost(&b, C_COUNT * sizeof(unsigned long long) + 256));
         return b;
     }
     void give_back(unsigned long long *b) {
@@ -313,6 +315,10 @@ struct stcsp_session {
     DBuf<int32_t> d_jobs;
     long long tables_built = 0;     // u64 words of the table pool already filled
     std::string cache_key;
+    long long hint_frontier = 0, hint_states = 0, hint_edges = 0, hint_table = 0;
+    DBuf<SearchCtl> d_ctl;
+    SearchCtl *h_ctl = nullptr;     // pinned, behind h_counters
+    int search_grid = 0;
     DBuf<DevSet> d_sets;
     DBuf<DevCon> d_cons;
     DBuf<DevProp> d_props;
@@ -345,11 +351,15 @@ struct stcsp_session {
     ~stcsp_session() {
         if (stream) cudaStreamSynchronize(stream);
         if (h_counters) pinned_cache().give_back(h_counters);
-        if (!cache_key.empty() && sets.table_jobs.empty() && tables_built == sets.table_words && d_tables.p) {
+        if (!cache_key.empty() && sets.table_jobs.empty() && tables_built == sets.table_words && dm.node_words > 0) {
             std::unique_ptr<ModelCache::Entry> e(new ModelCache::Entry());      // keep the relation tables resident
             e->tables.swap(d_tables);
             e->words = sets.table_words;
             e->dir = sets.export_tables();
+            e->cap_frontier = (long long)std::min(frontier[0].cap, frontier[1].cap) / dm.node_words;
+            e->cap_states = (long long)state_key.cap / dm.key_words;
+            e->cap_edges = (long long)edge_src.cap;
+            e->cap_table = table_size;
             model_cache().put(cache_key, std::move(e));
         }
         release_all();
@@ -362,7 +372,7 @@ struct stcsp_session {
 
     void release_all() {
         d_lb.release(); d_width.release(); d_sigvars.release(); d_scope.release(); d_stride.release(); d_aux.release();
-        d_arr_off.release(); d_arr_val.release(); d_tables.release(); d_jobs.release(); d_sets.release(); d_cons.release();
+        d_arr_off.release(); d_arr_val.release(); d_tables.release(); d_jobs.release(); d_ctl.release(); d_sets.release(); d_cons.release();
         d_props.release(); d_code.release(); d_wake.release(); frontier[0].release(); frontier[1].release();
         leaves.release(); unresolved.release(); gathered.release(); table.release(); state_key.release();
         edge_src.release(); edge_dst.release(); edge_label.release(); d_capmap.release(); d_capvals.release();
@@ -504,6 +514,10 @@ struct stcsp_session {
                 sets.seed_tables(e->dir, e->words);
                 d_tables.swap(e->tables);
                 tables_built = e->words;
+                hint_frontier = e->cap_frontier;
+                hint_states = e->cap_states;
+                hint_edges = e->cap_edges;
+                hint_table = e->cap_table;
             }
             sets.init(*problem);
         } catch (const std::invalid_argument &ex) {
@@ -514,16 +528,25 @@ struct stcsp_session {
         upload_model();
         counters.reserve(C_COUNT, 0, stream);
         CK(cudaMemsetAsync(counters.p, 0, C_COUNT * sizeof(unsigned long long), stream));
-        h_counters = pinned_cache().acquire();
+        h_counters = pinned_cache().acquire();       // C_COUNT counters + room for the search control block
         d_offsets.reserve(2 * kMaxWorld, 0, stream);
 
         const int NW = dm.node_words, KW = dm.key_words;
-        frontier[0].reserve((size_t)4096 * NW, 0, stream);
-        frontier[1].reserve((size_t)4096 * NW, 0, stream);
-        state_key.reserve((size_t)4096 * KW, 0, stream);
-        edge_src.reserve(8192, 0, stream);
-        edge_dst.reserve(8192, 0, stream);
-        edge_label.reserve((size_t)8192 * dm.V, 0, stream);
+        const size_t f0 = (size_t)std::max<long long>(4096, hint_frontier), s0 = (size_t)std::max<long long>(4096, hint_states),
+                     e0 = (size_t)std::max<long long>(8192, hint_edges);
+        frontier[0].reserve(f0 * NW, 0, stream);
+        frontier[1].reserve(f0 * NW, 0, stream);
+        leaves.reserve(f0 * dm.rec_words, 0, stream);
+        unresolved.reserve(f0, 0, stream);
+        state_key.reserve(s0 * KW, 0, stream);
+        edge_src.reserve(e0, 0, stream);
+        edge_dst.reserve(e0, 0, stream);
+        edge_label.reserve(e0 * dm.V, 0, stream);
+        d_ctl.reserve(1, 0, stream);
+        h_ctl = reinterpret_cast<SearchCtl *>(h_counters + C_COUNT);
+        search_grid = search_max_grid(dm, sm_count);
+        int coop = 0;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) search_grid = 0;
         if (rank == 0) {
             // root state (reference src/solveralgorithm.cpp:951-954) and its search node
             std::vector<int32_t> key(KW, 0);
@@ -545,7 +568,134 @@ struct stcsp_session {
             n_states = 1;
             n_in = 1;
         }
-        ensure_table(std::max<long long>(n_states, 1));
+        ensure_table(std::max<long long>(std::max<long long>(n_states, 1), hint_table / 2));
+    }
+
+    // Pools big enough for a wave over `nin` input nodes (see the SEARCH_GROW test in search_kernel).
+    void ensure_wave_capacity(long long nin) {
+        const int NW = dm.node_words, KW = dm.key_words, V = dm.V, RW = dm.rec_words;
+        leaves.reserve((size_t)nin * RW, 0, stream);
+        unresolved.reserve((size_t)nin, 0, stream);
+        frontier[cur].reserve((size_t)2 * nin * NW, (size_t)n_in * NW, stream);
+        frontier[cur ^ 1].reserve((size_t)2 * nin * NW, 0, stream);
+        state_key.reserve((size_t)(n_states + nin) * KW, (size_t)n_states * KW, stream);
+        edge_src.reserve((size_t)(n_edges + nin), (size_t)n_edges, stream);
+        edge_dst.reserve((size_t)(n_edges + nin), (size_t)n_edges, stream);
+        edge_label.reserve((size_t)(n_edges + nin) * V, (size_t)n_edges * V, stream);
+        ensure_table(n_states + nin);
+    }
+
+    // The wave loop in one cooperative launch (search_kernel); the host only steps in when the kernel asks.
+    void run_persistent(double deadline) {
+        begin_timing();
+        const int NW = dm.node_words, KW = dm.key_words, V = dm.V, RW = dm.rec_words;
+        zero_wave_counters();
+        while (n_in > 0) {
+            if (deadline > 0 && now_s() > deadline) throw Failure(STCSP_ERR_TIMEOUT, "time limit reached");
+            SearchArgs sa{};
+            sa.ctl = d_ctl.p;
+            sa.counters = counters.p;
+            sa.frontier[0] = frontier[0].p;
+            sa.frontier[1] = frontier[1].p;
+            sa.out_cap = (long long)(std::min(frontier[0].cap, frontier[1].cap) / NW);
+            sa.leaves = leaves.p;
+            sa.leaf_cap = (long long)(leaves.cap / RW);
+            sa.unresolved = unresolved.p;
+            sa.unresolved_cap = (long long)unresolved.cap;
+            sa.capmap = d_capmap.p;
+            sa.capvals = d_capvals.p;
+            sa.capmap_mask = capmap.empty() ? -1 : (int32_t)capmap.size() - 1;
+            sa.table = table.p;
+            sa.table_mask = table_size - 1;
+            sa.state_key = state_key.p;
+            sa.state_cap = (long long)(state_key.cap / KW);
+            sa.edge_src = edge_src.p;
+            sa.edge_dst = edge_dst.p;
+            sa.edge_label = edge_label.p;
+            sa.edge_cap = (long long)std::min(edge_src.cap, edge_label.cap / (size_t)V);
+            DBuf<unsigned long long> trace;
+            const long long trace_waves = 256;
+            if (opt.verbosity > 2) {
+                trace.reserve((size_t)trace_waves * 5, 0, stream);
+                CK(cudaMemsetAsync(trace.p, 0, (size_t)trace_waves * 5 * 8, stream));
+                sa.trace = trace.p;
+                sa.trace_cap = trace_waves;
+            }
+            memset(h_ctl, 0, sizeof *h_ctl);
+            h_ctl->n_in = n_in;
+            h_ctl->cur = cur;
+            h_ctl->status = SEARCH_RUN;
+            h_ctl->waves_left = deadline > 0 ? 256 : (1ll << 40);
+            CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof *h_ctl, cudaMemcpyHostToDevice, stream));
+            CK(launch_search(dm, sa, search_grid, stream));
+            CK(cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof *h_ctl, cudaMemcpyDeviceToHost, stream));
+            read_counters();
+            if (opt.verbosity > 2) {
+                std::vector<unsigned long long> tr((size_t)trace_waves * 5);
+                CK(cudaMemcpy(tr.data(), trace.p, tr.size() * 8, cudaMemcpyDeviceToHost));
+                for (long long w = 0; w < std::min<long long>(trace_waves, h_ctl->t_waves); w++)
+                    fprintf(stderr, "[stcsp] kernel wave %lld: expand %.1f us, route %.1f us, ingest %.1f us, bookkeeping %.1f us, gap to next %.1f us\n",
+                            w, (tr[w * 5 + 1] - tr[w * 5]) / 1e3, (tr[w * 5 + 2] - tr[w * 5 + 1]) / 1e3,
+                            (tr[w * 5 + 3] - tr[w * 5 + 2]) / 1e3, (tr[w * 5 + 4] - tr[w * 5 + 3]) / 1e3,
+                            w + 1 < h_ctl->t_waves ? (tr[w * 5 + 5] - tr[w * 5 + 4]) / 1e3 : 0.0);
+                CK(cudaStreamSynchronize(stream));
+            }
+            t_launches++;
+            h2d += sizeof *h_ctl;
+            d2h += sizeof *h_ctl;
+            t_nodes += h_ctl->t_nodes;
+            t_fails += h_ctl->t_fails;
+            t_tuples += h_ctl->t_tuples;
+            t_revisions += h_ctl->t_revisions;
+            t_dominance += h_ctl->t_dominance;
+            t_leaves += h_ctl->t_leaves;
+            t_waves += h_ctl->t_waves;
+            if (h_ctl->overflow & ~1) throw Failure(STCSP_ERR_CAPACITY, "internal: a pool overflowed inside the search kernel");
+            n_in = h_ctl->n_in;
+            cur = h_ctl->cur;
+            n_states = (long long)h_counters[C_STATES];
+            n_edges = (long long)h_counters[C_EDGES];
+            switch (h_ctl->status) {
+                case SEARCH_DONE:
+                    n_in = 0;
+                    break;
+                case SEARCH_YIELD:
+                    break;
+                case SEARCH_GROW:
+                    ensure_wave_capacity(n_in);
+                    break;
+                case SEARCH_RETRY:
+                    frontier[cur ^ 1].reserve((size_t)std::max<unsigned long long>(h_counters[C_OUT] + h_counters[C_OUT] / 4,
+                                                                                  2 * (frontier[cur ^ 1].cap / NW)) * NW, 0, stream);
+                    frontier[cur].reserve(frontier[cur ^ 1].cap, (size_t)n_in * NW, stream);
+                    zero_wave_counters();
+                    break;
+                case SEARCH_INGEST: {
+                    // expand + route of this wave are done on the device; finish it here
+                    n_out = (long long)h_counters[C_OUT];
+                    n_leaves = (long long)h_counters[C_LEAVES];
+                    n_unres = (long long)h_counters[C_UNRESOLVED];
+                    t_nodes += (long long)h_counters[C_NODES];
+                    t_fails += (long long)h_counters[C_FAILS];
+                    t_tuples += (long long)h_counters[C_TUPLES];
+                    t_revisions += (long long)h_counters[C_REVISIONS];
+                    t_leaves += n_leaves;
+                    t_waves++;
+                    pending.clear();
+                    if (n_unres > 0) {
+                        collect_pending();
+                        std::vector<int32_t> req = pending;
+                        resolve(req.data(), (int64_t)(req.size() / (size_t)(1 + V)));
+                    }
+                    int64_t next = 0;
+                    ingest(nullptr, 0, &next);
+                    zero_wave_counters();
+                    break;
+                }
+                default:
+                    throw Failure(STCSP_ERR_CUDA, "search kernel returned an unknown status");
+            }
+        }
     }
 
     void begin_timing() {
@@ -1229,6 +1379,10 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
         const double deadline = s->opt.time_limit_s > 0 ? t0 + s->opt.time_limit_s : 0;
         int64_t frontier = s->n_in;
         std::vector<int32_t> req;
+        if (!s->opt.profile_kernels && s->search_grid > 0) {       // default: the wave loop runs on the device
+            s->run_persistent(deadline);
+            frontier = 0;
+        }
         while (frontier > 0) {
             if (deadline > 0 && now_s() > deadline) throw Failure(STCSP_ERR_TIMEOUT, "time limit reached");
             int64_t n_leaves = 0, n_pending = 0;
