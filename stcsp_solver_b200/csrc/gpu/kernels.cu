@@ -37,7 +37,8 @@ struct WarpMem {
     // node-group state: private to a warp (warp-per-node mode) or shared by the CTA (CTA-per-node mode)
     int32_t *nodew;     // node words (header + domains)
     uint32_t *dirty;    // propagator bitmask: to be revised
-    uint32_t *dcur;     // CTA mode: the propagators of the current round
+    uint32_t *dcur;     // CTA mode: the propagators of the current cooperative round
+    uint32_t *hvy;      // cheap-class propagators that turned out to need 32 lanes (many unbound variables)
     int32_t *flag;      // [0] wipe-out, [1] propagators in the current round, [2..3] broadcast of the child base index
     // per-warp scratch of the revision in flight
     u64 *supp;          // [max_scope] support sets of the constraint being revised
@@ -53,7 +54,7 @@ struct WarpMem {
 __host__ __device__ inline size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
 
 __host__ __device__ inline size_t node_bytes(const DevModel &m) {
-    return align8((size_t)m.node_words * 4) + 2 * align8((size_t)m.max_words * 4) + 16;
+    return align8((size_t)m.node_words * 4) + 3 * align8((size_t)m.max_words * 4) + 16;
 }
 
 __host__ __device__ inline size_t scratch_bytes(const DevModel &m) {
@@ -75,6 +76,7 @@ __device__ inline WarpMem carve(unsigned char *smem, const DevModel &m, int node
     w.nodew = (int32_t *)p; p += align8((size_t)m.node_words * 4);
     w.dirty = (uint32_t *)p; p += align8((size_t)m.max_words * 4);
     w.dcur = (uint32_t *)p; p += align8((size_t)m.max_words * 4);
+    w.hvy = (uint32_t *)p; p += align8((size_t)m.max_words * 4);
     w.flag = (int32_t *)p;
     p = smem + (size_t)kExpandWarps * node_bytes(m) + (size_t)warp * scratch_bytes(m);
     w.supp = (u64 *)p; p += (size_t)m.max_scope * 8;
@@ -516,6 +518,201 @@ __device__ __forceinline__ bool revise(NodeCtx &c, int q) {
     return revise_until(c, con);
 }
 
+// ---- scalar revisions: ONE THREAD per propagator ------------------------------------------------------------
+// NEXT, UNTIL and relation-table propagators with at most two unbound prefix variables are cheap enough for a
+// single thread, so a warp revises up to 32 of them at once (a CTA: 256) instead of spending 32 lanes on one.
+// Domains are shared by the lanes: every write is an atomicAnd, every wake an atomicOr.
+enum ScalarResult : int { SR_OK = 0, SR_FAIL = 1, SR_HEAVY = 2 };
+
+__device__ __forceinline__ bool scalar_shrink(const DevModel &M, const DevSet &S, u64 *dom, uint32_t *dirty, int q, int idx,
+                                              u64 nd) {
+    const u64 old = atomicAnd(&dom[idx], nd);
+    const u64 now = old & nd;
+    if (now == 0ull) return false;
+    if (now != old) {
+        __threadfence_block();                          // the shrink is visible before anyone sees the wake
+        const uint32_t *wk = M.wake + S.wake_off + (size_t)idx * S.n_words;
+        for (int w = 0; w < S.n_words; w++) {
+            uint32_t m = wk[w];
+            if (w == (q >> 5)) m &= ~(1u << (q & 31));  // a revision is idempotent: it need not wake itself
+            if (m) atomicOr(&dirty[w], m);
+        }
+    }
+    return true;
+}
+
+__device__ int scalar_revise(const DevModel &M, const DevSet &S, int q, u64 *dom, uint32_t *dirty, int expire,
+                             unsigned long long &tuples) {
+    const DevProp pr = M.props[S.prop_off + q];
+    const DevCon con = M.cons[pr.con];
+    const int k = M.k, off = pr.offset;
+    if (con.kind == DK_NEXT) {
+        const int x = con.x, y = con.y;
+        const int s = M.lb[x] - M.lb[y];
+        for (int p = 0; p + 1 < k; p++) {
+            const u64 X = dom[x * k + p], Y = dom[y * k + p + 1];
+            const u64 nX = X & shift_bits(Y, -s) & width_mask(M.width[x]);
+            const u64 nY = Y & shift_bits(X, s) & width_mask(M.width[y]);
+            if (nX == 0ull || nY == 0ull) return SR_FAIL;
+            if (nX != X && !scalar_shrink(M, S, dom, dirty, q, x * k + p, nX)) return SR_FAIL;
+            if (nY != Y && !scalar_shrink(M, S, dom, dirty, q, y * k + p + 1, nY)) return SR_FAIL;
+        }
+        return SR_OK;
+    }
+    if (con.kind == DK_UNTIL) {
+        if ((expire >> con.until_idx) & 1) return SR_OK;
+        const u64 L = dom[con.x * k], R = dom[con.y * k];
+        if (__popcll(L) == 1 && __popcll(R) == 1) {
+            const int lv = M.lb[con.x] + __ffsll((long long)L) - 1;
+            const int rv = M.lb[con.y] + __ffsll((long long)R) - 1;
+            if (lv != 1 && rv != 1) return SR_FAIL;
+        }
+        return SR_OK;
+    }
+    // relation table
+    const int n = con.n_scope, pv = con.pivot;
+    int base = 0, nfree = 0, iy = 0, iz = 0, sy = 0, sz = 0, pidx = 0;
+    u64 Dy = 1ull, Dz = 1ull, Dp = 0ull;
+    for (int i = 0; i < n; i++) {
+        const int idx = M.scope[con.scope_off + i] * k + off;
+        const u64 d = dom[idx];
+        if (d == 0ull) return SR_FAIL;
+        if (i == pv) { Dp = d; pidx = idx; continue; }
+        const int st = M.stride[con.scope_off + i];
+        if ((d & (d - 1ull)) == 0ull) {
+            base += (__ffsll((long long)d) - 1) * st;
+        } else {
+            if (nfree == 0) { Dz = d; iz = idx; sz = st; }
+            else if (nfree == 1) { Dy = d; iy = idx; sy = st; }
+            nfree++;
+        }
+    }
+    if (nfree > 2) return SR_HEAVY;
+    if (nfree == 2 && __popcll(Dy) > __popcll(Dz)) {            // y: the smaller domain, walked in the outer loop
+        const u64 td = Dy; Dy = Dz; Dz = td;
+        int t = iy; iy = iz; iz = t;
+        t = sy; sy = sz; sz = t;
+    }
+    if (__popcll(Dy) * __popcll(Dz) > 192) return SR_HEAVY;     // long walks belong to 32 lanes
+    const u64 *T = M.tables + con.table_off + base;
+    u64 pm = 0ull, supp_y = 0ull, supp_z = 0ull;
+    for (u64 wy = Dy; wy; wy &= wy - 1ull) {
+        const int py = __ffsll((long long)wy) - 1;
+        const u64 *Ty = T + py * sy;
+        u64 row = 0ull;
+        for (u64 wz = Dz; wz; wz &= wz - 1ull) {
+            const int pz = __ffsll((long long)wz) - 1;
+            const u64 m = __ldg(Ty + pz * sz) & Dp;
+            if (m) { row |= m; supp_z |= 1ull << pz; }
+        }
+        if (row) { pm |= row; supp_y |= 1ull << py; }
+    }
+    tuples += (unsigned long long)(__popcll(Dy) * __popcll(Dz));
+    if (pm == 0ull) return SR_FAIL;
+    if (pm != Dp && !scalar_shrink(M, S, dom, dirty, q, pidx, pm)) return SR_FAIL;
+    if (nfree >= 1 && supp_z != Dz && !scalar_shrink(M, S, dom, dirty, q, iz, supp_z)) return SR_FAIL;
+    if (nfree == 2 && supp_y != Dy && !scalar_shrink(M, S, dom, dirty, q, iy, supp_y)) return SR_FAIL;
+    return SR_OK;
+}
+
+__device__ __forceinline__ uint32_t cheap_mask(const DevSet &S, int w) {
+    const int left = S.n_cheap - w * 32;
+    return left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+}
+
+// Propagate the node to a fixpoint.  Returns true on wipe-out.
+//   phase A  rounds of scalar revisions over the dirty cheap propagators, one per thread of the group
+//   phase B  what needs 32 lanes (bytecode enumerations, tables with many unbound variables): warp-cooperative,
+//            one at a time (warp per node) or dealt to the warps of the CTA (CTA per node); then back to A
+template <bool CTA>
+__device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned long long &st_rev,
+                          unsigned long long &my_tuples) {
+    const DevModel &M = ctx.M;
+    const DevSet &S = ctx.S;
+    WarpMem &wm = ctx.wm;
+    const int lane = ctx.lane;
+    for (;;) {
+        // ---- phase A
+        for (;;) {
+            bool myfail = false;
+            for (int q = gtid; q < S.n_cheap; q += gthreads) {
+                const uint32_t bit = 1u << (q & 31);
+                if (!(wm.dirty[q >> 5] & bit)) continue;
+                atomicAnd(&wm.dirty[q >> 5], ~bit);
+                const int r = scalar_revise(M, S, q, ctx.dom, wm.dirty, ctx.expire, my_tuples);
+                st_rev++;
+                if (r == SR_FAIL) myfail = true;
+                else if (r == SR_HEAVY) atomicOr(&wm.hvy[q >> 5], bit);
+            }
+            bool more, bad;
+            if (CTA) {
+                bad = __syncthreads_or(myfail) != 0;    // barrier: every revision of the round is done
+                more = __syncthreads_or(gtid < S.n_words && (wm.dirty[gtid] & cheap_mask(S, gtid)) != 0u) != 0;
+            } else {
+                bad = __any_sync(0xffffffffu, myfail);
+                more = __any_sync(0xffffffffu, lane < S.n_words && (wm.dirty[lane] & cheap_mask(S, lane)) != 0u);
+            }
+            if (bad) return true;
+            if (!more) break;
+        }
+        // ---- phase B
+        if (!CTA) {
+            int q = -1;
+            for (int base = 0; base < S.n_words; base += 32) {
+                const uint32_t w = base + lane < S.n_words ? (wm.hvy[base + lane] | (wm.dirty[base + lane] & ~cheap_mask(S, base + lane))) : 0u;
+                const unsigned b = __ballot_sync(0xffffffffu, w != 0u);
+                if (b) {
+                    const int l = __ffs(b) - 1;
+                    const uint32_t ww = __shfl_sync(0xffffffffu, w, l);
+                    q = (base + l) * 32 + __ffs(ww) - 1;
+                    break;
+                }
+            }
+            if (q < 0) return false;                    // fixpoint
+            __syncwarp();
+            if (lane == 0) {
+                wm.hvy[q >> 5] &= ~(1u << (q & 31));
+                wm.dirty[q >> 5] &= ~(1u << (q & 31));
+            }
+            __syncwarp();
+            const bool ok = revise<false>(ctx, q);
+            __syncwarp();
+            if (lane == 0) wm.dirty[q >> 5] &= ~(1u << (q & 31));       // idempotent: its own wake is void
+            __syncwarp();
+            st_rev += lane == 0;
+            if (!ok) return true;
+        } else {
+            if (threadIdx.x == 0) {
+                int total = 0;
+                for (int w = 0; w < S.n_words; w++) {
+                    const uint32_t take = wm.hvy[w] | (wm.dirty[w] & ~cheap_mask(S, w));
+                    wm.dcur[w] = take;
+                    wm.hvy[w] = 0u;
+                    wm.dirty[w] &= ~take;
+                    total += __popc(take);
+                }
+                wm.flag[1] = total;
+            }
+            __syncthreads();
+            if (wm.flag[1] == 0) return false;          // fixpoint
+            int seen_bits = 0;
+            bool ok = true;
+            for (int w = 0; ok && w < S.n_words; w++) {
+                uint32_t bits = wm.dcur[w];
+                while (ok && bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if ((seen_bits++ % kExpandWarps) != gw) continue;
+                    ok = revise<true>(ctx, w * 32 + b);
+                    __syncwarp();
+                    st_rev += lane == 0;
+                }
+            }
+            if (__syncthreads_or(!ok)) return true;
+        }
+    }
+}
+
 // CTA = true : one CTA per search node, its warps revise different dirty propagators of the node concurrently
 //              (narrow waves: fewer nodes than resident CTAs, the latency of one node is the wave's duration).
 // CTA = false: one warp per search node (wide waves: throughput).
@@ -530,13 +727,14 @@ __device__ __forceinline__ void expand_body(const DevModel &M, const ExpandArgs 
     const int gwarps = CTA ? kExpandWarps : 1;          // warps working on one node
     const int gw = CTA ? warp : 0;                      // this warp's index among them
     const int gtid = CTA ? threadIdx.x : lane, gthreads = gwarps * 32;
-    unsigned long long st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0;
+    unsigned long long st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;
 
     for (long long ni = first; ni < n_in; ni += step) {
         const int32_t *src = P.in_nodes + ni * NW;
         if (CTA) __syncthreads();                       // the previous node's shared state is no longer in use
         for (int w = gtid; w < NW; w += gthreads) wm.nodew[w] = src[w];
         if (gtid == 0) wm.flag[0] = 0;
+        for (int w = gtid; w < M.max_words; w += gthreads) wm.hvy[w] = 0u;
         if (CTA) __syncthreads(); else __syncwarp();
         const int cid = wm.nodew[1], bvar = wm.nodew[3];
         const DevSet S = M.sets[cid];
@@ -559,70 +757,7 @@ __device__ __forceinline__ void expand_body(const DevModel &M, const ExpandArgs 
         }
         if (CTA) __syncthreads(); else __syncwarp();
 
-        if (!CTA) {
-            // Gauss-Seidel: always the cheapest dirty propagator next
-            while (!fail) {
-                int q = -1;
-                for (int base = 0; base < S.n_words; base += 32) {
-                    const uint32_t w = base + lane < S.n_words ? wm.dirty[base + lane] : 0u;
-                    const unsigned b = __ballot_sync(0xffffffffu, w != 0u);
-                    if (b) {
-                        const int l = __ffs(b) - 1;
-                        const uint32_t ww = __shfl_sync(0xffffffffu, w, l);
-                        q = (base + l) * 32 + __ffs(ww) - 1;
-                        break;
-                    }
-                }
-                if (q < 0) break;
-                const bool ok = revise<false>(ctx, q);
-                __syncwarp();
-                if (lane == 0) wm.dirty[q >> 5] &= ~(1u << (q & 31));                // revisions are idempotent
-                __syncwarp();
-                st_rev++;
-                fail = !ok;
-            }
-        } else {
-            // Rounds: the dirty propagators of one cost class are dealt to the warps; whatever they wake runs in a
-            // later round.  Cheap propagators (NEXT, UNTIL, relation tables) always go before bytecode enumerations.
-            while (!fail) {         // `fail` is uniform over the CTA here (every warp looked at the same domains)
-                if (threadIdx.x == 0) {
-                    bool cheap = false;
-                    for (int w = 0; w < S.n_words; w++) {
-                        const int left = S.n_cheap - w * 32;
-                        const uint32_t cm = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
-                        cheap |= (wm.dirty[w] & cm) != 0u;
-                    }
-                    int total = 0;
-                    for (int w = 0; w < S.n_words; w++) {
-                        const int left = S.n_cheap - w * 32;
-                        const uint32_t cm = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
-                        const uint32_t take = cheap ? (wm.dirty[w] & cm) : wm.dirty[w];
-                        wm.dcur[w] = take;
-                        wm.dirty[w] &= ~take;
-                        total += __popc(take);
-                    }
-                    wm.flag[1] = total;
-                }
-                __syncthreads();
-                if (wm.flag[1] == 0 || wm.flag[0] != 0) break;
-                int seen_bits = 0;
-                bool ok = true;
-                for (int w = 0; ok && w < S.n_words; w++) {
-                    uint32_t bits = wm.dcur[w];
-                    while (ok && bits) {
-                        const int b = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        if ((seen_bits++ % kExpandWarps) != gw) continue;
-                        ok = revise<true>(ctx, w * 32 + b);
-                        __syncwarp();
-                        st_rev++;
-                    }
-                }
-                if (!ok && lane == 0) wm.flag[0] = 1;
-                __syncthreads();
-            }
-            fail = fail || wm.flag[0] != 0;
-        }
+        if (!fail) fail = propagate<CTA>(ctx, gw, gtid, gthreads, st_rev, my_tuples);   // `fail` is uniform over the group
         st_tuples += ctx.tuples;
         if (gw == 0) st_nodes++;
         if (fail) { if (gw == 0) st_fails++; continue; }
@@ -683,6 +818,9 @@ __device__ __forceinline__ void expand_body(const DevModel &M, const ExpandArgs 
             }
         }
     }
+    // st_rev / my_tuples are per thread (scalar revisions), st_tuples is warp-uniform (cooperative revisions)
+    st_rev = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_rev);
+    st_tuples += (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)my_tuples);
     if (lane == 0 && (st_nodes | st_tuples | st_rev)) {
         if (st_nodes) atomicAdd(&P.counters[C_NODES], st_nodes);
         if (st_fails) atomicAdd(&P.counters[C_FAILS], st_fails);
