@@ -96,7 +96,8 @@ typedef struct stcsp_options {
     int64_t max_states;              /* capacity of the state table */
     int64_t max_edges;               /* capacity of the edge store */
     int32_t reserved0;
-    int32_t profile_kernels;         /* 1: CUDA-event time every expand launch (fills expand_ms) */
+    int32_t profile_kernels;         /* 1: step-wise path (one expand / route / ingest launch per wave) with every expand launch
+                                        timed by CUDA events, instead of the persistent search kernel */
     int32_t no_trim;                 /* 1: stcsp_gpu_solve returns the untrimmed automaton */
     int32_t reserved[5];
 } stcsp_options_t;
@@ -142,8 +143,9 @@ typedef struct stcsp_automaton {
     int64_t n_kernel_launches;
     double solve_ms;                 /* device time, CUDA events around the whole search */
     double wall_ms;                  /* host wall clock of the call incl. uploads/downloads */
-    double expand_ms;                /* device time inside the expand kernel only (sum over waves; needs profile_kernels) */
-    int64_t n_expand_launches;
+    double expand_ms;                /* device time inside the dominant kernel, CUDA events around every launch: the persistent
+                                        search kernel (default path) or the expand kernel (profile_kernels = 1, step-wise path) */
+    int64_t n_expand_launches;       /* launches of that kernel */
     int64_t algorithmic_bytes;       /* SURVEY.md section 8(d) formula with this run's counts */
     int64_t h2d_bytes, d2h_bytes;
     void *impl;                      /* private */

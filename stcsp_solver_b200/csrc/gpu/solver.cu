@@ -417,8 +417,8 @@ struct stcsp_session {
         dm.max_scope = sets.max_scope();
         dm.max_stack = sets.max_stack();
         dm.max_words = (sets.max_props() + 31) / 32;
-        dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : 512;
-        dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : 8;
+        dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : 8;
+        dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : 4;
         dm.lb = d_lb.p;
         dm.width = d_width.p;
         dm.sig_vars = d_sigvars.p;
@@ -627,9 +627,17 @@ struct stcsp_session {
             h_ctl->status = SEARCH_RUN;
             h_ctl->waves_left = deadline > 0 ? 256 : (1ll << 40);
             CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof *h_ctl, cudaMemcpyHostToDevice, stream));
+            CK(cudaEventRecord(evk0, stream));
             CK(launch_search(dm, sa, search_grid, stream));
+            CK(cudaEventRecord(evk1, stream));
             CK(cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof *h_ctl, cudaMemcpyDeviceToHost, stream));
             read_counters();
+            {
+                float kms = 0;
+                CK(cudaEventElapsedTime(&kms, evk0, evk1));
+                expand_ms += kms;
+                t_expand_launches++;
+            }
             if (opt.verbosity > 2) {
                 std::vector<unsigned long long> tr((size_t)trace_waves * 5);
                 CK(cudaMemcpy(tr.data(), trace.p, tr.size() * 8, cudaMemcpyDeviceToHost));

@@ -1,17 +1,17 @@
 """Sweep the enumeration budgets; prints device ms per setting (best of 3)."""
 import sys
 from stcsp_solver_b200 import binding, instances
-names = sys.argv[1:] or ["juggling_b6_f6_nosym", "partialorder_14", "digitinvader9"]
+names = sys.argv[1:] or ["juggling_b6_f6_nosym", "partialorder_14", "digitinvader9", "juggling_b5_f6"]
 for name in names:
     m = binding.Model(instances.by_name(name))
     binding.solve(m)
-    for now in (64, 512, 4096, 32768):
-        for ahead in (1, 16, 64, 512, 4096):
+    for now in (8, 64, 512, 4096):
+        for ahead in (1, 8, 64):
             best = None
             for _ in range(3):
                 a = binding.solve(m, binding.default_options(enum_limit_now=now, enum_limit_ahead=ahead))
                 st = a.stats()
                 if best is None or st["solve_ms"] < best["solve_ms"]:
                     best = st
-            print("%-24s now %6d ahead %5d: dev_ms %8.3f nodes %8d fails %7d tuples %10d states %6d waves %4d" % (
-                name, now, ahead, best["solve_ms"], best["n_search_nodes"], best["n_fails"], best["n_tuples"], best["n_states"], best["n_waves"]), flush=True)
+            print("%-24s now %6d ahead %5d: dev_ms %8.3f nodes %8d fails %7d tuples %10d rev %9d states %6d" % (
+                name, now, ahead, best["solve_ms"], best["n_search_nodes"], best["n_fails"], best["n_tuples"], best["n_revisions"], best["n_states"]), flush=True)
