@@ -217,6 +217,9 @@ void SetTable::compile_set(int32_t s) {
     DevSet ds{};
     const int32_t V = n_vars();
     ds.prop_off = (int32_t)dev_props.size();
+    ds.con_off = (int32_t)dev_cons.size();
+    ds.scope_off = (int32_t)dev_scope.size();
+    ds.code_off = (int32_t)dev_code.size();
     ds.until_off = (int32_t)dev_aux.size();
     std::vector<int32_t> until_right, next_pairs;
     int32_t until_idx = 0;
@@ -276,6 +279,9 @@ void SetTable::compile_set(int32_t s) {
     dev_aux.insert(dev_aux.end(), hs.cap_vars.begin(), hs.cap_vars.end());
 
     ds.n_prop = (int32_t)dev_props.size() - ds.prop_off;
+    ds.n_con = (int32_t)dev_cons.size() - ds.con_off;
+    ds.n_scope = (int32_t)dev_scope.size() - ds.scope_off;
+    ds.n_code = (int32_t)dev_code.size() - ds.code_off;
     // the propagation loop runs the lowest dirty index first: cheap propagators before expensive ones
     auto cost = [&](const DevProp &pr) -> long long {
         const DevCon &dc = dev_cons[pr.con];
@@ -356,6 +362,18 @@ void SetTable::assign_table(DevCon &dc, const Constraint &c) {
     dc.table_entries = ref.entries;
     dc.table_off = ref.off;
     for (int i = 0; i < n; i++) dev_stride[dc.scope_off + i] = ref.strides[i];
+}
+
+size_t SetTable::max_stage_bytes() const {
+    auto a8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
+    size_t best = 0;
+    for (const DevSet &ds : dev_sets) {
+        size_t b = a8((size_t)ds.n_prop * sizeof(DevProp)) + a8((size_t)ds.n_con * sizeof(DevCon)) +
+                   2 * a8((size_t)ds.n_scope * 4) + a8((size_t)n_vars() * k_ * ds.n_words * 4) + 2 * a8((size_t)n_vars() * 4) +
+                   a8((size_t)ds.n_code * sizeof(Instr));
+        best = std::max(best, b);
+    }
+    return best;
 }
 
 void SetTable::resolve_static(int32_t s) {

@@ -71,6 +71,10 @@ struct DevSet {            // one constraint set
     int32_t n_next, next_off;      // (x, y) pairs of the NEXT constraints (into aux pool)
     int32_t max_stack;
     int32_t n_cheap;       // propagators [0, n_cheap) are NEXT / UNTIL / relation tables, the rest enumerate bytecode
+    // contiguous ranges of this set in the con / scope / code pools (staged into shared memory by the kernels)
+    int32_t con_off, n_con;
+    int32_t scope_off, n_scope;
+    int32_t code_off, n_code;
 };
 
 struct HostSet {
@@ -107,6 +111,8 @@ class SetTable {
     int32_t max_scope() const { return max_scope_; }
     int32_t max_stack() const { return max_stack_; }
     int32_t max_props() const { return max_props_; }
+    // shared-memory bytes needed to stage the metadata of the largest set (see stage_set in kernels.cu)
+    size_t max_stage_bytes() const;
     const std::vector<int32_t> &lb() const { return lb_; }
     const std::vector<int32_t> &width() const { return width_; }
     const HostSet &host_set(int32_t s) const { return sets_[s]; }

@@ -106,7 +106,7 @@ __device__ __forceinline__ int eval_tuple(const Instr *__restrict__ code, const 
     int pc = 0, sp = 0, tos = 0;
     bool valid = true;
     for (;;) {
-        const int2 in = __ldg(reinterpret_cast<const int2 *>(code) + pc);
+        const int2 in = reinterpret_cast<const int2 *>(code)[pc];       // generic load: the bytecode may be staged in shared memory
         pc++;
         const int arg = in.y;
         int l;
@@ -713,31 +713,92 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
     }
 }
 
+// ---- constraint-set metadata staged in shared memory ------------------------------------------------------
+// The propagators of a set (descriptors, scopes, strides, wake masks, bytecode, variable bounds) are read over and
+// over by every revision; the CTA copies the set most of its nodes belong to into shared memory once per wave and
+// hands the revisions a DevModel whose pointers are biased so that the ABSOLUTE pool indices still work.
+__device__ __forceinline__ unsigned char *stage_base(unsigned char *smem, const DevModel &m) {
+    return smem + (size_t)kExpandWarps * (node_bytes(m) + scratch_bytes(m));
+}
+
+// Called by every thread of the CTA (contains barriers).  Returns the constraint set staged, -1 if none.
+__device__ int stage_set(const DevModel &M, unsigned char *smem, int cid) {
+    DevModel *sm = reinterpret_cast<DevModel *>(stage_base(smem, M));
+    if (M.stage_bytes == 0 || cid < 0) return -1;
+    unsigned char *p = reinterpret_cast<unsigned char *>(sm) + align8(sizeof(DevModel));
+    const DevSet S = M.sets[cid];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t wake_words = (size_t)M.V * M.k * S.n_words;
+    int2 *s_props = reinterpret_cast<int2 *>(p); p += align8((size_t)S.n_prop * sizeof(DevProp));
+    int2 *s_cons = reinterpret_cast<int2 *>(p); p += align8((size_t)S.n_con * sizeof(DevCon));
+    int32_t *s_scope = reinterpret_cast<int32_t *>(p); p += align8((size_t)S.n_scope * 4);
+    int32_t *s_stride = reinterpret_cast<int32_t *>(p); p += align8((size_t)S.n_scope * 4);
+    uint32_t *s_wake = reinterpret_cast<uint32_t *>(p); p += align8(wake_words * 4);
+    int32_t *s_lb = reinterpret_cast<int32_t *>(p); p += align8((size_t)M.V * 4);
+    int32_t *s_width = reinterpret_cast<int32_t *>(p); p += align8((size_t)M.V * 4);
+    int2 *s_code = reinterpret_cast<int2 *>(p);
+    __syncthreads();                                    // nobody still reads the previous staging
+    const int2 *g_props = reinterpret_cast<const int2 *>(M.props + S.prop_off);
+    for (int i = tid; i < S.n_prop; i += nt) s_props[i] = g_props[i];
+    const int2 *g_cons = reinterpret_cast<const int2 *>(M.cons + S.con_off);
+    for (int i = tid; i < S.n_con * (int)(sizeof(DevCon) / 8); i += nt) s_cons[i] = g_cons[i];
+    for (int i = tid; i < S.n_scope; i += nt) {
+        s_scope[i] = M.scope[S.scope_off + i];
+        s_stride[i] = M.stride[S.scope_off + i];
+    }
+    for (int i = tid; i < (int)wake_words; i += nt) s_wake[i] = M.wake[S.wake_off + i];
+    for (int i = tid; i < M.V; i += nt) {
+        s_lb[i] = M.lb[i];
+        s_width[i] = M.width[i];
+    }
+    const int2 *g_code = reinterpret_cast<const int2 *>(M.code + S.code_off);
+    for (int i = tid; i < S.n_code; i += nt) s_code[i] = g_code[i];
+    if (tid == 0) {
+        DevModel m = M;
+        m.props = reinterpret_cast<const DevProp *>(s_props) - S.prop_off;
+        m.cons = reinterpret_cast<const DevCon *>(s_cons) - S.con_off;
+        m.scope = s_scope - S.scope_off;
+        m.stride = s_stride - S.scope_off;
+        m.wake = s_wake - S.wake_off;
+        m.lb = s_lb;
+        m.width = s_width;
+        m.code = reinterpret_cast<const Instr *>(s_code) - S.code_off;
+        *sm = m;
+    }
+    __syncthreads();
+    return cid;
+}
+
 // CTA = true : one CTA per search node, its warps revise different dirty propagators of the node concurrently
 //              (narrow waves: fewer nodes than resident CTAs, the latency of one node is the wave's duration).
 // CTA = false: one warp per search node (wide waves: throughput).
 template <bool CTA>
-__device__ __forceinline__ void expand_body(const DevModel &M, const ExpandArgs &P, unsigned char *smem) {
+__device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs &P, unsigned char *smem) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpMem wm = carve(smem, M, CTA ? 0 : warp, warp);
+    WarpMem wm = carve(smem, Mg, CTA ? 0 : warp, warp);
     const long long n_in = P.n_in;
     const long long first = CTA ? (long long)blockIdx.x : (long long)blockIdx.x * kExpandWarps + warp;
     const long long step = CTA ? (long long)gridDim.x : (long long)gridDim.x * kExpandWarps;
-    const int V = M.V, k = M.k, NW = M.node_words;
+    const int V = Mg.V, k = Mg.k, NW = Mg.node_words;
     const int gwarps = CTA ? kExpandWarps : 1;          // warps working on one node
     const int gw = CTA ? warp : 0;                      // this warp's index among them
     const int gtid = CTA ? threadIdx.x : lane, gthreads = gwarps * 32;
     unsigned long long st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;
+    // stage the constraint set of this CTA's first node (waves are almost always homogeneous)
+    const long long probe = CTA ? (long long)blockIdx.x : (long long)blockIdx.x * kExpandWarps;
+    const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1);
+    const DevModel &Ms = *reinterpret_cast<const DevModel *>(stage_base(smem, Mg));
 
     for (long long ni = first; ni < n_in; ni += step) {
         const int32_t *src = P.in_nodes + ni * NW;
         if (CTA) __syncthreads();                       // the previous node's shared state is no longer in use
         for (int w = gtid; w < NW; w += gthreads) wm.nodew[w] = src[w];
         if (gtid == 0) wm.flag[0] = 0;
-        for (int w = gtid; w < M.max_words; w += gthreads) wm.hvy[w] = 0u;
+        for (int w = gtid; w < Mg.max_words; w += gthreads) wm.hvy[w] = 0u;
         if (CTA) __syncthreads(); else __syncwarp();
         const int cid = wm.nodew[1], bvar = wm.nodew[3];
-        const DevSet S = M.sets[cid];
+        const DevModel &M = cid == staged ? Ms : Mg;    // metadata from shared memory when this node's set is the staged one
+        const DevSet S = Mg.sets[cid];
         NodeCtx ctx{M, S, wm, reinterpret_cast<u64 *>(wm.nodew + 4), lane, wm.nodew[2], 0ull};
         u64 *dom = ctx.dom;
 
@@ -1236,7 +1297,9 @@ uint32_t state_key_hash(const int32_t *key, int key_words) {
 
 int32_t owner_of_hash(uint32_t h, int32_t world) { return world > 1 ? (int32_t)(owner_hash(h) % (uint32_t)world) : 0; }
 
-size_t expand_smem_bytes(const DevModel &m) { return (node_bytes(m) + scratch_bytes(m)) * kExpandWarps; }
+size_t expand_smem_bytes(const DevModel &m) {
+    return (node_bytes(m) + scratch_bytes(m)) * kExpandWarps + align8(sizeof(DevModel)) + align8((size_t)m.stage_bytes);
+}
 
 static void configure_expand(size_t smem) {
     static size_t configured = 0;

@@ -44,6 +44,7 @@ struct DevModel {
     int32_t node_words, rec_words, key_words;
     int32_t n_sig, sig_len;
     int32_t max_scope, max_stack, max_words;
+    int32_t stage_bytes;        // shared memory reserved per CTA for one constraint set's metadata (0: never staged)
     long long enum_now, enum_ahead;
     const int32_t *lb, *width, *sig_vars;
     const DevSet *sets;

@@ -417,6 +417,10 @@ struct stcsp_session {
         dm.max_scope = sets.max_scope();
         dm.max_stack = sets.max_stack();
         dm.max_words = (sets.max_props() + 31) / 32;
+        {
+            const size_t sb = sets.max_stage_bytes();
+            dm.stage_bytes = sb <= 40 * 1024 ? (int32_t)sb : 0;     // larger sets stay in global memory / L1
+        }
         dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : 8;
         dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : 4;
         dm.lb = d_lb.p;

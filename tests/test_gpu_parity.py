@@ -71,6 +71,41 @@ def test_enumeration_budget_does_not_change_the_automaton(limits):
         assert sol.canonical_sha256() == g["sha256"], (name, limits)
 
 
+@pytest.mark.parametrize("name", ["juggling_b5_f6", "juggling_b5_f6_nosym", "digitinvader3", "partialorder_11", "probe_first_capture",
+                                  "probe_at2", "probe_until_two"])
+def test_stepwise_path_equals_persistent_kernel(name):
+    """profile_kernels=1 runs one expand / route / ingest launch per wave (the path the multi-GPU sessions use);
+    the default is the persistent search kernel.  Same automaton, same search statistics."""
+    g = GOLDENS[name]
+    _, a1, s1 = run_gpu(golden_text(g))
+    _, a2, s2 = run_gpu(golden_text(g), (), profile_kernels=1)
+    assert s1.canonical_sha256() == s2.canonical_sha256() == g["sha256"]
+    st1, st2 = a1.stats(), a2.stats()
+    for key in ("n_states", "n_edges", "n_search_nodes", "n_fails", "n_leaves", "n_waves"):
+        assert st1[key] == st2[key], key
+    assert st1["n_kernel_launches"] < st2["n_kernel_launches"]
+
+
+def test_session_api_single_rank_matches_solve():
+    """create / expand / [resolve] / ingest / finish / assemble / trim by hand == stcsp_gpu_solve."""
+    g = GOLDENS["probe_first_capture"]
+    model = binding.Model(g["model"])
+    s = binding.Session(model, None, 0, 1)
+    frontier, waves = 1, 0
+    while frontier > 0:
+        n_leaves, n_pending = s.expand()
+        if n_pending:
+            s.resolve(s.pending(n_pending))
+        frontier = s.ingest(None, 0)
+        waves += 1
+    part = s.finish()
+    s.close()
+    merged = binding.assemble([binding.part_to_arrays(part)], trim=True)
+    sol = binding.Solution(model, merged)
+    assert sol.canonical_sha256() == g["sha256"]
+    assert waves > 2
+
+
 @pytest.mark.parametrize("balls,height", [(3, 5), (5, 7), (6, 7), (7, 7)])
 def test_juggling_nosym_closed_form(balls, height):
     """juggling_b{B}_f{F}_nosym has 1 + F!/(F-B)! states; every non-root state is final."""
