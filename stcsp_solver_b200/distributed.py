@@ -99,28 +99,58 @@ def solve_distributed(model: binding.Model, options: Optional[binding.Options] =
     """Solve on all ranks of `group` (default: the world).  Returns the merged Automaton on rank 0, None elsewhere.
 
     The caller has initialised torch.distributed (backend nccl) and set the CUDA device of this process.
+    Per wave: local expand, ONE small all-gather (frontier size, pending requests, records for every rank) from
+    which each rank derives termination, the resolve decision and its receive counts, ONE payload all-to-all,
+    local ingest.
     """
     ex = WaveExchange(group)
     opts = options if options is not None else binding.default_options()
     opts.use_current_device = 1
     session = binding.Session(model, opts, ex.rank, ex.world)
     words = session.record_words
+    world, rank = ex.world, ex.rank
     stats = {"waves": 0, "records_sent": 0}
+    header = torch.zeros(2 + world, dtype=torch.int64, device=ex.device)
+    headers = torch.zeros((world, 2 + world), dtype=torch.int64, device=ex.device)
+    frontier = 1 if rank == 0 else 0
     try:
         while True:
             n_leaves, n_pending = session.expand()
-            if ex.total(n_pending) > 0:
+            send_counts = np.zeros(world, dtype=np.int64)
+            outbox = None
+            if n_pending == 0 and n_leaves > 0:
+                outbox = torch.empty((n_leaves, words), dtype=torch.int32, device=ex.device)
+                send_counts = session.outbox(outbox.data_ptr(), n_leaves)
+            header[0] = frontier
+            header[1] = n_pending
+            header[2:] = torch.as_tensor(send_counts)
+            dist.all_gather_into_tensor(headers.view(-1), header, group=ex.group)
+            h = headers.cpu().numpy()
+            if h[:, 0].sum() == 0:
+                break                                   # no rank had anything to expand: the search is over
+            if h[:, 1].sum() > 0:
+                # some rank met an unseen constraint-set transition: same sorted request list everywhere, then
+                # the ranks that were blocked group their leaves and the counts are exchanged again
                 session.resolve(ex.union_rows(session.pending(n_pending)))
-            outbox = torch.empty((max(n_leaves, 1), words), dtype=torch.int32, device=ex.device)
-            send_counts = session.outbox(outbox.data_ptr(), n_leaves)
-            recv_counts = ex.exchange_counts(send_counts)
-            inbox = ex.exchange_records(outbox[:n_leaves], send_counts, recv_counts)
-            torch.cuda.synchronize()
-            frontier = session.ingest(inbox.data_ptr() if inbox.shape[0] else None, int(inbox.shape[0]))
+                if n_leaves > 0 and outbox is None:
+                    outbox = torch.empty((n_leaves, words), dtype=torch.int32, device=ex.device)
+                    send_counts = session.outbox(outbox.data_ptr(), n_leaves)
+                header[1] = 0
+                header[2:] = torch.as_tensor(send_counts)
+                dist.all_gather_into_tensor(headers.view(-1), header, group=ex.group)
+                h = headers.cpu().numpy()
+            recv_counts = h[:, 2 + rank].copy()
+            if h[:, 2:].sum() > 0:
+                if outbox is None:
+                    outbox = torch.empty((0, words), dtype=torch.int32, device=ex.device)
+                inbox = ex.exchange_records(outbox, send_counts, recv_counts)
+                torch.cuda.current_stream().synchronize()
+                n_in = int(inbox.shape[0])
+                frontier = session.ingest(inbox.data_ptr() if n_in else None, n_in)
+            else:
+                frontier = session.ingest(None, 0)
             stats["waves"] += 1
             stats["records_sent"] += int(send_counts.sum())
-            if ex.total(frontier) == 0:
-                break
         part = session.finish()
         parts = ex.gather_arrays(binding.part_to_arrays(part))
     finally:

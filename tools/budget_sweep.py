@@ -1,5 +1,6 @@
 """Sweep the enumeration budgets; prints device ms per setting (best of 3)."""
-import sys
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stcsp_solver_b200 import binding, instances
 names = sys.argv[1:] or ["juggling_b6_f6_nosym", "partialorder_14", "digitinvader9", "juggling_b5_f6"]
 for name in names:

@@ -1,6 +1,8 @@
 """Quick GPU sanity run: every golden, states/edges/sha vs the reference; prints one line per case."""
 import sys, time, os
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import GOLDENS, golden_flags, golden_text
 from stcsp_solver_b200 import binding
 

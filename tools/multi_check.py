@@ -1,6 +1,6 @@
 """Run under torchrun: multi-GPU solve of several instances, checked against the reference goldens on rank 0."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist

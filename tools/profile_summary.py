@@ -6,7 +6,8 @@
 import collections
 import csv
 import subprocess
-import sys
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def launches(src, dst):

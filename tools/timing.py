@@ -1,6 +1,7 @@
 """Best-of-N device time per instance (steady state: caches warm): default path (persistent search kernel) and
 the step-wise path with per-launch expand timing."""
-import sys
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stcsp_solver_b200 import binding, instances
 names = sys.argv[1:] or ["juggling_b6_f6_nosym", "partialorder_14", "digitinvader9", "juggling_b5_f6", "digitinvader5"]
 for name in names:

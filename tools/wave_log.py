@@ -1,5 +1,6 @@
 """Per-wave log of one solve (library verbosity 1 + per-launch CUDA events)."""
-import sys
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stcsp_solver_b200 import binding, instances
 name = sys.argv[1] if len(sys.argv) > 1 else "juggling_b6_f6_nosym"
 kw = {}
