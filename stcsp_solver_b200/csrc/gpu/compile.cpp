@@ -8,6 +8,8 @@ namespace stcsp {
 
 namespace {
 
+constexpr int kScalarScope = 4;     // widest scope a single thread revises (see scalar_revise in kernels.cu)
+
 struct Emitter {
     const std::vector<int32_t> &scope;
     std::vector<Instr> &out;
@@ -283,17 +285,27 @@ void SetTable::compile_set(int32_t s) {
     ds.n_scope = (int32_t)dev_scope.size() - ds.scope_off;
     ds.n_code = (int32_t)dev_code.size() - ds.code_off;
     // the propagation loop runs the lowest dirty index first: cheap propagators before expensive ones
+    // A wide scope is scanned faster by 32 lanes than by one thread -- unless many wide tables are dirty together, in
+    // which case one thread each, side by side, wins (digitinvader: 22 of them; partial order: 2).
+    int wide_tables = 0;
+    for (int32_t q = ds.prop_off; q < (int32_t)dev_props.size(); q++) {
+        const DevCon &dc = dev_cons[dev_props[q].con];
+        wide_tables += dc.kind == DK_POINT && dc.pivot >= 0 && dc.n_scope > kScalarScope;
+    }
+    const bool wide_scalar = wide_tables >= 6;
     auto cost = [&](const DevProp &pr) -> long long {
         const DevCon &dc = dev_cons[pr.con];
         if (dc.kind != DK_POINT) return 0;
-        if (dc.pivot >= 0) return 1 + dc.table_entries;
+        // scalar class first (cheapest table first), then the cooperative tables, then the bytecode enumerations
+        if (dc.pivot >= 0)
+            return (dc.n_scope <= kScalarScope || wide_scalar) ? 1 + dc.table_entries : (1ll << 39) + dc.table_entries;
         return (1ll << 40) + dc.n_scope;
     };
     std::stable_sort(dev_props.begin() + ds.prop_off, dev_props.end(),
                      [&](const DevProp &a, const DevProp &b) { return cost(a) < cost(b); });
     ds.n_cheap = 0;
     for (int32_t q = 0; q < ds.n_prop; q++)
-        if (cost(dev_props[ds.prop_off + q]) < (1ll << 40)) ds.n_cheap = q + 1;
+        if (cost(dev_props[ds.prop_off + q]) < (1ll << 39)) ds.n_cheap = q + 1;
     ds.n_words = std::max(1, (ds.n_prop + 31) / 32);
     max_props_ = std::max(max_props_, ds.n_prop);
     ds.wake_off = (int32_t)dev_wake.size();

@@ -70,7 +70,8 @@ struct DevSet {            // one constraint set
     int32_t n_until, until_off;    // right-hand variable of each until constraint (into aux pool)
     int32_t n_next, next_off;      // (x, y) pairs of the NEXT constraints (into aux pool)
     int32_t max_stack;
-    int32_t n_cheap;       // propagators [0, n_cheap) are NEXT / UNTIL / relation tables, the rest enumerate bytecode
+    int32_t n_cheap;       // propagators [0, n_cheap) are revised by one thread each (NEXT / UNTIL / tables over <= 4
+                           // variables); the rest need a warp (wide tables, then bytecode enumerations)
     // contiguous ranges of this set in the con / scope / code pools (staged into shared memory by the kernels)
     int32_t con_off, n_con;
     int32_t scope_off, n_scope;
