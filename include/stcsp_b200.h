@@ -99,7 +99,10 @@ typedef struct stcsp_options {
     int32_t profile_kernels;         /* 1: step-wise path (one expand / route / ingest launch per wave) with every expand launch
                                         timed by CUDA events, instead of the persistent search kernel */
     int32_t no_trim;                 /* 1: stcsp_gpu_solve returns the untrimmed automaton */
-    int32_t reserved[5];
+    int32_t lookahead;               /* pointwise constraints at time offsets >= 1: 0 default, 1 eager (propagated like the
+                                        current point, the reference's prefix-k consistency), 2 lazy (checked once, when every
+                                        variable of the current point is bound).  Never changes the automaton. */
+    int32_t reserved[4];
 } stcsp_options_t;
 
 /* ---------------------------------------------------------------------------------------------

@@ -309,13 +309,16 @@ void SetTable::compile_set(int32_t s) {
     ds.n_words = std::max(1, (ds.n_prop + 31) / 32);
     max_props_ = std::max(max_props_, ds.n_prop);
     ds.wake_off = (int32_t)dev_wake.size();
-    dev_wake.resize(dev_wake.size() + (size_t)V * k_ * ds.n_words, 0u);
+    // V*k rows of wake masks, then one more row: the pointwise propagators at look-ahead offsets (>= 1)
+    dev_wake.resize(dev_wake.size() + ((size_t)V * k_ + 1) * ds.n_words, 0u);
     auto wake = [&](int32_t var, int32_t off, int32_t q) {
         dev_wake[ds.wake_off + ((size_t)var * k_ + off) * ds.n_words + q / 32] |= 1u << (q % 32);
     };
     for (int32_t q = 0; q < ds.n_prop; q++) {
         const DevProp &pr = dev_props[ds.prop_off + q];
         const DevCon &dc = dev_cons[pr.con];
+        if (dc.kind == DK_POINT && pr.offset >= 1)
+            dev_wake[ds.wake_off + (size_t)V * k_ * ds.n_words + q / 32] |= 1u << (q % 32);
         if (dc.kind == DK_POINT) {
             for (int32_t i = 0; i < dc.n_scope; i++) wake(dev_scope[dc.scope_off + i], pr.offset, q);
         } else if (dc.kind == DK_NEXT) {
@@ -381,7 +384,7 @@ size_t SetTable::max_stage_bytes() const {
     size_t best = 0;
     for (const DevSet &ds : dev_sets) {
         size_t b = a8((size_t)ds.n_prop * sizeof(DevProp)) + a8((size_t)ds.n_con * sizeof(DevCon)) +
-                   2 * a8((size_t)ds.n_scope * 4) + a8((size_t)n_vars() * k_ * ds.n_words * 4) + 2 * a8((size_t)n_vars() * 4) +
+                   2 * a8((size_t)ds.n_scope * 4) + a8(((size_t)n_vars() * k_ + 1) * ds.n_words * 4) + 2 * a8((size_t)n_vars() * 4) +
                    a8((size_t)ds.n_code * sizeof(Instr));
         best = std::max(best, b);
     }

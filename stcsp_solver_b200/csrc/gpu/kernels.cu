@@ -631,13 +631,31 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
     const DevSet &S = ctx.S;
     WarpMem &wm = ctx.wm;
     const int lane = ctx.lane;
+    // look-ahead row of the wake table: pointwise propagators at offsets >= 1
+    const uint32_t *ahead = M.wake + S.wake_off + (size_t)M.V * M.k * S.n_words;
+    bool held = M.lazy_ahead != 0;                      // look-ahead propagators are held back (uniform over the group)
     for (;;) {
+        if (held) {
+            // released once every variable of the current time point is bound; then all of them run, once
+            bool unbound = false;
+            for (int v = gtid; v < M.V; v += gthreads) unbound |= __popcll(ctx.dom[v * M.k]) > 1;
+            const bool any_unbound = CTA ? __syncthreads_or(unbound) != 0 : __any_sync(0xffffffffu, unbound);
+            if (!any_unbound) {
+                held = false;
+                for (int w = gtid; w < S.n_words; w += gthreads) {
+                    const uint32_t m = ahead[w];
+                    if (m) atomicOr(&wm.dirty[w], m);
+                }
+                if (CTA) __syncthreads(); else __syncwarp();
+            }
+        }
         // ---- phase A
         for (;;) {
             bool myfail = false;
             for (int q = gtid; q < S.n_cheap; q += gthreads) {
                 const uint32_t bit = 1u << (q & 31);
                 if (!(wm.dirty[q >> 5] & bit)) continue;
+                if (held && (ahead[q >> 5] & bit)) continue;
                 atomicAnd(&wm.dirty[q >> 5], ~bit);
                 const int r = scalar_revise(M, S, q, ctx.dom, wm.dirty, ctx.expire, my_tuples);
                 st_rev++;
@@ -647,10 +665,12 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
             bool more, bad;
             if (CTA) {
                 bad = __syncthreads_or(myfail) != 0;    // barrier: every revision of the round is done
-                more = __syncthreads_or(gtid < S.n_words && (wm.dirty[gtid] & cheap_mask(S, gtid)) != 0u) != 0;
+                more = __syncthreads_or(gtid < S.n_words &&
+                                        (wm.dirty[gtid] & cheap_mask(S, gtid) & (held ? ~ahead[gtid] : ~0u)) != 0u) != 0;
             } else {
                 bad = __any_sync(0xffffffffu, myfail);
-                more = __any_sync(0xffffffffu, lane < S.n_words && (wm.dirty[lane] & cheap_mask(S, lane)) != 0u);
+                more = __any_sync(0xffffffffu, lane < S.n_words &&
+                                                   (wm.dirty[lane] & cheap_mask(S, lane) & (held ? ~ahead[lane] : ~0u)) != 0u);
             }
             if (bad) return true;
             if (!more) break;
@@ -659,7 +679,8 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
         if (!CTA) {
             int q = -1;
             for (int base = 0; base < S.n_words; base += 32) {
-                const uint32_t w = base + lane < S.n_words ? (wm.hvy[base + lane] | (wm.dirty[base + lane] & ~cheap_mask(S, base + lane))) : 0u;
+                uint32_t w = base + lane < S.n_words ? (wm.hvy[base + lane] | (wm.dirty[base + lane] & ~cheap_mask(S, base + lane))) : 0u;
+                if (held && base + lane < S.n_words) w &= ~ahead[base + lane];
                 const unsigned b = __ballot_sync(0xffffffffu, w != 0u);
                 if (b) {
                     const int l = __ffs(b) - 1;
@@ -668,7 +689,13 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                     break;
                 }
             }
-            if (q < 0) return false;                    // fixpoint
+            if (q < 0) {                                // fixpoint ...
+                if (!held) return false;
+                bool unbound = false;                   // ... unless the look-ahead propagators were held and are due now
+                for (int v = lane; v < M.V; v += 32) unbound |= __popcll(ctx.dom[v * M.k]) > 1;
+                if (__any_sync(0xffffffffu, unbound)) return false;
+                continue;
+            }
             __syncwarp();
             if (lane == 0) {
                 wm.hvy[q >> 5] &= ~(1u << (q & 31));
@@ -685,7 +712,8 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
             if (threadIdx.x == 0) {
                 int total = 0;
                 for (int w = 0; w < S.n_words; w++) {
-                    const uint32_t take = wm.hvy[w] | (wm.dirty[w] & ~cheap_mask(S, w));
+                    uint32_t take = wm.hvy[w] | (wm.dirty[w] & ~cheap_mask(S, w));
+                    if (held) take &= ~ahead[w];
                     wm.dcur[w] = take;
                     wm.hvy[w] = 0u;
                     wm.dirty[w] &= ~take;
@@ -694,7 +722,13 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                 wm.flag[1] = total;
             }
             __syncthreads();
-            if (wm.flag[1] == 0) return false;          // fixpoint
+            if (wm.flag[1] == 0) {                      // fixpoint ...
+                if (!held) return false;
+                bool unbound = false;                   // ... unless the held look-ahead propagators are due now
+                for (int v = gtid; v < M.V; v += gthreads) unbound |= __popcll(ctx.dom[v * M.k]) > 1;
+                if (__syncthreads_or(unbound)) return false;
+                continue;
+            }
             int seen_bits = 0;
             bool ok = true;
             for (int w = 0; ok && w < S.n_words; w++) {
@@ -728,7 +762,7 @@ __device__ int stage_set(const DevModel &M, unsigned char *smem, int cid) {
     unsigned char *p = reinterpret_cast<unsigned char *>(sm) + align8(sizeof(DevModel));
     const DevSet S = M.sets[cid];
     const int tid = threadIdx.x, nt = blockDim.x;
-    const size_t wake_words = (size_t)M.V * M.k * S.n_words;
+    const size_t wake_words = ((size_t)M.V * M.k + 1) * S.n_words;      // + the look-ahead row
     int2 *s_props = reinterpret_cast<int2 *>(p); p += align8((size_t)S.n_prop * sizeof(DevProp));
     int2 *s_cons = reinterpret_cast<int2 *>(p); p += align8((size_t)S.n_con * sizeof(DevCon));
     int32_t *s_scope = reinterpret_cast<int32_t *>(p); p += align8((size_t)S.n_scope * 4);

@@ -45,6 +45,7 @@ struct DevModel {
     int32_t n_sig, sig_len;
     int32_t max_scope, max_stack, max_words;
     int32_t stage_bytes;        // shared memory reserved per CTA for one constraint set's metadata (0: never staged)
+    int32_t lazy_ahead;         // 1: pointwise propagators at look-ahead offsets run only once the current point is bound
     long long enum_now, enum_ahead;
     const int32_t *lb, *width, *sig_vars;
     const DevSet *sets;

@@ -421,6 +421,7 @@ struct stcsp_session {
             const size_t sb = sets.max_stage_bytes();
             dm.stage_bytes = sb <= 40 * 1024 ? (int32_t)sb : 0;     // larger sets stay in global memory / L1
         }
+        dm.lazy_ahead = opt.lookahead == 2 ? 1 : 0;
         dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : 8;
         dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : 4;
         dm.lb = d_lb.p;
