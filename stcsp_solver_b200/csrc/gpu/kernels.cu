@@ -1215,6 +1215,10 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             if (blockIdx.x == 0 && threadIdx.x == 0) ctl->status = SEARCH_RETRY;
             return;
         }
+        // Every block must take the same exit decisions, so they may only depend on values that no block is changing
+        // while they are read: C_OUT is frozen during route (ingest moves it again), C_LEAVES after expand,
+        // C_UNRESOLVED after route.
+        const long long out_after_expand = (long long)cnt[C_OUT];
         RouteArgs ra;
         ra.leaves = A.leaves;
         ra.list = nullptr;
@@ -1229,7 +1233,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         grid.sync();
         stamp(2);
         const long long n_leaves = (long long)cnt[C_LEAVES];
-        if (cnt[C_UNRESOLVED] != 0ull || (long long)cnt[C_OUT] + n_leaves > A.out_cap) {
+        if (cnt[C_UNRESOLVED] != 0ull || out_after_expand + n_leaves > A.out_cap) {
             // the host finishes this wave (resolve + ingest) and relaunches
             if (blockIdx.x == 0 && threadIdx.x == 0) ctl->status = SEARCH_INGEST;
             return;

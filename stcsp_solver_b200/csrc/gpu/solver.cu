@@ -663,6 +663,11 @@ struct stcsp_session {
             t_dominance += h_ctl->t_dominance;
             t_leaves += h_ctl->t_leaves;
             t_waves += h_ctl->t_waves;
+            if (opt.verbosity > 0)
+                fprintf(stderr, "[stcsp r%d] t=%.3f ms search kernel returned: status %d after %lld waves, n_in %lld, states %llu, edges %llu, "
+                                "out %llu leaves %llu overflow %d\n",
+                        rank, (now_s() - t_create) * 1e3, h_ctl->status, h_ctl->t_waves, h_ctl->n_in, h_counters[C_STATES],
+                        h_counters[C_EDGES], h_counters[C_OUT], h_counters[C_LEAVES], h_ctl->overflow);
             if (h_ctl->overflow & ~1) throw Failure(STCSP_ERR_CAPACITY, "internal: a pool overflowed inside the search kernel");
             n_in = h_ctl->n_in;
             cur = h_ctl->cur;

@@ -1,6 +1,6 @@
 """Large generated instances on one GPU: time, counts, memory."""
-import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), time
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stcsp_solver_b200 import binding, instances
 for name in sys.argv[1:]:
     m = binding.Model(instances.by_name(name))
