@@ -966,66 +966,71 @@ __device__ __forceinline__ int key_word(const DevModel &M, const int32_t *rec, i
 
 // ---- route: successor constraint set, until flags and state-key hash of every leaf --------------------
 // (reference src/solveralgorithm.cpp:755-837: constraint rewriting -> constraintID, signature)
+// Route one leaf (all lanes of the warp).  Returns false when the successor constraint set is not known yet:
+// the leaf is then listed for the host.
+__device__ __forceinline__ bool route_leaf(const DevModel &M, const RouteArgs &P, int32_t *rec, long long li, int lane) {
+    const int KW = M.key_words;
+    const int cid = rec[1], exp = rec[2];
+    const DevSet S = M.sets[cid];
+    int ncid = S.static_next;
+    if (ncid < 0) {
+        // the successor set depends on the values captured by `first`: host-filled map
+        int found = -1;
+        if (lane == 0 && P.capmap_mask >= 0) {
+            const int32_t *cap = M.aux + S.cap_off;
+            uint32_t h = cap_hash_begin(cid);
+            for (int i = 0; i < S.n_cap; i++) h = cap_hash_step(h, rec[4 + cap[i]]);
+            h = cap_hash_end(h) & (uint32_t)P.capmap_mask;
+            for (;;) {
+                const CapEntry e = P.capmap[h];
+                if (e.cid == -1) break;
+                bool eq = e.cid == cid;
+                for (int i = 0; eq && i < S.n_cap; i++) eq = P.capvals[e.off + i] == rec[4 + cap[i]];
+                if (eq) { found = e.next; break; }
+                h = (h + 1) & (uint32_t)P.capmap_mask;
+            }
+        }
+        found = __shfl_sync(0xffffffffu, found, 0);
+        if (found < 0) {
+            if (lane == 0) {
+                const unsigned long long u = atomicAdd(&P.counters[C_UNRESOLVED], 1ull);
+                if ((long long)u < P.unresolved_cap) P.unresolved[u] = (int32_t)li;
+                else atomicOr(&P.counters[C_OVERFLOW], 16ull);
+            }
+            return false;
+        }
+        ncid = found;
+    }
+    const DevSet NS = M.sets[ncid];
+    int nexp = exp;                                   // until flags (src/solveralgorithm.cpp:821-834)
+    for (int u = 0; u < NS.n_until; u++)
+        if (rec[4 + M.aux[NS.until_off + u]] == 1) nexp |= 1 << u;
+
+    uint32_t h = 0;
+    for (int j = lane; j < KW; j += 32) h ^= key_word_hash(key_word(M, rec, ncid, nexp, j), j);
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, s);
+    h = mix32(h);
+    __syncwarp();
+    if (lane == 0) {
+        rec[1] = ncid;
+        rec[2] = nexp;
+        rec[3] = (int32_t)h;
+        const int owner = M.world > 1 ? (int)(owner_hash(h) % (uint32_t)M.world) : 0;
+        atomicAdd(&P.counters[C_OWNER0 + owner], 1ull);
+    }
+    __syncwarp();
+    return true;
+}
+
 __device__ __forceinline__ void route_body(const DevModel &M, const RouteArgs &P) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long n = P.list ? P.count : (long long)P.counters[C_LEAVES];
-    const int KW = M.key_words;
-
     for (long long it = warp_id; it < n; it += total_warps) {
         const long long li = P.list ? (long long)P.list[it] : it;
-        int32_t *rec = P.leaves + li * M.rec_words;
-        const int cid = rec[1], exp = rec[2];
-        const DevSet S = M.sets[cid];
-        int ncid = S.static_next;
-        if (ncid < 0) {
-            // the successor set depends on the values captured by `first`: host-filled map
-            int found = -1;
-            if (lane == 0 && P.capmap_mask >= 0) {
-                const int32_t *cap = M.aux + S.cap_off;
-                uint32_t h = cap_hash_begin(cid);
-                for (int i = 0; i < S.n_cap; i++) h = cap_hash_step(h, rec[4 + cap[i]]);
-                h = cap_hash_end(h) & (uint32_t)P.capmap_mask;
-                for (;;) {
-                    const CapEntry e = P.capmap[h];
-                    if (e.cid == -1) break;
-                    bool eq = e.cid == cid;
-                    for (int i = 0; eq && i < S.n_cap; i++) eq = P.capvals[e.off + i] == rec[4 + cap[i]];
-                    if (eq) { found = e.next; break; }
-                    h = (h + 1) & (uint32_t)P.capmap_mask;
-                }
-            }
-            found = __shfl_sync(0xffffffffu, found, 0);
-            if (found < 0) {
-                if (lane == 0) {
-                    const unsigned long long u = atomicAdd(&P.counters[C_UNRESOLVED], 1ull);
-                    if ((long long)u < P.unresolved_cap) P.unresolved[u] = (int32_t)li;
-                    else atomicOr(&P.counters[C_OVERFLOW], 16ull);
-                }
-                continue;
-            }
-            ncid = found;
-        }
-        const DevSet NS = M.sets[ncid];
-        int nexp = exp;                                   // until flags (src/solveralgorithm.cpp:821-834)
-        for (int u = 0; u < NS.n_until; u++)
-            if (rec[4 + M.aux[NS.until_off + u]] == 1) nexp |= 1 << u;
-
-        uint32_t h = 0;
-        for (int j = lane; j < KW; j += 32) h ^= key_word_hash(key_word(M, rec, ncid, nexp, j), j);
-#pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, s);
-        h = mix32(h);
-        __syncwarp();
-        if (lane == 0) {
-            rec[1] = ncid;
-            rec[2] = nexp;
-            rec[3] = (int32_t)h;
-            const int owner = M.world > 1 ? (int)(owner_hash(h) % (uint32_t)M.world) : 0;
-            atomicAdd(&P.counters[C_OWNER0 + owner], 1ull);
-        }
-        __syncwarp();
+        route_leaf(M, P, P.leaves + li * M.rec_words, li, lane);
     }
 }
 
@@ -1064,98 +1069,113 @@ __global__ void __launch_bounds__(256) gather_kernel(const int32_t *src, const i
 // ---- ingest: state dedup, edge append, first search node of every new state ------------------------------
 // One warp per routed leaf record (reference vertexTableGetVertex/AddVertex src/graph.cpp:108-123,
 // edgeNew src/graph.cpp:78-89, variableAdvanceOneTimeStep src/variable.cpp:94-108).
+// Merge one routed leaf record into the automaton (all lanes of the warp).
+__device__ __forceinline__ void ingest_leaf(const DevModel &M, const IngestArgs &P, const int32_t *rec, int lane,
+                                            unsigned long long &st_dom) {
+    const int V = M.V, k = M.k, KW = M.key_words, NW = M.node_words;
+    const int src = rec[0], ncid = rec[1], nexp = rec[2];
+    const uint32_t h = (uint32_t)rec[3];
+    const DevSet NS = M.sets[ncid];
+
+    long long slot = (long long)h & P.table_mask;
+    int dst = -1;                                     // local index of the destination state
+    bool is_new = false, abort_leaf = false;
+    for (;;) {
+        int v = 0;
+        if (lane == 0) v = atomicCAS(&P.table[slot], -1, -2);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        if (v == -1) {                                // slot claimed: this leaf creates the state
+            unsigned long long id = 0;
+            if (lane == 0) id = atomicAdd(&P.counters[C_STATES], 1ull);
+            id = __shfl_sync(0xffffffffu, id, 0);
+            if ((long long)id >= P.state_cap) {
+                if (lane == 0) { atomicOr(&P.counters[C_OVERFLOW], 4ull); atomicExch(&P.table[slot], -3); }
+                abort_leaf = true;
+                break;
+            }
+            for (int j = lane; j < KW; j += 32) P.state_key[id * KW + j] = key_word(M, rec, ncid, nexp, j);
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicExch(&P.table[slot], (int)id);
+            dst = (int)id;
+            is_new = true;
+            break;
+        }
+        if (v == -2) {                                // another warp is writing this slot's key
+            if (lane == 0) {
+                volatile int32_t *vs = P.table + slot;
+                do { v = *vs; } while (v == -2);
+            }
+            v = __shfl_sync(0xffffffffu, v, 0);
+        }
+        if (v == -3) { abort_leaf = true; break; }
+        __threadfence();
+        bool eq = true;
+        for (int j = lane; j < KW; j += 32)
+            eq &= __ldcg(&P.state_key[(long long)v * KW + j]) == key_word(M, rec, ncid, nexp, j);
+        if (__all_sync(0xffffffffu, eq)) { dst = v; break; }
+        slot = (slot + 1) & P.table_mask;
+    }
+    if (abort_leaf) return;
+    const int dst_global = dst * M.world + M.rank;
+
+    if (is_new) {
+        // first search node of the new state: next-linked variables take the values just chosen,
+        // everything else restarts from its declared range
+        unsigned long long o = 0;
+        if (lane == 0) o = atomicAdd(&P.counters[C_OUT], 1ull);
+        o = __shfl_sync(0xffffffffu, o, 0);
+        if ((long long)o >= P.out_cap) {
+            if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
+        } else {
+            int32_t *node = P.out_nodes + o * NW;
+            if (lane == 0) { node[0] = dst_global; node[1] = ncid; node[2] = nexp; node[3] = -1; }
+            u64 *nd = reinterpret_cast<u64 *>(node + 4);
+            for (int i = lane; i < V * k; i += 32) {
+                const int v = i / k, p = i % k;
+                u64 m = width_mask(M.width[v]);
+                if (p == 0 && k > 1) {                // with k == 1 the reference never links time points
+                    for (int t = 0; t < NS.n_next; t++) {
+                        if (M.aux[NS.next_off + 2 * t + 1] != v) continue;
+                        const long long b = (long long)rec[4 + M.aux[NS.next_off + 2 * t]] - (long long)M.lb[v];
+                        m &= (b >= 0 && b < 64) ? (1ull << b) : 0ull;
+                    }
+                }
+                nd[i] = m;
+            }
+        }
+    } else {
+        st_dom++;
+    }
+    unsigned long long e = 0;
+    if (lane == 0) e = atomicAdd(&P.counters[C_EDGES], 1ull);
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if ((long long)e >= P.edge_cap) {
+        if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 8ull);
+        return;
+    }
+    if (lane == 0) { P.edge_src[e] = src; P.edge_dst[e] = dst_global; }
+    for (int v = lane; v < V; v += 32) P.edge_label[e * V + v] = rec[4 + v];
+}
+
 __device__ __forceinline__ void ingest_body(const DevModel &M, const IngestArgs &P) {
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int V = M.V, k = M.k, KW = M.key_words, NW = M.node_words;
     unsigned long long st_dom = 0;
+    for (long long it = warp_id; it < P.count; it += total_warps) ingest_leaf(M, P, P.records + it * M.rec_words, lane, st_dom);
+    if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+}
 
-    for (long long it = warp_id; it < P.count; it += total_warps) {
-        const int32_t *rec = P.records + it * M.rec_words;
-        const int src = rec[0], ncid = rec[1], nexp = rec[2];
-        const uint32_t h = (uint32_t)rec[3];
-        const DevSet NS = M.sets[ncid];
-
-        long long slot = (long long)h & P.table_mask;
-        int dst = -1;                                     // local index of the destination state
-        bool is_new = false, abort_leaf = false;
-        for (;;) {
-            int v = 0;
-            if (lane == 0) v = atomicCAS(&P.table[slot], -1, -2);
-            v = __shfl_sync(0xffffffffu, v, 0);
-            if (v == -1) {                                // slot claimed: this leaf creates the state
-                unsigned long long id = 0;
-                if (lane == 0) id = atomicAdd(&P.counters[C_STATES], 1ull);
-                id = __shfl_sync(0xffffffffu, id, 0);
-                if ((long long)id >= P.state_cap) {
-                    if (lane == 0) { atomicOr(&P.counters[C_OVERFLOW], 4ull); atomicExch(&P.table[slot], -3); }
-                    abort_leaf = true;
-                    break;
-                }
-                for (int j = lane; j < KW; j += 32) P.state_key[id * KW + j] = key_word(M, rec, ncid, nexp, j);
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicExch(&P.table[slot], (int)id);
-                dst = (int)id;
-                is_new = true;
-                break;
-            }
-            if (v == -2) {                                // another warp is writing this slot's key
-                if (lane == 0) {
-                    volatile int32_t *vs = P.table + slot;
-                    do { v = *vs; } while (v == -2);
-                }
-                v = __shfl_sync(0xffffffffu, v, 0);
-            }
-            if (v == -3) { abort_leaf = true; break; }
-            __threadfence();
-            bool eq = true;
-            for (int j = lane; j < KW; j += 32)
-                eq &= __ldcg(&P.state_key[(long long)v * KW + j]) == key_word(M, rec, ncid, nexp, j);
-            if (__all_sync(0xffffffffu, eq)) { dst = v; break; }
-            slot = (slot + 1) & P.table_mask;
-        }
-        if (abort_leaf) continue;
-        const int dst_global = dst * M.world + M.rank;
-
-        if (is_new) {
-            // first search node of the new state: next-linked variables take the values just chosen,
-            // everything else restarts from its declared range
-            unsigned long long o = 0;
-            if (lane == 0) o = atomicAdd(&P.counters[C_OUT], 1ull);
-            o = __shfl_sync(0xffffffffu, o, 0);
-            if ((long long)o >= P.out_cap) {
-                if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
-            } else {
-                int32_t *node = P.out_nodes + o * NW;
-                if (lane == 0) { node[0] = dst_global; node[1] = ncid; node[2] = nexp; node[3] = -1; }
-                u64 *nd = reinterpret_cast<u64 *>(node + 4);
-                for (int i = lane; i < V * k; i += 32) {
-                    const int v = i / k, p = i % k;
-                    u64 m = width_mask(M.width[v]);
-                    if (p == 0 && k > 1) {                // with k == 1 the reference never links time points
-                        for (int t = 0; t < NS.n_next; t++) {
-                            if (M.aux[NS.next_off + 2 * t + 1] != v) continue;
-                            const long long b = (long long)rec[4 + M.aux[NS.next_off + 2 * t]] - (long long)M.lb[v];
-                            m &= (b >= 0 && b < 64) ? (1ull << b) : 0ull;
-                        }
-                    }
-                    nd[i] = m;
-                }
-            }
-        } else {
-            st_dom++;
-        }
-        unsigned long long e = 0;
-        if (lane == 0) e = atomicAdd(&P.counters[C_EDGES], 1ull);
-        e = __shfl_sync(0xffffffffu, e, 0);
-        if ((long long)e >= P.edge_cap) {
-            if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 8ull);
-            continue;
-        }
-        if (lane == 0) { P.edge_src[e] = src; P.edge_dst[e] = dst_global; }
-        for (int v = lane; v < V; v += 32) P.edge_label[e * V + v] = rec[4 + v];
+// Route and merge in one pass (single rank): what cannot be routed yet is left for the host.
+__device__ __forceinline__ void leaf_body(const DevModel &M, const RouteArgs &R, const IngestArgs &P, long long n_leaves) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long st_dom = 0;
+    for (long long li = warp_id; li < n_leaves; li += total_warps) {
+        int32_t *rec = R.leaves + li * M.rec_words;
+        if (route_leaf(M, R, rec, li, lane)) ingest_leaf(M, P, rec, lane, st_dom);
     }
     if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
 }
@@ -1219,6 +1239,12 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         // while they are read: C_OUT is frozen during route (ingest moves it again), C_LEAVES after expand,
         // C_UNRESOLVED after route.
         const long long out_after_expand = (long long)cnt[C_OUT];
+        const long long n_leaves = (long long)cnt[C_LEAVES];
+        if (out_after_expand + n_leaves > A.out_cap) {
+            // no room for the first nodes of new states: the host grows the frontier and finishes the wave (route + ingest)
+            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->status = SEARCH_INGEST;
+            return;
+        }
         RouteArgs ra;
         ra.leaves = A.leaves;
         ra.list = nullptr;
@@ -1229,15 +1255,6 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         ra.unresolved = A.unresolved;
         ra.unresolved_cap = A.unresolved_cap;
         ra.counters = A.counters;
-        route_body(M, ra);
-        grid.sync();
-        stamp(2);
-        const long long n_leaves = (long long)cnt[C_LEAVES];
-        if (cnt[C_UNRESOLVED] != 0ull || out_after_expand + n_leaves > A.out_cap) {
-            // the host finishes this wave (resolve + ingest) and relaunches
-            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->status = SEARCH_INGEST;
-            return;
-        }
         IngestArgs ia;
         ia.records = A.leaves;
         ia.count = n_leaves;
@@ -1252,9 +1269,15 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         ia.out_nodes = A.frontier[cur ^ 1];
         ia.out_cap = A.out_cap;
         ia.counters = A.counters;
-        ingest_body(M, ia);
+        leaf_body(M, ra, ia, n_leaves);                 // route + ingest in one pass
         grid.sync();
+        stamp(2);
         stamp(3);
+        if (cnt[C_UNRESOLVED] != 0ull) {
+            // leaves with an unseen constraint-set transition are still pending: the host resolves and ingests them
+            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->status = SEARCH_RESOLVE;
+            return;
+        }
         // ---- wave end: totals, swap, reset the wave counters
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             ctl->t_nodes += (long long)cnt[C_NODES];

@@ -109,8 +109,9 @@ enum SearchStatus : int {
     SEARCH_DONE = 1,       // frontier empty
     SEARCH_GROW = 2,       // a pool is too small for the next wave: the host grows it, nothing of the wave has run
     SEARCH_RETRY = 3,      // the output frontier overflowed during expand: grow it, run the wave again
-    SEARCH_INGEST = 4,     // expand + route done; the host resolves constraint-set transitions / grows, then ingests
-    SEARCH_YIELD = 5       // wave budget used up (time-limit checks)
+    SEARCH_INGEST = 4,     // expand done, no room for new states' nodes: the host grows the frontier, routes and ingests
+    SEARCH_YIELD = 5,      // wave budget used up (time-limit checks)
+    SEARCH_RESOLVE = 6     // expand + route + ingest done except for leaves whose constraint-set transition is unseen
 };
 struct SearchCtl {
     long long n_in;

@@ -688,8 +688,24 @@ struct stcsp_session {
                     frontier[cur].reserve(frontier[cur ^ 1].cap, (size_t)n_in * NW, stream);
                     zero_wave_counters();
                     break;
-                case SEARCH_INGEST: {
-                    // expand + route of this wave are done on the device; finish it here
+                case SEARCH_INGEST:
+                case SEARCH_RESOLVE: {
+                    // the device stopped in the middle of a wave; finish it here
+                    const bool routed = h_ctl->status == SEARCH_RESOLVE;
+                    if (!routed) {                      // expand done, nothing routed yet
+                        RouteArgs ra{};
+                        ra.leaves = leaves.p;
+                        ra.capmap = d_capmap.p;
+                        ra.capvals = d_capvals.p;
+                        ra.capmap_mask = capmap.empty() ? -1 : (int32_t)capmap.size() - 1;
+                        ra.unresolved = unresolved.p;
+                        ra.unresolved_cap = (long long)unresolved.cap;
+                        ra.counters = counters.p;
+                        launch_route(dm, ra, (int)std::min<long long>((n_in + 7) / 8, sm_count * 8), stream);
+                        CK(cudaGetLastError());
+                        read_counters();
+                        t_launches++;
+                    }
                     n_out = (long long)h_counters[C_OUT];
                     n_leaves = (long long)h_counters[C_LEAVES];
                     n_unres = (long long)h_counters[C_UNRESOLVED];
@@ -701,9 +717,28 @@ struct stcsp_session {
                     t_waves++;
                     pending.clear();
                     if (n_unres > 0) {
+                        const long long listed = n_unres;
                         collect_pending();
                         std::vector<int32_t> req = pending;
-                        resolve(req.data(), (int64_t)(req.size() / (size_t)(1 + V)));
+                        resolve(req.data(), (int64_t)(req.size() / (size_t)(1 + V)));     // re-routes the listed leaves in place
+                        if (routed) {
+                            // everything else of this wave is in the automaton already: only the listed leaves remain
+                            t_dominance += (long long)h_counters[C_DOMINANCE];
+                            gathered.reserve((size_t)listed * RW, 0, stream);
+                            launch_gather(leaves.p, unresolved.p, listed, RW, gathered.p,
+                                          (int)std::min<long long>((listed + 7) / 8, sm_count * 8), stream);
+                            t_launches++;
+                            CK(cudaMemsetAsync(counters.p + C_DOMINANCE, 0, sizeof(unsigned long long), stream));
+                            n_out = (long long)h_counters[C_OUT];
+                            n_states = (long long)h_counters[C_STATES];
+                            n_edges = (long long)h_counters[C_EDGES];
+                            int64_t next = 0;
+                            ingest(gathered.p, listed, &next);
+                            zero_wave_counters();
+                            break;
+                        }
+                    } else if (routed) {
+                        throw Failure(STCSP_ERR_CUDA, "internal: SEARCH_RESOLVE without pending leaves");
                     }
                     int64_t next = 0;
                     ingest(nullptr, 0, &next);
