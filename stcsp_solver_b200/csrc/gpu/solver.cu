@@ -136,29 +136,45 @@ struct DBuf {
     }
 };
 
-// Relation tables of recently solved models stay resident on the device (take / put: one session at a time owns
-// an entry, a concurrent solve of the same model simply builds its own).
+// Everything a solve derives from the model alone -- compiled constraint sets, relation tables, the constraint-set
+// transition map, and their device copies -- stays resident between solves of the same model (take / put: one session
+// at a time owns an entry; a concurrent solve of the same model simply builds its own).
+struct ModelState {
+    SetTable sets;
+    // constraint-set transitions resolved so far
+    std::vector<CapEntry> capmap;
+    std::vector<int32_t> capvals;
+    long long capmap_used = 0;
+    std::map<std::vector<int32_t>, int32_t> cap_lookup;
+    // device copies
+    DBuf<int32_t> d_lb, d_width, d_sigvars, d_scope, d_stride, d_aux, d_arr_off, d_arr_val, d_capvals;
+    DBuf<unsigned long long> d_tables;
+    DBuf<DevSet> d_sets;
+    DBuf<DevCon> d_cons;
+    DBuf<DevProp> d_props;
+    DBuf<Instr> d_code;
+    DBuf<uint32_t> d_wake;
+    DBuf<CapEntry> d_capmap;
+    long long tables_built = 0;     // u64 words of the table pool already filled
+    bool uploaded = false;
+    // pool sizes the last solve of this model ended with: the next one starts there and never has to grow
+    long long hint_frontier = 0, hint_states = 0, hint_edges = 0, hint_table = 0;
+};
+
 struct ModelCache {
-    struct Entry {
-        DBuf<unsigned long long> tables;
-        long long words = 0;
-        SetTable::TableDirectory dir;
-        // pool sizes the last solve of this model ended with: the next one starts there and never has to grow
-        long long cap_frontier = 0, cap_states = 0, cap_edges = 0, cap_table = 0;
-    };
     std::mutex mu;
-    std::map<std::string, std::unique_ptr<Entry>> entries;
+    std::map<std::string, std::unique_ptr<ModelState>> entries;
     std::vector<std::string> order;
-    std::unique_ptr<Entry> take(const std::string &key) {
+    std::unique_ptr<ModelState> take(const std::string &key) {
         std::lock_guard<std::mutex> g(mu);
         auto it = entries.find(key);
         if (it == entries.end()) return nullptr;
-        std::unique_ptr<Entry> e = std::move(it->second);
+        std::unique_ptr<ModelState> e = std::move(it->second);
         entries.erase(it);
         order.erase(std::remove(order.begin(), order.end(), key), order.end());
         return e;
     }
-    void put(const std::string &key, std::unique_ptr<Entry> e) {
+    void put(const std::string &key, std::unique_ptr<ModelState> e) {
         std::lock_guard<std::mutex> g(mu);
         if (entries.count(key)) return;
         entries[key] = std::move(e);
@@ -303,44 +319,27 @@ struct PinnedStore : Store {    // single-rank automata finished on the device
 using namespace stcsp;
 
 struct stcsp_session {
-    SetTable sets;
+    std::unique_ptr<ModelState> model;
     stcsp_options_t opt{};
     int rank = 0, world = 1, device = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     DevModel dm{};
-    // model pools
-    DBuf<int32_t> d_lb, d_width, d_sigvars, d_scope, d_stride, d_aux, d_arr_off, d_arr_val;
-    DBuf<unsigned long long> d_tables;
     DBuf<int32_t> d_jobs;
-    long long tables_built = 0;     // u64 words of the table pool already filled
     std::string cache_key;
-    long long hint_frontier = 0, hint_states = 0, hint_edges = 0, hint_table = 0;
     DBuf<SearchCtl> d_ctl;
     SearchCtl *h_ctl = nullptr;     // pinned, behind h_counters
     int search_grid = 0;
-    DBuf<DevSet> d_sets;
-    DBuf<DevCon> d_cons;
-    DBuf<DevProp> d_props;
-    DBuf<Instr> d_code;
-    DBuf<uint32_t> d_wake;
     // search pools
     DBuf<int32_t> frontier[2];
     int cur = 0;
     DBuf<int32_t> leaves, unresolved, gathered, table, state_key, edge_src, edge_dst, edge_label;
-    DBuf<CapEntry> d_capmap;
     DBuf<unsigned long long> counters;
     DBuf<long long> d_offsets;
     unsigned long long *h_counters = nullptr;       // pinned
     long long table_size = 0;
     long long n_in = 0, n_out = 0, n_leaves = 0, n_unres = 0, n_states = 0, n_edges = 0;
     int expand_grid_max = 148;
-    // constraint-set transitions resolved so far
-    std::vector<CapEntry> capmap;
-    std::vector<int32_t> capvals;
-    DBuf<int32_t> d_capvals;
-    long long capmap_used = 0;
-    std::map<std::vector<int32_t>, int32_t> cap_lookup;
     std::vector<int32_t> pending;                   // flat requests [cid, values[V]]
     // statistics
     long long t_nodes = 0, t_fails = 0, t_tuples = 0, t_revisions = 0, t_leaves = 0, t_dominance = 0, t_waves = 0,
@@ -351,16 +350,13 @@ struct stcsp_session {
     ~stcsp_session() {
         if (stream) cudaStreamSynchronize(stream);
         if (h_counters) pinned_cache().give_back(h_counters);
-        if (!cache_key.empty() && sets.table_jobs.empty() && tables_built == sets.table_words && dm.node_words > 0) {
-            std::unique_ptr<ModelCache::Entry> e(new ModelCache::Entry());      // keep the relation tables resident
-            e->tables.swap(d_tables);
-            e->words = sets.table_words;
-            e->dir = sets.export_tables();
-            e->cap_frontier = (long long)std::min(frontier[0].cap, frontier[1].cap) / dm.node_words;
-            e->cap_states = (long long)state_key.cap / dm.key_words;
-            e->cap_edges = (long long)edge_src.cap;
-            e->cap_table = table_size;
-            model_cache().put(cache_key, std::move(e));
+        if (model && !cache_key.empty() && model->uploaded && !model->sets.dirty() && model->sets.table_jobs.empty() &&
+            model->tables_built == model->sets.table_words && dm.node_words > 0) {
+            model->hint_frontier = (long long)std::min(frontier[0].cap, frontier[1].cap) / dm.node_words;
+            model->hint_states = (long long)state_key.cap / dm.key_words;
+            model->hint_edges = (long long)edge_src.cap;
+            model->hint_table = table_size;
+            model_cache().put(cache_key, std::move(model));       // the compiled model stays resident for the next solve
         }
         release_all();
         if (ev0) cudaEventDestroy(ev0);
@@ -371,12 +367,10 @@ struct stcsp_session {
     }
 
     void release_all() {
-        d_lb.release(); d_width.release(); d_sigvars.release(); d_scope.release(); d_stride.release(); d_aux.release();
-        d_arr_off.release(); d_arr_val.release(); d_tables.release(); d_jobs.release(); d_ctl.release(); d_sets.release(); d_cons.release();
-        d_props.release(); d_code.release(); d_wake.release(); frontier[0].release(); frontier[1].release();
+        model.reset();     // (if it was not handed to the cache) its device blocks go back to the block cache
+        d_jobs.release(); d_ctl.release(); frontier[0].release(); frontier[1].release();
         leaves.release(); unresolved.release(); gathered.release(); table.release(); state_key.release();
-        edge_src.release(); edge_dst.release(); edge_label.release(); d_capmap.release(); d_capvals.release();
-        counters.release(); d_offsets.release();
+        edge_src.release(); edge_dst.release(); edge_label.release(); counters.release(); d_offsets.release();
     }
 
     template <class T>
@@ -389,75 +383,81 @@ struct stcsp_session {
     }
 
     void upload_model() {
-        upload(d_lb, sets.lb());
-        upload(d_width, sets.width());
-        upload(d_sigvars, sets.sig_vars());
-        upload(d_sets, sets.dev_sets);
-        upload(d_cons, sets.dev_cons);
-        upload(d_props, sets.dev_props);
-        upload(d_scope, sets.dev_scope);
-        sets.dev_stride.resize(sets.dev_scope.size(), 0);
-        upload(d_stride, sets.dev_stride);
-        d_tables.reserve((size_t)std::max<long long>(sets.table_words, 1), (size_t)tables_built, stream);
-        upload(d_code, sets.dev_code);
-        upload(d_wake, sets.dev_wake);
-        upload(d_aux, sets.dev_aux);
-        upload(d_arr_off, sets.arr_off);
-        upload(d_arr_val, sets.arr_val);
+        upload(model->d_lb, model->sets.lb());
+        upload(model->d_width, model->sets.width());
+        upload(model->d_sigvars, model->sets.sig_vars());
+        upload(model->d_sets, model->sets.dev_sets);
+        upload(model->d_cons, model->sets.dev_cons);
+        upload(model->d_props, model->sets.dev_props);
+        upload(model->d_scope, model->sets.dev_scope);
+        model->sets.dev_stride.resize(model->sets.dev_scope.size(), 0);
+        upload(model->d_stride, model->sets.dev_stride);
+        model->d_tables.reserve((size_t)std::max<long long>(model->sets.table_words, 1), (size_t)model->tables_built, stream);
+        upload(model->d_code, model->sets.dev_code);
+        upload(model->d_wake, model->sets.dev_wake);
+        upload(model->d_aux, model->sets.dev_aux);
+        upload(model->d_arr_off, model->sets.arr_off);
+        upload(model->d_arr_val, model->sets.arr_val);
         CK(cudaStreamSynchronize(stream));      // the host vectors may be reallocated by the next set
-        dm.V = sets.n_vars();
-        dm.k = sets.k();
-        dm.world = world;
-        dm.rank = rank;
-        dm.n_sig = (int32_t)sets.sig_vars().size();
-        dm.sig_len = dm.n_sig + sets.n_until();
-        dm.node_words = 4 + 2 * dm.V * dm.k;
-        dm.rec_words = 4 + dm.V;
-        dm.key_words = 1 + dm.sig_len;
-        dm.max_scope = sets.max_scope();
-        dm.max_stack = sets.max_stack();
-        dm.max_words = (sets.max_props() + 31) / 32;
-        {
-            const size_t sb = sets.max_stage_bytes();
-            dm.stage_bytes = sb <= 40 * 1024 ? (int32_t)sb : 0;     // larger sets stay in global memory / L1
-        }
-        dm.lazy_ahead = opt.lookahead == 2 ? 1 : 0;
-        dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : 8;
-        dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : 4;
-        dm.lb = d_lb.p;
-        dm.width = d_width.p;
-        dm.sig_vars = d_sigvars.p;
-        dm.sets = d_sets.p;
-        dm.cons = d_cons.p;
-        dm.props = d_props.p;
-        dm.scope = d_scope.p;
-        dm.stride = d_stride.p;
-        dm.tables = d_tables.p;
-        dm.code = d_code.p;
-        dm.wake = d_wake.p;
-        dm.aux = d_aux.p;
-        dm.arr_off = d_arr_off.p;
-        dm.arr_val = d_arr_val.p;
-        if (expand_smem_bytes(dm) > 200 * 1024)
-            throw Failure(STCSP_ERR_UNSUPPORTED, "model needs more shared memory per CTA than an SM has");
-        expand_grid_max = expand_max_grid(dm, sm_count);
+        refresh_model();
         // fill the relation tables of constraints seen for the first time
-        if (!sets.table_jobs.empty()) {
+        if (!model->sets.table_jobs.empty()) {
             std::vector<int32_t> jobs;
             int max_entries = 1;
-            for (const TableJob &job : sets.table_jobs) {
+            for (const TableJob &job : model->sets.table_jobs) {
                 jobs.push_back(job.con);
-                max_entries = std::max(max_entries, sets.dev_cons[job.con].table_entries);
+                max_entries = std::max(max_entries, model->sets.dev_cons[job.con].table_entries);
             }
             upload(d_jobs, jobs);
-            launch_build_tables(dm, d_jobs.p, (int)jobs.size(), max_entries, d_tables.p, stream);
+            launch_build_tables(dm, d_jobs.p, (int)jobs.size(), max_entries, model->d_tables.p, stream);
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(stream));
             t_launches++;
         }
-        sets.table_jobs.clear();
-        tables_built = sets.table_words;
-        sets.clear_dirty();
+        model->sets.table_jobs.clear();
+        model->tables_built = model->sets.table_words;
+        model->sets.clear_dirty();
+        model->uploaded = true;
+    }
+
+    // dm <- the resident model (dimensions, device pointers, this solve's options)
+    void refresh_model() {
+        dm.V = model->sets.n_vars();
+        dm.k = model->sets.k();
+        dm.world = world;
+        dm.rank = rank;
+        dm.n_sig = (int32_t)model->sets.sig_vars().size();
+        dm.sig_len = dm.n_sig + model->sets.n_until();
+        dm.node_words = 4 + 2 * dm.V * dm.k;
+        dm.rec_words = 4 + dm.V;
+        dm.key_words = 1 + dm.sig_len;
+        dm.max_scope = model->sets.max_scope();
+        dm.max_stack = model->sets.max_stack();
+        dm.max_words = (model->sets.max_props() + 31) / 32;
+        {
+            const size_t sb = model->sets.max_stage_bytes();
+            dm.stage_bytes = sb <= 40 * 1024 ? (int32_t)sb : 0;     // larger model->sets stay in global memory / L1
+        }
+        dm.lazy_ahead = opt.lookahead == 2 ? 1 : 0;
+        dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : 8;
+        dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : 4;
+        dm.lb = model->d_lb.p;
+        dm.width = model->d_width.p;
+        dm.sig_vars = model->d_sigvars.p;
+        dm.sets = model->d_sets.p;
+        dm.cons = model->d_cons.p;
+        dm.props = model->d_props.p;
+        dm.scope = model->d_scope.p;
+        dm.stride = model->d_stride.p;
+        dm.tables = model->d_tables.p;
+        dm.code = model->d_code.p;
+        dm.wake = model->d_wake.p;
+        dm.aux = model->d_aux.p;
+        dm.arr_off = model->d_arr_off.p;
+        dm.arr_val = model->d_arr_val.p;
+        if (expand_smem_bytes(dm) > 200 * 1024)
+            throw Failure(STCSP_ERR_UNSUPPORTED, "model needs more shared memory per CTA than an SM has");
+        expand_grid_max = expand_max_grid(dm, sm_count);
     }
 
     void zero_wave_counters() {
@@ -514,31 +514,29 @@ struct stcsp_session {
         CK(cudaEventCreate(&evk0));
         CK(cudaEventCreate(&evk1));
         try {
-            cache_key = model_key(*problem, device);
-            if (std::unique_ptr<ModelCache::Entry> e = model_cache().take(cache_key)) {
-                sets.seed_tables(e->dir, e->words);
-                d_tables.swap(e->tables);
-                tables_built = e->words;
-                hint_frontier = e->cap_frontier;
-                hint_states = e->cap_states;
-                hint_edges = e->cap_edges;
-                hint_table = e->cap_table;
+            if (w == 1) {           // multi-rank solves number constraint sets in lock-step: always from a fresh state
+                cache_key = model_key(*problem, device);
+                model = model_cache().take(cache_key);
             }
-            sets.init(*problem);
+            if (!model) {
+                model.reset(new ModelState());
+                model->sets.init(*problem);
+            }
         } catch (const std::invalid_argument &ex) {
             throw Failure(STCSP_ERR_UNSUPPORTED, ex.what());
         } catch (const std::runtime_error &ex) {
             throw Failure(STCSP_ERR_INVALID, ex.what());
         }
-        upload_model();
+        if (!model->uploaded || model->sets.dirty()) upload_model();
+        else refresh_model();
         counters.reserve(C_COUNT, 0, stream);
         CK(cudaMemsetAsync(counters.p, 0, C_COUNT * sizeof(unsigned long long), stream));
         h_counters = pinned_cache().acquire();       // C_COUNT counters + room for the search control block
         d_offsets.reserve(2 * kMaxWorld, 0, stream);
 
         const int NW = dm.node_words, KW = dm.key_words;
-        const size_t f0 = (size_t)std::max<long long>(4096, hint_frontier), s0 = (size_t)std::max<long long>(4096, hint_states),
-                     e0 = (size_t)std::max<long long>(8192, hint_edges);
+        const size_t f0 = (size_t)std::max<long long>(4096, model->hint_frontier), s0 = (size_t)std::max<long long>(4096, model->hint_states),
+                     e0 = (size_t)std::max<long long>(8192, model->hint_edges);
         frontier[0].reserve(f0 * NW, 0, stream);
         frontier[1].reserve(f0 * NW, 0, stream);
         leaves.reserve(f0 * dm.rec_words, 0, stream);
@@ -561,7 +559,7 @@ struct stcsp_session {
             node[3] = -1;
             for (int v = 0; v < dm.V; v++)
                 for (int o = 0; o < dm.k; o++) {
-                    const int w_ = sets.width()[v];
+                    const int w_ = model->sets.width()[v];
                     const unsigned long long m = w_ >= 64 ? ~0ull : ((1ull << w_) - 1ull);
                     memcpy(&node[4 + 2 * (v * dm.k + o)], &m, 8);
                 }
@@ -573,7 +571,7 @@ struct stcsp_session {
             n_states = 1;
             n_in = 1;
         }
-        ensure_table(std::max<long long>(std::max<long long>(n_states, 1), hint_table / 2));
+        ensure_table(std::max<long long>(std::max<long long>(n_states, 1), model->hint_table / 2));
     }
 
     // Pools big enough for a wave over `nin` input nodes (see the SEARCH_GROW test in search_kernel).
@@ -607,9 +605,9 @@ struct stcsp_session {
             sa.leaf_cap = (long long)(leaves.cap / RW);
             sa.unresolved = unresolved.p;
             sa.unresolved_cap = (long long)unresolved.cap;
-            sa.capmap = d_capmap.p;
-            sa.capvals = d_capvals.p;
-            sa.capmap_mask = capmap.empty() ? -1 : (int32_t)capmap.size() - 1;
+            sa.capmap = model->d_capmap.p;
+            sa.capvals = model->d_capvals.p;
+            sa.capmap_mask = model->capmap.empty() ? -1 : (int32_t)model->capmap.size() - 1;
             sa.table = table.p;
             sa.table_mask = table_size - 1;
             sa.state_key = state_key.p;
@@ -695,9 +693,9 @@ struct stcsp_session {
                     if (!routed) {                      // expand done, nothing routed yet
                         RouteArgs ra{};
                         ra.leaves = leaves.p;
-                        ra.capmap = d_capmap.p;
-                        ra.capvals = d_capvals.p;
-                        ra.capmap_mask = capmap.empty() ? -1 : (int32_t)capmap.size() - 1;
+                        ra.capmap = model->d_capmap.p;
+                        ra.capvals = model->d_capvals.p;
+                        ra.capmap_mask = model->capmap.empty() ? -1 : (int32_t)model->capmap.size() - 1;
                         ra.unresolved = unresolved.p;
                         ra.unresolved_cap = (long long)unresolved.cap;
                         ra.counters = counters.p;
@@ -795,9 +793,9 @@ struct stcsp_session {
                 RouteArgs ra{};
                 ra.leaves = leaves.p;
                 ra.list = nullptr;
-                ra.capmap = d_capmap.p;
-                ra.capvals = d_capvals.p;
-                ra.capmap_mask = capmap.empty() ? -1 : (int32_t)capmap.size() - 1;
+                ra.capmap = model->d_capmap.p;
+                ra.capvals = model->d_capvals.p;
+                ra.capmap_mask = model->capmap.empty() ? -1 : (int32_t)model->capmap.size() - 1;
                 ra.unresolved = unresolved.p;
                 ra.unresolved_cap = (long long)unresolved.cap;
                 ra.counters = counters.p;
@@ -846,7 +844,7 @@ struct stcsp_session {
     }
 
     std::vector<int32_t> cap_key(int32_t cid, const int32_t *values) const {
-        const HostSet &hs = sets.host_set(cid);
+        const HostSet &hs = model->sets.host_set(cid);
         std::vector<int32_t> key;
         key.reserve(1 + hs.cap_vars.size());
         key.push_back(cid);
@@ -867,36 +865,36 @@ struct stcsp_session {
         for (long long i = 0; i < n_unres; i++) {
             const int32_t *rec = host.data() + i * RW;
             std::vector<int32_t> key = cap_key(rec[1], rec + 4);
-            if (cap_lookup.count(key) || !seen.emplace(key, 1).second) continue;
+            if (model->cap_lookup.count(key) || !seen.emplace(key, 1).second) continue;
             pending.push_back(rec[1]);
             pending.insert(pending.end(), rec + 4, rec + 4 + V);
         }
     }
 
     void capmap_insert(int32_t cid, const std::vector<int32_t> &key, int32_t next) {
-        if ((capmap_used + 1) * 2 > (long long)capmap.size()) {
+        if ((model->capmap_used + 1) * 2 > (long long)model->capmap.size()) {
             std::vector<CapEntry> old;
-            old.swap(capmap);
+            old.swap(model->capmap);
             CapEntry empty{};
             empty.cid = -1;
-            capmap.assign(std::max<size_t>(64, old.size() * 2), empty);
-            capmap_used = 0;
+            model->capmap.assign(std::max<size_t>(64, old.size() * 2), empty);
+            model->capmap_used = 0;
             for (const CapEntry &e : old)
                 if (e.cid != -1) place(e);
         }
         CapEntry e{};
         e.cid = cid;
         e.next = next;
-        e.off = (int32_t)capvals.size();
-        capvals.insert(capvals.end(), key.begin() + 1, key.end());
+        e.off = (int32_t)model->capvals.size();
+        model->capvals.insert(model->capvals.end(), key.begin() + 1, key.end());
         place(e);
     }
     void place(const CapEntry &e) {
-        const int n = (int)sets.host_set(e.cid).cap_vars.size();
-        uint32_t h = capmap_hash(e.cid, capvals.data() + e.off, n) & (uint32_t)(capmap.size() - 1);
-        while (capmap[h].cid != -1) h = (h + 1) & (uint32_t)(capmap.size() - 1);
-        capmap[h] = e;
-        capmap_used++;
+        const int n = (int)model->sets.host_set(e.cid).cap_vars.size();
+        uint32_t h = capmap_hash(e.cid, model->capvals.data() + e.off, n) & (uint32_t)(model->capmap.size() - 1);
+        while (model->capmap[h].cid != -1) h = (h + 1) & (uint32_t)(model->capmap.size() - 1);
+        model->capmap[h] = e;
+        model->capmap_used++;
     }
 
     void resolve(const int32_t *requests, int64_t n_req) {
@@ -905,26 +903,26 @@ struct stcsp_session {
         for (int64_t i = 0; i < n_req; i++) {
             const int32_t *rq = requests + i * (1 + V);
             const int32_t cid = rq[0];
-            if (cid < 0 || cid >= sets.n_sets()) throw Failure(STCSP_ERR_INVALID, "resolve request names an unknown constraint set");
+            if (cid < 0 || cid >= model->sets.n_sets()) throw Failure(STCSP_ERR_INVALID, "resolve request names an unknown constraint set");
             std::vector<int32_t> key = cap_key(cid, rq + 1);
-            if (cap_lookup.count(key)) continue;
+            if (model->cap_lookup.count(key)) continue;
             int32_t next;
             try {
-                next = sets.successor(cid, rq + 1);
+                next = model->sets.successor(cid, rq + 1);
             } catch (const std::invalid_argument &ex) {
                 throw Failure(STCSP_ERR_UNSUPPORTED, ex.what());
             }
-            cap_lookup[key] = next;
+            model->cap_lookup[key] = next;
             capmap_insert(cid, key, next);
             added = true;
         }
-        if (sets.dirty()) upload_model();
+        if (model->sets.dirty()) upload_model();
         if (added) {
-            d_capmap.reserve(capmap.size(), 0, stream);
-            CK(cudaMemcpyAsync(d_capmap.p, capmap.data(), capmap.size() * sizeof(CapEntry), cudaMemcpyHostToDevice, stream));
-            upload(d_capvals, capvals);
+            model->d_capmap.reserve(model->capmap.size(), 0, stream);
+            CK(cudaMemcpyAsync(model->d_capmap.p, model->capmap.data(), model->capmap.size() * sizeof(CapEntry), cudaMemcpyHostToDevice, stream));
+            upload(model->d_capvals, model->capvals);
             CK(cudaStreamSynchronize(stream));
-            h2d += (long long)(capmap.size() * sizeof(CapEntry));
+            h2d += (long long)(model->capmap.size() * sizeof(CapEntry));
         }
         if (n_unres > 0) {
             CK(cudaMemsetAsync(counters.p + C_UNRESOLVED, 0, sizeof(unsigned long long), stream));
@@ -932,9 +930,9 @@ struct stcsp_session {
             ra.leaves = leaves.p;
             ra.list = unresolved.p;
             ra.count = n_unres;
-            ra.capmap = d_capmap.p;
-            ra.capvals = d_capvals.p;
-            ra.capmap_mask = capmap.empty() ? -1 : (int32_t)capmap.size() - 1;
+            ra.capmap = model->d_capmap.p;
+            ra.capvals = model->d_capvals.p;
+            ra.capmap_mask = model->capmap.empty() ? -1 : (int32_t)model->capmap.size() - 1;
             ra.unresolved = gathered.p;         // scratch: nothing may remain unresolved
             ra.unresolved_cap = (long long)gathered.cap;
             ra.counters = counters.p;
@@ -1047,7 +1045,7 @@ struct stcsp_session {
             throw;
         }
         d2h += (long long)keys.size() * 4 + n_edges * (2 + V) * 4;
-        st->sig_vars = sets.sig_vars();
+        st->sig_vars = model->sets.sig_vars();
         st->state_sig.assign((size_t)n_states * SL, 0);
         st->state_cset.resize((size_t)n_states);
         st->state_failed.assign((size_t)n_states, 0);
@@ -1063,11 +1061,11 @@ struct stcsp_session {
         const int V = dm.V, SL = dm.sig_len;
         part->n_vars = V;
         part->n_sig_vars = dm.n_sig;
-        part->n_until = sets.n_until();
-        part->n_until_vars = sets.n_until_vars();
+        part->n_until = model->sets.n_until();
+        part->n_until_vars = model->sets.n_until_vars();
         part->sig_len = SL;
-        part->root_final = sets.n_until() == 0;
-        part->n_constraint_sets = sets.n_sets();
+        part->root_final = model->sets.n_until() == 0;
+        part->n_constraint_sets = model->sets.n_sets();
         if (part->n_states == 0) part->n_states = n_states;
         if (part->n_edges == 0) part->n_edges = n_edges;
         part->n_search_nodes = t_nodes;
@@ -1169,14 +1167,14 @@ struct stcsp_session {
         auto *st = new PinnedStore();
         Release guard{stream};
         try {
-            st->sig_vars.alloc(sets.sig_vars().size() * 4);
+            st->sig_vars.alloc(model->sets.sig_vars().size() * 4);
             st->state_sig.alloc((size_t)ns * SL * 4);
             st->state_cset.alloc((size_t)ns * 4);
             st->state_failed.alloc((size_t)ns);
             st->edge_src.alloc((size_t)n_final * 4);
             st->edge_dst.alloc((size_t)n_final * 4);
             st->edge_label.alloc((size_t)n_final * V * 4);
-            if (!sets.sig_vars().empty()) memcpy(st->sig_vars.p, sets.sig_vars().data(), sets.sig_vars().size() * 4);
+            if (!model->sets.sig_vars().empty()) memcpy(st->sig_vars.p, model->sets.sig_vars().data(), model->sets.sig_vars().size() * 4);
             if (ns) {
                 if (SL) CK(cudaMemcpyAsync(st->state_sig.p, rows_sig.p, (size_t)ns * SL * 4, cudaMemcpyDeviceToHost, stream));
                 CK(cudaMemcpyAsync(st->state_cset.p, rows_cset.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, stream));
