@@ -1378,10 +1378,15 @@ static void configure_expand(size_t smem) {
 int expand_max_grid(const DevModel &m, int sm_count) {
     const size_t smem = expand_smem_bytes(m);
     configure_expand(smem);
+    static size_t cached_smem = ~(size_t)0;
+    static int cached_per_sm = 0;
+    if (smem == cached_smem) return cached_per_sm * sm_count;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_kernel<false>, kExpandWarps * 32, smem) != cudaSuccess ||
         per_sm < 1)
         per_sm = 1;
+    cached_smem = smem;
+    cached_per_sm = per_sm;
     return per_sm * sm_count;
 }
 
@@ -1400,9 +1405,14 @@ int search_max_grid(const DevModel &m, int sm_count) {
         cudaFuncSetAttribute(search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = smem;
     }
+    static size_t cached_smem = ~(size_t)0;
+    static int cached_per_sm = 0;
+    if (smem == cached_smem) return cached_per_sm * sm_count;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel, kExpandWarps * 32, smem) != cudaSuccess || per_sm < 1)
-        return 0;
+        per_sm = 0;
+    cached_smem = smem;
+    cached_per_sm = per_sm;
     return per_sm * sm_count;
 }
 

@@ -209,6 +209,44 @@ std::string model_key(const stcsp_problem_t &p, int device) {
     return k;
 }
 
+// A stream with its timing events, pooled per device: creating them costs ~50 us per solve otherwise.
+struct ExecContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int sm_count = 0, coop = 0;
+};
+struct ExecPool {
+    std::mutex mu;
+    std::vector<ExecContext> idle;
+    ExecContext acquire(int device) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (size_t i = 0; i < idle.size(); i++)
+                if (idle[i].device == device) {
+                    ExecContext c = idle[i];
+                    idle.erase(idle.begin() + (long)i);
+                    return c;
+                }
+        }
+        ExecContext c;
+        c.device = device;
+        CK(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
+        if (cudaDeviceGetAttribute(&c.coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess) c.coop = 0;
+        CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c.ev[i]));
+        return c;
+    }
+    void give_back(const ExecContext &c) {
+        std::lock_guard<std::mutex> g(mu);
+        idle.push_back(c);
+    }
+};
+ExecPool &exec_pool() {
+    static ExecPool *p = new ExecPool();
+    return *p;
+}
+
 // Pinned host blocks for the counter read-back, cached per process (cudaMallocHost costs ~1 ms).
 struct PinnedCache {
     std::mutex mu;
@@ -321,7 +359,7 @@ using namespace stcsp;
 struct stcsp_session {
     std::unique_ptr<ModelState> model;
     stcsp_options_t opt{};
-    int rank = 0, world = 1, device = 0, sm_count = 148;
+    int rank = 0, world = 1, device = 0, sm_count = 148, coop_launch = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     DevModel dm{};
@@ -359,11 +397,15 @@ struct stcsp_session {
             model_cache().put(cache_key, std::move(model));       // the compiled model stays resident for the next solve
         }
         release_all();
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
-        if (evk0) cudaEventDestroy(evk0);
-        if (evk1) cudaEventDestroy(evk1);
-        if (stream) cudaStreamDestroy(stream);
+        if (stream) {                       // idle again (synchronised above): back to the pool
+            ExecContext c;
+            c.device = device;
+            c.stream = stream;
+            c.ev[0] = ev0; c.ev[1] = ev1; c.ev[2] = evk0; c.ev[3] = evk1;
+            c.sm_count = sm_count;
+            c.coop = coop_launch;
+            exec_pool().give_back(c);
+        }
     }
 
     void release_all() {
@@ -507,12 +549,13 @@ struct stcsp_session {
         } else {
             CK(cudaGetDevice(&device));
         }
-        CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
-        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        CK(cudaEventCreate(&ev0));
-        CK(cudaEventCreate(&ev1));
-        CK(cudaEventCreate(&evk0));
-        CK(cudaEventCreate(&evk1));
+        {
+            const ExecContext c = exec_pool().acquire(device);
+            stream = c.stream;
+            ev0 = c.ev[0]; ev1 = c.ev[1]; evk0 = c.ev[2]; evk1 = c.ev[3];
+            sm_count = c.sm_count;
+            coop_launch = c.coop;
+        }
         try {
             if (w == 1) {           // multi-rank solves number constraint sets in lock-step: always from a fresh state
                 cache_key = model_key(*problem, device);
@@ -548,8 +591,7 @@ struct stcsp_session {
         d_ctl.reserve(1, 0, stream);
         h_ctl = reinterpret_cast<SearchCtl *>(h_counters + C_COUNT);
         search_grid = search_max_grid(dm, sm_count);
-        int coop = 0;
-        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) search_grid = 0;
+        if (!coop_launch) search_grid = 0;
         if (rank == 0) {
             // root state (reference src/solveralgorithm.cpp:951-954) and its search node
             std::vector<int32_t> key(KW, 0);
