@@ -94,6 +94,83 @@ __global__ void __launch_bounds__(256) state_rows_kernel(const int32_t *keys, lo
     }
 }
 
+// Small automata: everything above in ONE CTA (no launches or host round trips between the steps).
+//   deg/first/cursor/outdeg: n_states + 1 ints each; failed: n_states bytes; alive: n_edges bytes
+// result[0] = edges that died in the fail-rule fixpoint (the host compacts only then).
+__global__ void __launch_bounds__(1024) finish_small_kernel(const int32_t *src, const int32_t *dst, const int32_t *label,
+                                                           int n_edges, int V, int n_states, int32_t *deg, int32_t *first,
+                                                           int32_t *cursor, int32_t *outdeg, uint8_t *failed, uint8_t *alive,
+                                                           int32_t *osrc, int32_t *odst, int32_t *olabel, const int32_t *keys,
+                                                           int KW, int32_t *cset, int32_t *sig, int do_trim, int32_t *result) {
+    __shared__ int32_t partial[1024];
+    __shared__ int s_changed, s_dead;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    for (int s = tid; s <= n_states; s += nt) deg[s] = 0;
+    if (tid == 0) { s_changed = 0; s_dead = 0; }
+    __syncthreads();
+    for (int e = tid; e < n_edges; e += nt) atomicAdd(&deg[src[e]], 1);
+    __syncthreads();
+    // exclusive scan of deg[0 .. n_states]: contiguous chunk per thread, block scan of the chunk sums
+    const int n = n_states + 1, chunk = (n + nt - 1) / nt, lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += deg[i];
+    partial[tid] = sum;
+    __syncthreads();
+    for (int off = 1; off < nt; off <<= 1) {
+        const int v = tid >= off ? partial[tid - off] : 0;
+        __syncthreads();
+        partial[tid] += v;
+        __syncthreads();
+    }
+    int run = partial[tid] - sum;
+    for (int i = lo; i < hi; i++) {
+        const int d = deg[i];
+        first[i] = run;
+        cursor[i] = run;
+        outdeg[i] = d;
+        if (i < n_states) failed[i] = do_trim && d == 0;
+        run += d;
+    }
+    __syncthreads();
+    // group by source: one warp per edge
+    for (int e = warp; e < n_edges; e += nwarps) {
+        const int s = src[e];
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(&cursor[s], 1);
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (lane == 0) { osrc[pos] = s; odst[pos] = dst[e]; alive[pos] = 1; }
+        for (int v = lane; v < V; v += 32) olabel[(long long)pos * V + v] = label[(long long)e * V + v];
+    }
+    // state rows
+    for (int i = tid; i < n_states * KW; i += nt) {
+        const int s = i / KW, j = i % KW, v = keys[i];
+        if (j == 0) cset[s] = v < 0 ? 0 : v;
+        else sig[s * (KW - 1) + (j - 1)] = v;
+    }
+    __syncthreads();
+    // fail rule to a fixpoint
+    if (do_trim) {
+        for (;;) {
+            for (int e = tid; e < n_edges; e += nt) {
+                if (!alive[e] || !failed[odst[e]]) continue;
+                alive[e] = 0;
+                atomicAdd(&s_dead, 1);
+                if (atomicSub(&outdeg[osrc[e]], 1) == 1) {
+                    failed[osrc[e]] = 1;
+                    s_changed = 1;
+                }
+            }
+            __syncthreads();
+            const int again = s_changed;
+            __syncthreads();
+            if (!again) break;
+            if (tid == 0) s_changed = 0;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) result[0] = s_dead;
+}
+
 int grid_for(long long n, int per_block, int sm_count) {
     long long g = (n + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -141,6 +218,14 @@ void launch_edge_compact(const int32_t *src, const int32_t *dst, const int32_t *
                          long long n, int V, int32_t *osrc, int32_t *odst, int32_t *olabel, int sm_count, cudaStream_t stream) {
     if (n > 0)
         edge_compact_kernel<<<grid_for(n, 8, sm_count), 256, 0, stream>>>(src, dst, label, alive, pos, n, V, osrc, odst, olabel);
+}
+
+void launch_finish_small(const int32_t *src, const int32_t *dst, const int32_t *label, int n_edges, int V, int n_states,
+                         int32_t *deg, int32_t *first, int32_t *cursor, int32_t *outdeg, uint8_t *failed, uint8_t *alive,
+                         int32_t *osrc, int32_t *odst, int32_t *olabel, const int32_t *keys, int KW, int32_t *cset, int32_t *sig,
+                         int do_trim, int32_t *result, cudaStream_t stream) {
+    finish_small_kernel<<<1, 1024, 0, stream>>>(src, dst, label, n_edges, V, n_states, deg, first, cursor, outdeg, failed, alive,
+                                                osrc, odst, olabel, keys, KW, cset, sig, do_trim, result);
 }
 
 void launch_state_rows(const int32_t *keys, long long n_states, int KW, int32_t *cset, int32_t *sig, int sm_count,

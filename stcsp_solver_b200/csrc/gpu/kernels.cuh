@@ -179,6 +179,11 @@ void launch_trim_step(const int32_t *src, const int32_t *dst, long long n, uint8
 void launch_alive_to_int(const uint8_t *alive, long long n, int32_t *flag, int sm_count, cudaStream_t stream);
 void launch_edge_compact(const int32_t *src, const int32_t *dst, const int32_t *label, const uint8_t *alive, const int32_t *pos,
                          long long n, int V, int32_t *osrc, int32_t *odst, int32_t *olabel, int sm_count, cudaStream_t stream);
+// small automata: group by source + fail rule + state rows in one single-CTA launch; result[0] = dead edges
+void launch_finish_small(const int32_t *src, const int32_t *dst, const int32_t *label, int n_edges, int V, int n_states,
+                         int32_t *deg, int32_t *first, int32_t *cursor, int32_t *outdeg, uint8_t *failed, uint8_t *alive,
+                         int32_t *osrc, int32_t *odst, int32_t *olabel, const int32_t *keys, int KW, int32_t *cset, int32_t *sig,
+                         int do_trim, int32_t *result, cudaStream_t stream);
 void launch_state_rows(const int32_t *keys, long long n_states, int KW, int32_t *cset, int32_t *sig, int sm_count,
                        cudaStream_t stream);
 

@@ -1143,7 +1143,27 @@ struct stcsp_session {
         };
         int32_t *f_src = edge_src.p, *f_dst = edge_dst.p, *f_label = edge_label.p;
         long long n_final = ne;
-        {
+        // small automata: one single-CTA launch does all of it and the host learns afterwards whether any edge died
+        const bool small = ns <= 16384 && ne <= 4096;
+        if (small) {
+            deg.reserve((size_t)ns + 1, 0, stream);
+            first.reserve((size_t)ns + 1, 0, stream);
+            fill.reserve((size_t)ns + 1, 0, stream);
+            outdeg.reserve((size_t)ns + 1, 0, stream);
+            failed.reserve((size_t)ns + 1, 0, stream);
+            alive.reserve((size_t)ne + 1, 0, stream);
+            s_src.reserve((size_t)ne + 1, 0, stream);
+            s_dst.reserve((size_t)ne + 1, 0, stream);
+            s_label.reserve((size_t)ne * V + 1, 0, stream);
+            rows_cset.reserve((size_t)ns + 1, 0, stream);
+            rows_sig.reserve((size_t)ns * std::max(SL, 1) + 1, 0, stream);
+            launch_finish_small(edge_src.p, edge_dst.p, edge_label.p, (int)ne, V, (int)ns, deg.p, first.p, fill.p, outdeg.p,
+                                failed.p, alive.p, s_src.p, s_dst.p, s_label.p, state_key.p, KW, rows_cset.p, rows_sig.p,
+                                trim ? 1 : 0, reinterpret_cast<int32_t *>(counters.p + C_OUT), stream);
+            CK(cudaGetLastError());
+            f_src = s_src.p; f_dst = s_dst.p; f_label = s_label.p;
+            t_launches++;
+        } else {
             deg.reserve((size_t)ns + 1, 0, stream);
             first.reserve((size_t)ns + 1, 0, stream);
             fill.reserve((size_t)ns + 1, 0, stream);
@@ -1227,8 +1247,29 @@ struct stcsp_session {
                 CK(cudaMemcpyAsync(st->edge_dst.p, f_dst, (size_t)n_final * 4, cudaMemcpyDeviceToHost, stream));
                 CK(cudaMemcpyAsync(st->edge_label.p, f_label, (size_t)n_final * V * 4, cudaMemcpyDeviceToHost, stream));
             }
+            if (small) CK(cudaMemcpyAsync(h_counters, counters.p + C_OUT, 8, cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             if (timing_open) CK(cudaEventElapsedTime(&ms, ev0, ev1));
+            const long long dead = small ? (long long)(int32_t)h_counters[0] : 0;
+            if (dead > 0) {
+                // rare (models with dead ends): compact the live edges into the append-order buffers and copy them again
+                flags.reserve((size_t)ne + 1, 0, stream);
+                launch_alive_to_int(alive.p, ne, flags.p, sm_count, stream);
+                const size_t tmp2 = scan_temp_bytes(ne + 1);
+                scan_tmp.reserve(tmp2 + 16, 0, stream);
+                launch_exclusive_scan(scan_tmp.p, tmp2, flags.p, flags.p, ne, stream);
+                launch_edge_compact(f_src, f_dst, f_label, alive.p, flags.p, ne, V, edge_src.p, edge_dst.p, edge_label.p, sm_count,
+                                    stream);
+                CK(cudaGetLastError());
+                n_final = ne - dead;
+                t_launches += 3;
+                if (n_final) {
+                    CK(cudaMemcpyAsync(st->edge_src.p, edge_src.p, (size_t)n_final * 4, cudaMemcpyDeviceToHost, stream));
+                    CK(cudaMemcpyAsync(st->edge_dst.p, edge_dst.p, (size_t)n_final * 4, cudaMemcpyDeviceToHost, stream));
+                    CK(cudaMemcpyAsync(st->edge_label.p, edge_label.p, (size_t)n_final * V * 4, cudaMemcpyDeviceToHost, stream));
+                }
+                CK(cudaStreamSynchronize(stream));
+            }
         } catch (...) {
             delete st;
             throw;
