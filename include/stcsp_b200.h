@@ -92,9 +92,10 @@ typedef struct stcsp_options {
     int32_t verbosity;               /* flag -l */
     int64_t enum_limit_now;          /* max tuples enumerated per constraint revision at the current time point */
     int64_t enum_limit_ahead;        /* same, at look-ahead time points 1..k-1 */
-    int64_t max_frontier_nodes;      /* capacity of each search-node frontier buffer */
-    int64_t max_states;              /* capacity of the state table */
-    int64_t max_edges;               /* capacity of the edge store */
+    int64_t max_frontier_nodes;      /* > 0: give up with STCSP_ERR_CAPACITY as soon as a wave is wider than this (a multi-GPU
+                                        driver uses it to keep small instances on one GPU); 0: no limit */
+    int64_t max_states;              /* reserved */
+    int64_t max_edges;               /* reserved */
     int32_t reserved0;
     int32_t profile_kernels;         /* 1: step-wise path (one expand / route / ingest launch per wave) with every expand launch
                                         timed by CUDA events, instead of the persistent search kernel */

@@ -1207,7 +1207,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             const long long states = (long long)cnt[C_STATES], edges = (long long)cnt[C_EDGES];
             int st = SEARCH_RUN;
             if (n_in == 0) st = SEARCH_DONE;
-            else if (ctl->waves_left <= 0) st = SEARCH_YIELD;
+            else if (ctl->waves_left <= 0 || (A.max_frontier > 0 && n_in > A.max_frontier)) st = SEARCH_YIELD;
             else if (n_in > A.leaf_cap || n_in > A.unresolved_cap || states + n_in > A.state_cap ||
                      edges + n_in > A.edge_cap || 2 * (states + n_in) > A.table_mask + 1 || 2 * n_in > A.out_cap)
                 st = SEARCH_GROW;

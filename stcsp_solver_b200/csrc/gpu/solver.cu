@@ -637,6 +637,8 @@ struct stcsp_session {
         zero_wave_counters();
         while (n_in > 0) {
             if (deadline > 0 && now_s() > deadline) throw Failure(STCSP_ERR_TIMEOUT, "time limit reached");
+            if (opt.max_frontier_nodes > 0 && n_in > opt.max_frontier_nodes)
+                throw Failure(STCSP_ERR_CAPACITY, "frontier wider than max_frontier_nodes");
             SearchArgs sa{};
             sa.ctl = d_ctl.p;
             sa.counters = counters.p;
@@ -658,6 +660,7 @@ struct stcsp_session {
             sa.edge_dst = edge_dst.p;
             sa.edge_label = edge_label.p;
             sa.edge_cap = (long long)std::min(edge_src.cap, edge_label.cap / (size_t)V);
+            sa.max_frontier = opt.max_frontier_nodes;
             DBuf<unsigned long long> trace;
             const long long trace_waves = 256;
             if (opt.verbosity > 2) {
@@ -1519,6 +1522,8 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
         }
         while (frontier > 0) {
             if (deadline > 0 && now_s() > deadline) throw Failure(STCSP_ERR_TIMEOUT, "time limit reached");
+            if (s->opt.max_frontier_nodes > 0 && frontier > s->opt.max_frontier_nodes)
+                throw Failure(STCSP_ERR_CAPACITY, "frontier wider than max_frontier_nodes");
             int64_t n_leaves = 0, n_pending = 0;
             s->expand(&n_leaves, &n_pending);
             if (n_pending > 0) {

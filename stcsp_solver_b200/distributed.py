@@ -94,18 +94,46 @@ class WaveExchange:
         return out
 
 
+# A wave this wide keeps one B200 busy; below it, sharding only adds two collectives per wave.
+SINGLE_GPU_FRONTIER = 32768
+
+
 def solve_distributed(model: binding.Model, options: Optional[binding.Options] = None, group=None,
-                      trim: bool = True):
+                      trim: bool = True, adaptive: bool = True):
     """Solve on all ranks of `group` (default: the world).  Returns the merged Automaton on rank 0, None elsewhere.
 
     The caller has initialised torch.distributed (backend nccl) and set the CUDA device of this process.
-    Per wave: local expand, ONE small all-gather (frontier size, pending requests, records for every rank) from
+    adaptive: instances whose waves never exceed SINGLE_GPU_FRONTIER nodes are solved by rank 0 alone (the other ranks
+    wait for its verdict); larger ones are sharded.  Per wave of the sharded search: local expand, ONE small all-gather (frontier size, pending requests, records for every rank) from
     which each rank derives termination, the resolve decision and its receive counts, ONE payload all-to-all,
     local ingest.
     """
     ex = WaveExchange(group)
     opts = options if options is not None else binding.default_options()
     opts.use_current_device = 1
+    if adaptive and ex.world > 1:
+        # Small instances stay on one GPU: rank 0 runs the persistent single-GPU search with a bound on the wave width;
+        # only if a wave outgrows it do all ranks start the sharded search (the bounded attempt costs a few waves).
+        verdict = torch.zeros(1, dtype=torch.int64, device=ex.device)
+        automaton = None
+        if ex.rank == 0:
+            saved = opts.max_frontier_nodes
+            opts.max_frontier_nodes = SINGLE_GPU_FRONTIER
+            try:
+                automaton = binding.solve(model, opts)
+                if not trim:
+                    raise ValueError("adaptive single-GPU path always trims")
+                verdict[0] = 1
+            except binding.StcspError as e:
+                if e.status != binding.ERR_CAPACITY:
+                    raise
+            finally:
+                opts.max_frontier_nodes = saved
+        dist.broadcast(verdict, src=0, group=ex.group)
+        if int(verdict.item()) == 1:
+            if automaton is not None:
+                automaton.exchange_stats = {"waves": 0, "records_sent": 0, "single_gpu": True}
+            return automaton
     session = binding.Session(model, opts, ex.rank, ex.world)
     words = session.record_words
     world, rank = ex.world, ex.rank

@@ -19,7 +19,7 @@ for name in names:
     model = binding.Model(text)
     for rep in range(2):
         dist.barrier(); torch.cuda.synchronize(); t0 = time.time()
-        a = distributed.solve_distributed(model)
+        a = distributed.solve_distributed(model, adaptive=os.environ.get("ADAPTIVE", "1") == "1")
         torch.cuda.synchronize(); dt = time.time() - t0
     if dist.get_rank() == 0:
         sol = binding.Solution(model, a)
