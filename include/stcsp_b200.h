@@ -208,6 +208,8 @@ void stcsp_session_destroy(stcsp_session_t *s);
 /* int32 words per leaf record / per resolve request (1 + n_vars: constraint set, assignment) */
 int32_t stcsp_session_record_words(const stcsp_session_t *s);
 int32_t stcsp_session_request_words(const stcsp_session_t *s);
+/* int32 words per state key (1 + sig_len: constraint set, signature values, until flags) */
+int32_t stcsp_session_key_words(const stcsp_session_t *s);
 /* Expand the local frontier by one wave.  *n_leaves: leaves found; *n_pending: distinct resolve
  * requests this rank has (0 almost always). */
 int stcsp_session_expand(stcsp_session_t *s, int64_t *n_leaves, int64_t *n_pending);
@@ -227,6 +229,19 @@ int stcsp_session_ingest(stcsp_session_t *s, const int32_t *inbox, int64_t n_rec
  * local_index * world_size + rank) and the edges INTO them with global src/dst ids, untrimmed and
  * unsorted.  Release with stcsp_automaton_free. */
 int stcsp_session_finish(stcsp_session_t *s, stcsp_automaton_t *part);
+
+/* Device-side merge (preferred over finish + assemble for large automata):
+ *   counts        this rank's state / edge counts and its 10 search statistics
+ *   export        copy this rank's part into caller-provided DEVICE memory: keys [n_states * (1 + sig_len)], src / dst
+ *                 [n_edges] (global ids), label [n_edges * n_vars]; the caller moves them to rank 0 (NCCL send / recv)
+ *   finish_merged rank 0 only: the parts of all ranks, concatenated in rank order in device memory (keys, src, dst, label;
+ *                 src / dst / label are overwritten), are renumbered to dense ids, grouped by source, trimmed and copied to
+ *                 the host.  extra_stats = element-wise sum of the other ranks' statistics (or NULL). */
+int stcsp_session_counts(stcsp_session_t *s, int64_t *n_states, int64_t *n_edges, int64_t *stats10);
+int stcsp_session_export(stcsp_session_t *s, int32_t *keys, int32_t *src, int32_t *dst, int32_t *label);
+int stcsp_session_finish_merged(stcsp_session_t *s, int32_t world_size, const int64_t *n_states, const int64_t *n_edges,
+                                const int32_t *keys, int32_t *src, int32_t *dst, int32_t *label, const int64_t *extra_stats,
+                                int32_t trim, stcsp_automaton_t *out);
 
 /* Merge the per-rank parts (parts[r] = part of rank r; arrays may live in caller memory) into one
  * automaton with dense state ids (ascending global id, root = 0) and edges grouped by source;

@@ -119,12 +119,19 @@ def lib() -> C.CDLL:
         L.stcsp_session_record_words.restype = C.c_int32
         L.stcsp_session_request_words.argtypes = [C.c_void_p]
         L.stcsp_session_request_words.restype = C.c_int32
+        L.stcsp_session_key_words.argtypes = [C.c_void_p]
+        L.stcsp_session_key_words.restype = C.c_int32
         L.stcsp_session_expand.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.stcsp_session_pending.argtypes = [C.c_void_p, C.c_void_p]
         L.stcsp_session_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.stcsp_session_outbox.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.stcsp_session_ingest.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.stcsp_session_finish.argtypes = [C.c_void_p, C.POINTER(AutomatonC)]
+        L.stcsp_session_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.stcsp_session_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.stcsp_session_finish_merged.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32,
+                                                  C.POINTER(AutomatonC)]
         L.stcsp_automaton_assemble.argtypes = [C.POINTER(AutomatonC), C.c_int32, C.POINTER(AutomatonC)]
         _lib = L
     return _lib
@@ -293,6 +300,7 @@ class Session:
         self.rank, self.world_size = rank, world_size
         self.record_words = lib().stcsp_session_record_words(self._h)
         self.request_words = lib().stcsp_session_request_words(self._h)
+        self.key_words = lib().stcsp_session_key_words(self._h)
 
     def close(self):
         try:
@@ -332,6 +340,26 @@ class Session:
     def finish(self) -> Automaton:
         out = AutomatonC()
         _check(lib().stcsp_session_finish(self._h, C.byref(out)))
+        return Automaton(out, lib().stcsp_automaton_free)
+
+    def counts(self):
+        """(n_states, n_edges, stats[10]) of this rank's part."""
+        ns, ne = C.c_int64(), C.c_int64()
+        stats = (C.c_int64 * 10)()
+        _check(lib().stcsp_session_counts(self._h, C.byref(ns), C.byref(ne), stats))
+        return ns.value, ne.value, np.array(list(stats), dtype=np.int64)
+
+    def export(self, keys_ptr: int, src_ptr: int, dst_ptr: int, label_ptr: int) -> None:
+        _check(lib().stcsp_session_export(self._h, keys_ptr, src_ptr, dst_ptr, label_ptr))
+
+    def finish_merged(self, n_states, n_edges, keys_ptr, src_ptr, dst_ptr, label_ptr, extra_stats, trim=True) -> Automaton:
+        w = len(n_states)
+        ns = (C.c_int64 * w)(*[int(x) for x in n_states])
+        ne = (C.c_int64 * w)(*[int(x) for x in n_edges])
+        ex = (C.c_int64 * 10)(*[int(x) for x in extra_stats])
+        out = AutomatonC()
+        _check(lib().stcsp_session_finish_merged(self._h, w, ns, ne, keys_ptr, src_ptr, dst_ptr, label_ptr, ex, int(trim),
+                                                 C.byref(out)))
         return Automaton(out, lib().stcsp_automaton_free)
 
 

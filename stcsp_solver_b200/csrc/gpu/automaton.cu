@@ -171,6 +171,40 @@ __global__ void __launch_bounds__(1024) finish_small_kernel(const int32_t *src, 
     if (tid == 0) result[0] = s_dead;
 }
 
+// ---- multi-rank merge: global state ids (local * W + rank) -> dense ids in ascending global order --------------
+struct RankCounts {
+    int W;
+    long long n[16];        // states owned by each rank
+    long long off[16];      // first row of each rank in the concatenated key array
+};
+
+__device__ __forceinline__ int dense_id(const RankCounts &rc, long long g) {
+    const long long l = g / rc.W;
+    const int r = (int)(g % rc.W);
+    long long d = 0;
+    for (int q = 0; q < rc.W; q++) d += (rc.n[q] < l ? rc.n[q] : l) + (q < r && rc.n[q] > l ? 1 : 0);
+    return (int)d;
+}
+
+__global__ void __launch_bounds__(256) remap_ids_kernel(int32_t *ids, long long n, RankCounts rc) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        ids[i] = dense_id(rc, ids[i]);
+}
+
+// keys_in: rank 0's rows, then rank 1's ... ; keys_out: rows in dense order
+__global__ void __launch_bounds__(256) place_keys_kernel(const int32_t *keys_in, int32_t *keys_out, long long total_rows, int KW,
+                                                         RankCounts rc) {
+    const long long total = total_rows * KW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / KW;
+        const int j = (int)(i % KW);
+        int r = 0;
+        while (r + 1 < rc.W && row >= rc.off[r + 1]) r++;
+        const long long l = row - rc.off[r];
+        keys_out[(long long)dense_id(rc, l * rc.W + r) * KW + j] = keys_in[i];
+    }
+}
+
 int grid_for(long long n, int per_block, int sm_count) {
     long long g = (n + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -226,6 +260,29 @@ void launch_finish_small(const int32_t *src, const int32_t *dst, const int32_t *
                          int do_trim, int32_t *result, cudaStream_t stream) {
     finish_small_kernel<<<1, 1024, 0, stream>>>(src, dst, label, n_edges, V, n_states, deg, first, cursor, outdeg, failed, alive,
                                                 osrc, odst, olabel, keys, KW, cset, sig, do_trim, result);
+}
+
+static RankCounts make_counts(int world, const long long *n_states) {
+    RankCounts rc{};
+    rc.W = world;
+    long long off = 0;
+    for (int r = 0; r < world; r++) {
+        rc.n[r] = n_states[r];
+        rc.off[r] = off;
+        off += n_states[r];
+    }
+    return rc;
+}
+
+void launch_remap_ids(int32_t *ids, long long n, int world, const long long *n_states, int sm_count, cudaStream_t stream) {
+    if (n > 0) remap_ids_kernel<<<grid_for(n, 256, sm_count), 256, 0, stream>>>(ids, n, make_counts(world, n_states));
+}
+
+void launch_place_keys(const int32_t *keys_in, int32_t *keys_out, long long total_rows, int KW, int world, const long long *n_states,
+                       int sm_count, cudaStream_t stream) {
+    if (total_rows > 0)
+        place_keys_kernel<<<grid_for(total_rows * KW, 256, sm_count), 256, 0, stream>>>(keys_in, keys_out, total_rows, KW,
+                                                                                        make_counts(world, n_states));
 }
 
 void launch_state_rows(const int32_t *keys, long long n_states, int KW, int32_t *cset, int32_t *sig, int sm_count,

@@ -185,6 +185,10 @@ void launch_finish_small(const int32_t *src, const int32_t *dst, const int32_t *
                          int32_t *deg, int32_t *first, int32_t *cursor, int32_t *outdeg, uint8_t *failed, uint8_t *alive,
                          int32_t *osrc, int32_t *odst, int32_t *olabel, const int32_t *keys, int KW, int32_t *cset, int32_t *sig,
                          int do_trim, int32_t *result, cudaStream_t stream);
+// multi-rank merge on one device: global ids -> dense ids; key rows (concatenated by rank) -> dense order
+void launch_remap_ids(int32_t *ids, long long n, int world, const long long *n_states, int sm_count, cudaStream_t stream);
+void launch_place_keys(const int32_t *keys_in, int32_t *keys_out, long long total_rows, int KW, int world, const long long *n_states,
+                       int sm_count, cudaStream_t stream);
 void launch_state_rows(const int32_t *keys, long long n_states, int KW, int32_t *cset, int32_t *sig, int sm_count,
                        cudaStream_t stream);
 

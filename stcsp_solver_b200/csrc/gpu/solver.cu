@@ -299,7 +299,7 @@ void bind_store(stcsp_automaton_t *a, AutoStore *st) {
 struct HostCache {
     std::mutex mu;
     std::map<size_t, std::vector<void *>> free_blocks;
-    static constexpr size_t kMaxPinned = (size_t)4 << 30;      // larger blocks are plain malloc
+    static constexpr size_t kMaxPinned = (size_t)4 << 30;      // larger blocks are plain malloc, filled through pinned staging
     void *acquire(size_t bytes, bool &pinned) {
         pinned = bytes <= kMaxPinned;
         if (!pinned) {
@@ -1134,17 +1134,101 @@ struct stcsp_session {
 
     // Single-rank finish: edges grouped by source and the fail rule applied ON THE DEVICE, then one copy into pinned
     // host memory.  State ids are already dense (world == 1: global id == local index, root == 0).
+    // Device -> host.  Pinned destinations take one asynchronous copy; large pageable ones are filled through two pinned
+    // staging chunks so that the PCIe transfer of one chunk overlaps the host memcpy of the previous one (pinning
+    // gigabytes costs seconds, an unstaged pageable copy runs at ~2.5 GB/s).  Returns with the stream drained if staged.
+    void download(const HostBlock &dst, const void *src, size_t bytes) {
+        if (bytes == 0) return;
+        if (dst.pinned || bytes <= ((size_t)4 << 20)) {
+            CK(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyDeviceToHost, stream));
+            return;
+        }
+        const size_t CH = (size_t)32 << 20;
+        HostBlock stage[2];
+        stage[0].alloc(CH);
+        stage[1].alloc(CH);
+        cudaEvent_t done[2] = {evk0, evk1};
+        size_t off[2] = {0, 0}, len[2] = {0, 0};
+        size_t pos = 0;
+        for (int i = 0; pos < bytes || len[i & 1] || len[(i + 1) & 1]; i++) {
+            const int slot = i & 1;
+            if (len[slot]) {                            // the chunk issued two steps ago has landed: move it out
+                CK(cudaEventSynchronize(done[slot]));
+                memcpy((char *)dst.p + off[slot], stage[slot].p, len[slot]);
+                len[slot] = 0;
+            }
+            if (pos < bytes) {
+                const size_t n = std::min(CH, bytes - pos);
+                CK(cudaMemcpyAsync(stage[slot].p, (const char *)src + pos, n, cudaMemcpyDeviceToHost, stream));
+                CK(cudaEventRecord(done[slot], stream));
+                off[slot] = pos;
+                len[slot] = n;
+                pos += n;
+            }
+        }
+    }
+
+    // Copy this rank's part (state keys, edges with global ids) into caller-provided device memory.
+    void export_part(int32_t *keys, int32_t *src, int32_t *dst, int32_t *label) {
+        const int KW = dm.key_words, V = dm.V;
+        if (n_states) CK(cudaMemcpyAsync(keys, state_key.p, (size_t)n_states * KW * 4, cudaMemcpyDeviceToDevice, stream));
+        if (n_edges) {
+            CK(cudaMemcpyAsync(src, edge_src.p, (size_t)n_edges * 4, cudaMemcpyDeviceToDevice, stream));
+            CK(cudaMemcpyAsync(dst, edge_dst.p, (size_t)n_edges * 4, cudaMemcpyDeviceToDevice, stream));
+            CK(cudaMemcpyAsync(label, edge_label.p, (size_t)n_edges * V * 4, cudaMemcpyDeviceToDevice, stream));
+        }
+        CK(cudaStreamSynchronize(stream));
+    }
+
+    // Rank 0: all ranks' parts, concatenated in rank order in device memory, become the final automaton here.
+    void finish_merged(int32_t W, const int64_t *ns_r, const int64_t *ne_r, const int32_t *keys, int32_t *src, int32_t *dst,
+                       int32_t *label, const int64_t *extra, bool trim, stcsp_automaton_t *out) {
+        if (W < 1 || W > kMaxWorld) throw Failure(STCSP_ERR_INVALID, "finish_merged: bad world size");
+        long long ns = 0, ne = 0, counts[kMaxWorld] = {0};
+        for (int r = 0; r < W; r++) { counts[r] = ns_r[r]; ns += ns_r[r]; ne += ne_r[r]; }
+        if (counts[0] < 1) throw Failure(STCSP_ERR_INVALID, "finish_merged: rank 0 does not hold the root state");
+        DBuf<int32_t> dense_keys;
+        dense_keys.reserve((size_t)ns * dm.key_words + 1, 0, stream);
+        launch_place_keys(keys, dense_keys.p, ns, dm.key_words, W, counts, sm_count, stream);
+        launch_remap_ids(src, ne, W, counts, sm_count, stream);
+        launch_remap_ids(dst, ne, W, counts, sm_count, stream);
+        CK(cudaGetLastError());
+        t_launches += 3;
+        if (extra) {            // the other ranks' search statistics (same order as stcsp_session_counts)
+            t_nodes += extra[0]; t_fails += extra[1]; t_leaves += extra[2]; t_dominance += extra[3]; t_tuples += extra[4];
+            t_revisions += extra[5]; t_launches += extra[6]; t_expand_launches += extra[7]; h2d += extra[8]; d2h += extra[9];
+        }
+        const long long my_states = n_states, my_edges = n_edges;
+        n_states = ns;          // fill_header reports the merged automaton
+        n_edges = ne;
+        try {
+            finish_arrays(out, trim, dense_keys.p, ns, src, dst, label, ne);
+        } catch (...) {
+            n_states = my_states;
+            n_edges = my_edges;
+            throw;
+        }
+        n_states = my_states;
+        n_edges = my_edges;
+    }
+
     void finish_device(stcsp_automaton_t *out, bool trim) {
+        finish_arrays(out, trim, state_key.p, n_states, edge_src.p, edge_dst.p, edge_label.p, n_edges);
+    }
+
+    // Group the edges (src, dst, label)[0 .. ne) by source, apply the fail rule, and copy states + edges to pinned host
+    // memory.  State ids must be dense (0 .. ns); the edge arrays are scratch afterwards.
+    void finish_arrays(stcsp_automaton_t *out, bool trim, const int32_t *keys_p, long long ns, int32_t *esrc_p, int32_t *edst_p,
+                       int32_t *elabel_p, long long ne) {
         memset(out, 0, sizeof *out);
         const int KW = dm.key_words, V = dm.V, SL = dm.sig_len;
-        const long long ns = n_states, ne = n_edges;
         DBuf<int32_t> deg, first, fill, s_src, s_dst, s_label, outdeg, flags, rows_cset, rows_sig;
         DBuf<uint8_t> failed, alive, scan_tmp;
         struct Release {        // return the scratch blocks only after the stream drained
             cudaStream_t st;
             ~Release() { cudaStreamSynchronize(st); }
         };
-        int32_t *f_src = edge_src.p, *f_dst = edge_dst.p, *f_label = edge_label.p;
+        int32_t *f_src = esrc_p, *f_dst = edst_p, *f_label = elabel_p;
         long long n_final = ne;
         // small automata: one single-CTA launch does all of it and the host learns afterwards whether any edge died
         const bool small = ns <= 16384 && ne <= 4096;
@@ -1160,8 +1244,8 @@ struct stcsp_session {
             s_label.reserve((size_t)ne * V + 1, 0, stream);
             rows_cset.reserve((size_t)ns + 1, 0, stream);
             rows_sig.reserve((size_t)ns * std::max(SL, 1) + 1, 0, stream);
-            launch_finish_small(edge_src.p, edge_dst.p, edge_label.p, (int)ne, V, (int)ns, deg.p, first.p, fill.p, outdeg.p,
-                                failed.p, alive.p, s_src.p, s_dst.p, s_label.p, state_key.p, KW, rows_cset.p, rows_sig.p,
+            launch_finish_small(esrc_p, edst_p, elabel_p, (int)ne, V, (int)ns, deg.p, first.p, fill.p, outdeg.p,
+                                failed.p, alive.p, s_src.p, s_dst.p, s_label.p, keys_p, KW, rows_cset.p, rows_sig.p,
                                 trim ? 1 : 0, reinterpret_cast<int32_t *>(counters.p + C_OUT), stream);
             CK(cudaGetLastError());
             f_src = s_src.p; f_dst = s_dst.p; f_label = s_label.p;
@@ -1174,7 +1258,7 @@ struct stcsp_session {
             CK(cudaMemsetAsync(deg.p, 0, ((size_t)ns + 1) * 4, stream));
             CK(cudaMemsetAsync(fill.p, 0, ((size_t)ns + 1) * 4, stream));
             CK(cudaMemsetAsync(failed.p, 0, (size_t)ns + 1, stream));
-            launch_edge_count(edge_src.p, ne, deg.p, sm_count, stream);
+            launch_edge_count(esrc_p, ne, deg.p, sm_count, stream);
             const size_t tmp = scan_temp_bytes(std::max<long long>(ns + 1, ne + 1));
             scan_tmp.reserve(tmp + 16, 0, stream);
             launch_exclusive_scan(scan_tmp.p, tmp, deg.p, first.p, ns + 1, stream);
@@ -1182,7 +1266,7 @@ struct stcsp_session {
                 s_src.reserve((size_t)ne, 0, stream);
                 s_dst.reserve((size_t)ne, 0, stream);
                 s_label.reserve((size_t)ne * V, 0, stream);
-                launch_edge_scatter(edge_src.p, edge_dst.p, edge_label.p, ne, V, first.p, fill.p, s_src.p, s_dst.p, s_label.p,
+                launch_edge_scatter(esrc_p, edst_p, elabel_p, ne, V, first.p, fill.p, s_src.p, s_dst.p, s_label.p,
                                     sm_count, stream);
                 f_src = s_src.p; f_dst = s_dst.p; f_label = s_label.p;
                 t_launches += 3;
@@ -1212,16 +1296,16 @@ struct stcsp_session {
                     const size_t tmp2 = scan_temp_bytes(ne + 1);
                     scan_tmp.reserve(tmp2 + 16, 0, stream);
                     launch_exclusive_scan(scan_tmp.p, tmp2, flags.p, flags.p, ne, stream);
-                    launch_edge_compact(f_src, f_dst, f_label, alive.p, flags.p, ne, V, edge_src.p, edge_dst.p, edge_label.p,
+                    launch_edge_compact(f_src, f_dst, f_label, alive.p, flags.p, ne, V, esrc_p, edst_p, elabel_p,
                                         sm_count, stream);
-                    f_src = edge_src.p; f_dst = edge_dst.p; f_label = edge_label.p;
+                    f_src = esrc_p; f_dst = edst_p; f_label = elabel_p;
                     n_final = ne - dead;
                     t_launches += 3;
                 }
             }
             rows_cset.reserve((size_t)ns + 1, 0, stream);
             rows_sig.reserve((size_t)ns * std::max(SL, 1) + 1, 0, stream);
-            launch_state_rows(state_key.p, ns, KW, rows_cset.p, rows_sig.p, sm_count, stream);
+            launch_state_rows(keys_p, ns, KW, rows_cset.p, rows_sig.p, sm_count, stream);
             t_launches++;
             CK(cudaGetLastError());
         }
@@ -1241,14 +1325,14 @@ struct stcsp_session {
             st->edge_label.alloc((size_t)n_final * V * 4);
             if (!model->sets.sig_vars().empty()) memcpy(st->sig_vars.p, model->sets.sig_vars().data(), model->sets.sig_vars().size() * 4);
             if (ns) {
-                if (SL) CK(cudaMemcpyAsync(st->state_sig.p, rows_sig.p, (size_t)ns * SL * 4, cudaMemcpyDeviceToHost, stream));
-                CK(cudaMemcpyAsync(st->state_cset.p, rows_cset.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, stream));
-                CK(cudaMemcpyAsync(st->state_failed.p, failed.p, (size_t)ns, cudaMemcpyDeviceToHost, stream));
+                if (SL) download(st->state_sig, rows_sig.p, (size_t)ns * SL * 4);
+                download(st->state_cset, rows_cset.p, (size_t)ns * 4);
+                download(st->state_failed, failed.p, (size_t)ns);
             }
             if (n_final) {
-                CK(cudaMemcpyAsync(st->edge_src.p, f_src, (size_t)n_final * 4, cudaMemcpyDeviceToHost, stream));
-                CK(cudaMemcpyAsync(st->edge_dst.p, f_dst, (size_t)n_final * 4, cudaMemcpyDeviceToHost, stream));
-                CK(cudaMemcpyAsync(st->edge_label.p, f_label, (size_t)n_final * V * 4, cudaMemcpyDeviceToHost, stream));
+                download(st->edge_src, f_src, (size_t)n_final * 4);
+                download(st->edge_dst, f_dst, (size_t)n_final * 4);
+                download(st->edge_label, f_label, (size_t)n_final * V * 4);
             }
             if (small) CK(cudaMemcpyAsync(h_counters, counters.p + C_OUT, 8, cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
@@ -1261,15 +1345,15 @@ struct stcsp_session {
                 const size_t tmp2 = scan_temp_bytes(ne + 1);
                 scan_tmp.reserve(tmp2 + 16, 0, stream);
                 launch_exclusive_scan(scan_tmp.p, tmp2, flags.p, flags.p, ne, stream);
-                launch_edge_compact(f_src, f_dst, f_label, alive.p, flags.p, ne, V, edge_src.p, edge_dst.p, edge_label.p, sm_count,
+                launch_edge_compact(f_src, f_dst, f_label, alive.p, flags.p, ne, V, esrc_p, edst_p, elabel_p, sm_count,
                                     stream);
                 CK(cudaGetLastError());
                 n_final = ne - dead;
                 t_launches += 3;
                 if (n_final) {
-                    CK(cudaMemcpyAsync(st->edge_src.p, edge_src.p, (size_t)n_final * 4, cudaMemcpyDeviceToHost, stream));
-                    CK(cudaMemcpyAsync(st->edge_dst.p, edge_dst.p, (size_t)n_final * 4, cudaMemcpyDeviceToHost, stream));
-                    CK(cudaMemcpyAsync(st->edge_label.p, edge_label.p, (size_t)n_final * V * 4, cudaMemcpyDeviceToHost, stream));
+                    download(st->edge_src, esrc_p, (size_t)n_final * 4);
+                    download(st->edge_dst, edst_p, (size_t)n_final * 4);
+                    download(st->edge_label, elabel_p, (size_t)n_final * V * 4);
                 }
                 CK(cudaStreamSynchronize(stream));
             }
@@ -1350,6 +1434,7 @@ void stcsp_session_destroy(stcsp_session_t *s) { delete s; }
 
 int32_t stcsp_session_record_words(const stcsp_session_t *s) { return s->dm.rec_words; }
 int32_t stcsp_session_request_words(const stcsp_session_t *s) { return 1 + s->dm.V; }
+int32_t stcsp_session_key_words(const stcsp_session_t *s) { return s->dm.key_words; }
 
 int stcsp_session_expand(stcsp_session_t *s, int64_t *n_leaves, int64_t *n_pending) {
     return guarded([&] { s->expand(n_leaves, n_pending); });
@@ -1374,6 +1459,27 @@ int stcsp_session_ingest(stcsp_session_t *s, const int32_t *inbox, int64_t n_rec
 
 int stcsp_session_finish(stcsp_session_t *s, stcsp_automaton_t *part) {
     return guarded([&] { s->finish(part); });
+}
+
+int stcsp_session_counts(stcsp_session_t *s, int64_t *n_states, int64_t *n_edges, int64_t *stats) {
+    *n_states = s->n_states;
+    *n_edges = s->n_edges;
+    if (stats) {
+        const int64_t v[10] = {s->t_nodes, s->t_fails, s->t_leaves, s->t_dominance, s->t_tuples, s->t_revisions, s->t_launches,
+                               s->t_expand_launches, s->h2d, s->d2h};
+        memcpy(stats, v, sizeof v);
+    }
+    return STCSP_OK;
+}
+
+int stcsp_session_export(stcsp_session_t *s, int32_t *keys, int32_t *src, int32_t *dst, int32_t *label) {
+    return guarded([&] { s->export_part(keys, src, dst, label); });
+}
+
+int stcsp_session_finish_merged(stcsp_session_t *s, int32_t world_size, const int64_t *n_states, const int64_t *n_edges,
+                                const int32_t *keys, int32_t *src, int32_t *dst, int32_t *label, const int64_t *extra_stats,
+                                int32_t trim, stcsp_automaton_t *out) {
+    return guarded([&] { s->finish_merged(world_size, n_states, n_edges, keys, src, dst, label, extra_stats, trim != 0, out); });
 }
 
 int stcsp_automaton_assemble(const stcsp_automaton_t *parts, int32_t n_parts, stcsp_automaton_t *out) {

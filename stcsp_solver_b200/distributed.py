@@ -95,7 +95,7 @@ class WaveExchange:
 
 
 # A wave this wide keeps one B200 busy; below it, sharding only adds two collectives per wave.
-SINGLE_GPU_FRONTIER = 32768
+SINGLE_GPU_FRONTIER = 262144
 
 
 def solve_distributed(model: binding.Model, options: Optional[binding.Options] = None, group=None,
@@ -179,12 +179,72 @@ def solve_distributed(model: binding.Model, options: Optional[binding.Options] =
                 frontier = session.ingest(None, 0)
             stats["waves"] += 1
             stats["records_sent"] += int(send_counts.sum())
-        part = session.finish()
-        parts = ex.gather_arrays(binding.part_to_arrays(part))
+        automaton = _merge_on_rank0(session, ex, model, trim)
     finally:
         session.close()
-    if ex.rank != 0:
-        return None
-    automaton = binding.assemble(parts, trim=trim)
-    automaton.exchange_stats = stats
+    if automaton is not None:
+        automaton.exchange_stats = stats
     return automaton
+
+
+def _merge_on_rank0(session, ex, model, trim):
+    """Parts travel device-to-device (NCCL send / recv) into rank 0's GPU, which renumbers, groups, trims and downloads."""
+    import os
+    import time
+    trace = os.environ.get("STCSP_TRACE") == "1"
+    t0 = time.perf_counter()
+
+    def lap(what):
+        if trace and ex.rank == 0:
+            torch.cuda.synchronize()
+            print("[merge] %s %.2f ms" % (what, (time.perf_counter() - t0) * 1e3), flush=True)
+    world, rank = ex.world, ex.rank
+    ns, ne, st = session.counts()
+    head = torch.zeros(12, dtype=torch.int64, device=ex.device)
+    head[0], head[1] = ns, ne
+    head[2:] = torch.as_tensor(st)
+    heads = torch.zeros((world, 12), dtype=torch.int64, device=ex.device)
+    dist.all_gather_into_tensor(heads.view(-1), head, group=ex.group)
+    h = heads.cpu().numpy()
+    n_vars = model.n_vars
+    key_words = session.key_words
+    all_ns, all_ne = h[:, 0], h[:, 1]
+    if rank == 0:
+        tot_s, tot_e = int(all_ns.sum()), int(all_ne.sum())
+        keys = torch.empty((max(tot_s, 1), key_words), dtype=torch.int32, device=ex.device)
+        src = torch.empty(max(tot_e, 1), dtype=torch.int32, device=ex.device)
+        dst = torch.empty(max(tot_e, 1), dtype=torch.int32, device=ex.device)
+        label = torch.empty((max(tot_e, 1), n_vars), dtype=torch.int32, device=ex.device)
+        lap("alloc")
+        session.export(keys.data_ptr(), src.data_ptr(), dst.data_ptr(), label.data_ptr())
+        lap("export")
+        s_off, e_off = int(all_ns[0]), int(all_ne[0])
+        for r in range(1, world):
+            s_n, e_n = int(all_ns[r]), int(all_ne[r])
+            if s_n:
+                dist.recv(keys[s_off:s_off + s_n], src=r, group=ex.group)
+            if e_n:
+                dist.recv(src[e_off:e_off + e_n], src=r, group=ex.group)
+                dist.recv(dst[e_off:e_off + e_n], src=r, group=ex.group)
+                dist.recv(label[e_off:e_off + e_n], src=r, group=ex.group)
+            s_off += s_n
+            e_off += e_n
+        torch.cuda.current_stream().synchronize()
+        lap("recv")
+        extra = h[1:, 2:].sum(axis=0) if world > 1 else np.zeros(10, dtype=np.int64)
+        out = session.finish_merged(all_ns, all_ne, keys.data_ptr(), src.data_ptr(), dst.data_ptr(), label.data_ptr(), extra, trim)
+        lap("finish_merged")
+        return out
+    keys = torch.empty((max(ns, 1), key_words), dtype=torch.int32, device=ex.device)
+    src = torch.empty(max(ne, 1), dtype=torch.int32, device=ex.device)
+    dst = torch.empty(max(ne, 1), dtype=torch.int32, device=ex.device)
+    label = torch.empty((max(ne, 1), n_vars), dtype=torch.int32, device=ex.device)
+    session.export(keys.data_ptr(), src.data_ptr(), dst.data_ptr(), label.data_ptr())
+    if ns:
+        dist.send(keys[:ns], dst=0, group=ex.group)
+    if ne:
+        dist.send(src[:ne], dst=0, group=ex.group)
+        dist.send(dst[:ne], dst=0, group=ex.group)
+        dist.send(label[:ne], dst=0, group=ex.group)
+    torch.cuda.current_stream().synchronize()
+    return None

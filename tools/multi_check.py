@@ -17,7 +17,9 @@ for name in names:
     g = json.load(open(path)) if os.path.exists(path) else None
     text = g["model"] if g and "model" in g else instances.by_name(name)
     model = binding.Model(text)
+    a = None
     for rep in range(2):
+        a = None                # release the previous automaton (its pinned blocks go back to the cache)
         dist.barrier(); torch.cuda.synchronize(); t0 = time.time()
         a = distributed.solve_distributed(model, adaptive=os.environ.get("ADAPTIVE", "1") == "1")
         torch.cuda.synchronize(); dt = time.time() - t0
