@@ -374,9 +374,10 @@ def part_to_arrays(a: Automaton) -> dict:
     head = np.array([c.n_vars, c.n_sig_vars, c.n_until, c.n_until_vars, c.sig_len, c.root_final, c.n_states, c.n_edges]
                     + [getattr(c, k) for k in _PART_STATS], dtype=np.int64)
     times = np.array([getattr(c, k) for k in _PART_TIMES], dtype=np.float64)
-    return {"head": head, "times": times, "sig_vars": a.sig_vars, "state_sig": a.state_sig.reshape(-1),
-            "state_cset": a.state_cset, "edge_src": a.edge_src, "edge_dst": a.edge_dst,
-            "edge_label": a.edge_label.reshape(-1)}
+    # copies: the dict outlives the automaton whose memory the arrays of `a` are views of
+    return {"head": head, "times": times, "sig_vars": np.array(a.sig_vars), "state_sig": np.array(a.state_sig).reshape(-1),
+            "state_cset": np.array(a.state_cset), "edge_src": np.array(a.edge_src), "edge_dst": np.array(a.edge_dst),
+            "edge_label": np.array(a.edge_label).reshape(-1)}
 
 
 def assemble(parts: Sequence[dict], trim: bool = True) -> Automaton:

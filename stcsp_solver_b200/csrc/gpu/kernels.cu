@@ -957,6 +957,13 @@ __host__ __device__ inline uint32_t cap_hash(int cid, const int32_t *vals, int n
     return cap_hash_end(h);
 }
 
+// Rank that owns the successor state of a ROUTED record.  The root (constraint set 0, empty signature) was created on
+// rank 0 before the search started, so a stateless model's only key must map there too.
+__device__ __forceinline__ int leaf_owner(const DevModel &M, int ncid, uint32_t h) {
+    if (M.world <= 1 || (M.sig_len == 0 && ncid == 0)) return 0;
+    return (int)(owner_hash(h) % (uint32_t)M.world);
+}
+
 // word j of the state key of the successor described by a routed record
 __device__ __forceinline__ int key_word(const DevModel &M, const int32_t *rec, int ncid, int nexp, int j) {
     if (j == 0) return ncid;
@@ -1016,8 +1023,7 @@ __device__ __forceinline__ bool route_leaf(const DevModel &M, const RouteArgs &P
         rec[1] = ncid;
         rec[2] = nexp;
         rec[3] = (int32_t)h;
-        const int owner = M.world > 1 ? (int)(owner_hash(h) % (uint32_t)M.world) : 0;
-        atomicAdd(&P.counters[C_OWNER0 + owner], 1ull);
+        atomicAdd(&P.counters[C_OWNER0 + leaf_owner(M, ncid, h)], 1ull);
     }
     __syncwarp();
     return true;
@@ -1046,7 +1052,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const DevModel M, const in
     const int RW = M.rec_words;
     for (long long li = warp_id; li < n; li += total_warps) {
         const int32_t *rec = leaves + li * RW;
-        const int owner = (int)(owner_hash((uint32_t)rec[3]) % (uint32_t)M.world);
+        const int owner = leaf_owner(M, rec[1], (uint32_t)rec[3]);
         unsigned long long pos = 0;
         if (lane == 0) pos = atomicAdd(&fill[owner], 1ull);
         pos = __shfl_sync(0xffffffffu, pos, 0);

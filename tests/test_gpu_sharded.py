@@ -1,0 +1,91 @@
+"""The sharded (multi-rank) search on ONE GPU: the sessions of all ranks live in this process and the test plays the
+part of the collectives (hash-owner routing of leaf records, the union of resolve requests, the gather of parts).
+Every session call completes before the next one starts, so no kernel ever waits for another rank.
+Covers stcsp_session_{expand,pending,resolve,outbox,ingest,counts,export,finish_merged} and the finish+assemble path."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDENS, golden_text
+from stcsp_solver_b200 import binding
+
+pytestmark = pytest.mark.gpu
+
+
+def solve_sharded_on_one_gpu(model, world, merge="device"):
+    dev = torch.device("cuda", 0)
+    opts = binding.default_options(device=0)
+    sessions = [binding.Session(model, opts, r, world) for r in range(world)]
+    words = sessions[0].record_words
+    frontier = [1] + [0] * (world - 1)
+    waves = 0
+    try:
+        while sum(frontier) > 0:
+            leaves, pend = [], []
+            for s in sessions:
+                n_leaves, n_pending = s.expand()
+                leaves.append(n_leaves)
+                pend.append(s.pending(n_pending))
+            if sum(p.shape[0] for p in pend) > 0:
+                union = np.unique(np.concatenate(pend, axis=0), axis=0)        # same sorted list for every rank
+                for s in sessions:
+                    s.resolve(union)
+            outboxes, counts = [], []
+            for s, n in zip(sessions, leaves):
+                box = torch.empty((max(n, 1), words), dtype=torch.int32, device=dev)
+                counts.append(s.outbox(box.data_ptr(), n) if n else np.zeros(world, dtype=np.int64))
+                outboxes.append(box)
+            for q, s in enumerate(sessions):
+                chunks = []
+                for r in range(world):
+                    start = int(counts[r][:q].sum())
+                    chunks.append(outboxes[r][start:start + int(counts[r][q])])
+                inbox = torch.cat(chunks, dim=0).contiguous()
+                torch.cuda.synchronize()
+                frontier[q] = s.ingest(inbox.data_ptr() if inbox.shape[0] else None, int(inbox.shape[0]))
+            waves += 1
+            assert waves < 10000
+        if merge == "host":
+            parts = [binding.part_to_arrays(s.finish()) for s in sessions]
+            return binding.assemble(parts, trim=True)
+        cnt = [s.counts() for s in sessions]
+        ns = [c[0] for c in cnt]
+        ne = [c[1] for c in cnt]
+        kw, nv = sessions[0].key_words, model.n_vars
+        keys = torch.empty((max(sum(ns), 1), kw), dtype=torch.int32, device=dev)
+        src = torch.empty(max(sum(ne), 1), dtype=torch.int32, device=dev)
+        dst = torch.empty(max(sum(ne), 1), dtype=torch.int32, device=dev)
+        label = torch.empty((max(sum(ne), 1), nv), dtype=torch.int32, device=dev)
+        so = eo = 0
+        for s, a, b in zip(sessions, ns, ne):
+            s.export(keys[so:].data_ptr(), src[eo:].data_ptr(), dst[eo:].data_ptr(), label[eo:].data_ptr())
+            so += a
+            eo += b
+        extra = np.sum([c[2] for c in cnt[1:]], axis=0) if world > 1 else np.zeros(10, dtype=np.int64)
+        return sessions[0].finish_merged(ns, ne, keys.data_ptr(), src.data_ptr(), dst.data_ptr(), label.data_ptr(), extra, True)
+    finally:
+        for s in sessions:
+            s.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("name", ["juggling_b4_f5_nosym", "juggling_b5_f6", "digitinvader3", "partialorder_11",
+                                  "probe_first_capture", "probe_at2", "probe_until_two", "probe_dead_branch", "probe_unsat_next",
+                                  "probe_stateless"])
+def test_sharded_search_matches_reference(name, world):
+    g = GOLDENS[name]
+    model = binding.Model(golden_text(g))
+    automaton = solve_sharded_on_one_gpu(model, world)
+    sol = binding.Solution(model, automaton)
+    assert (sol.n_states, sol.n_edges) == (g["states"], g["edges"])
+    assert sol.canonical_sha256() == g["sha256"]
+
+
+@pytest.mark.parametrize("name", ["juggling_b4_f6", "probe_dead_branch", "partialorder_10"])
+def test_host_assembly_equals_device_merge(name):
+    g = GOLDENS[name]
+    model = binding.Model(golden_text(g))
+    a = binding.Solution(model, solve_sharded_on_one_gpu(model, 4, merge="host"))
+    b = binding.Solution(model, solve_sharded_on_one_gpu(model, 4, merge="device"))
+    assert a.canonical_text() == b.canonical_text()
+    assert a.canonical_sha256() == g["sha256"]
