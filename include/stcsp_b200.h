@@ -176,6 +176,10 @@ void stcsp_automaton_free(stcsp_automaton_t *a);
  * src/util.cpp:161-178; a library must not exit). */
 const char *stcsp_last_error(void);
 
+/* The library keeps device blocks, pinned host blocks, streams and the compiled form of recently solved models alive
+ * between calls (a solve in steady state allocates nothing).  This gives the memory back (idle sessions only). */
+void stcsp_gpu_release_caches(void);
+
 /* Number of usable CUDA devices (0 if none); never fails. */
 int stcsp_gpu_device_count(void);
 

@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         L.stcsp_solution_canonical.argtypes = [C.POINTER(Problem), C.POINTER(SolutionC)]
         L.stcsp_solution_canonical.restype = C.c_void_p
         L.stcsp_gpu_device_count.restype = C.c_int
+        L.stcsp_gpu_release_caches.restype = None
         L.stcsp_session_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.c_int32, C.c_int32,
                                            C.POINTER(C.c_void_p)]
         L.stcsp_session_destroy.argtypes = [C.c_void_p]
@@ -276,6 +277,11 @@ def solve(model: Model, options: Optional[Options] = None) -> Automaton:
     opts = options if options is not None else default_options()
     _check(lib().stcsp_gpu_solve(model.problem, C.byref(opts), C.byref(out)))
     return Automaton(out, lib().stcsp_automaton_free)
+
+
+def release_caches() -> None:
+    """Give the library's cached device / pinned memory and resident models back (stcsp_gpu_release_caches)."""
+    lib().stcsp_gpu_release_caches()
 
 
 def solve_text(text: str, flags: Sequence[str] = (), options: Optional[Options] = None):

@@ -1404,6 +1404,30 @@ int guarded(F &&body) {
 
 extern "C" {
 
+void stcsp_gpu_release_caches(void) {
+    // resident models first (their blocks return to the block cache), then the blocks themselves
+    {
+        ModelCache &mc = model_cache();
+        std::lock_guard<std::mutex> g(mc.mu);
+        mc.entries.clear();
+        mc.order.clear();
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    for (int d = 0; d < ndev; d++) device_cache().trim(d);
+    {
+        HostCache &hc = host_cache();
+        std::lock_guard<std::mutex> g(hc.mu);
+        for (auto &kv : hc.free_blocks) {
+            for (void *p : kv.second) cudaFreeHost(p);
+            kv.second.clear();
+        }
+    }
+}
+
 int stcsp_gpu_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {

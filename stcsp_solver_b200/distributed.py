@@ -116,6 +116,7 @@ def solve_distributed(model: binding.Model, options: Optional[binding.Options] =
         # only if a wave outgrows it do all ranks start the sharded search (the bounded attempt costs a few waves).
         verdict = torch.zeros(1, dtype=torch.int64, device=ex.device)
         automaton = None
+        failure = None
         if ex.rank == 0:
             saved = opts.max_frontier_nodes
             opts.max_frontier_nodes = SINGLE_GPU_FRONTIER
@@ -126,10 +127,13 @@ def solve_distributed(model: binding.Model, options: Optional[binding.Options] =
                 verdict[0] = 1
             except binding.StcspError as e:
                 if e.status != binding.ERR_CAPACITY:
-                    raise
+                    failure = e
+                    verdict[0] = -1                     # tell the waiting ranks before raising
             finally:
                 opts.max_frontier_nodes = saved
         dist.broadcast(verdict, src=0, group=ex.group)
+        if int(verdict.item()) == -1:
+            raise failure if failure is not None else RuntimeError("rank 0 failed in the single-GPU attempt")
         if int(verdict.item()) == 1:
             if automaton is not None:
                 automaton.exchange_stats = {"waves": 0, "records_sent": 0, "single_gpu": True}

@@ -132,6 +132,24 @@ def test_trim_is_idempotent_and_edges_grouped():
     assert np.all(np.diff(before[1]) >= 0)
 
 
+def test_release_caches_then_solve_again():
+    g = GOLDENS["juggling_b4_f5_nosym"]
+    _, _, s1 = run_gpu(golden_text(g))
+    binding.release_caches()
+    _, _, s2 = run_gpu(golden_text(g))
+    assert s1.canonical_sha256() == s2.canonical_sha256() == g["sha256"]
+
+
+def test_frontier_limit_reports_capacity():
+    model = binding.Model(instances.by_name("partialorder_10"))
+    with pytest.raises(binding.StcspError) as e:
+        binding.solve(model, binding.default_options(max_frontier_nodes=16))
+    assert e.value.status == binding.ERR_CAPACITY
+    # and the library is still usable afterwards
+    _, _, sol = run_gpu(instances.by_name("partialorder_10"))
+    assert sol.canonical_sha256() == GOLDENS["partialorder_10"]["sha256"]
+
+
 def test_no_device_option_errors_loudly():
     model = binding.Model(instances.by_name("juggling_b4_f4"))
     with pytest.raises(binding.StcspError) as e:
