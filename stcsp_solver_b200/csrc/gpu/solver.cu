@@ -1231,7 +1231,7 @@ struct stcsp_session {
         int32_t *f_src = esrc_p, *f_dst = edst_p, *f_label = elabel_p;
         long long n_final = ne;
         // small automata: one single-CTA launch does all of it and the host learns afterwards whether any edge died
-        const bool small = ns <= 16384 && ne <= 4096;
+        const bool small = ns <= 2048 && ne <= 512;    // (one CTA is slower than six launches beyond that)
         if (small) {
             deg.reserve((size_t)ns + 1, 0, stream);
             first.reserve((size_t)ns + 1, 0, stream);
