@@ -299,8 +299,13 @@ struct Oracle {
             default: return 0;
         }
     }
+    struct TimeUp {};
     bool validate(const Con &c) {                         /* src/solveralgorithm.cpp:428-431 */
         st.validates++;
+        if (deadline > 0 && (st.validates & 0xFFFFF) == 0) {      /* a single propagation may run for hours */
+            double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+            if (now > deadline) { timed_out = true; throw TimeUp(); }
+        }
         bool valid = true;
         return eval(c.root.get(), valid) != 0;
     }
@@ -568,8 +573,12 @@ struct Oracle {
         std::vector<int> expire;
         for (size_t c = 0; c < q0.cons.size(); c++)
             if (q0.cons[c].kind == K_UNTIL) expire.push_back(0);
-        if (gac(seen[0], expire, d)) solveRe(0, 0, expire, d, 1);
-        else numFails++;
+        try {
+            if (gac(seen[0], expire, d)) solveRe(0, 0, expire, d, 1);
+            else numFails++;
+        } catch (const TimeUp &) {
+            timed_out = true;
+        }
     }
 };
 

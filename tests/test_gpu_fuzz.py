@@ -1,0 +1,34 @@
+"""Differential test: random models, CUDA path (C ABI) vs the oracle -- canonical automata must be identical.
+Both look-ahead modes and the step-wise path take part, so every propagation variant sees every model."""
+import pytest
+
+import _oracle
+from model_fuzz import random_model
+from stcsp_solver_b200 import binding
+
+pytestmark = pytest.mark.gpu
+
+SEEDS = list(range(0, 700))     # 0-299: grammar coverage (mostly tiny automata); 300-699: models with real dynamics
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_random_model_matches_oracle(seed):
+    text = random_model(seed)
+    try:
+        model = binding.Model(text)
+    except binding.StcspError:
+        pytest.skip("rejected by the front end")
+    oracle_automaton, _ = _oracle.solve(model, 2.0)
+    if oracle_automaton is None:
+        pytest.skip("oracle needs more than 5 s")
+    want = binding.Solution(model, oracle_automaton).canonical_text()
+    variants = [dict(), dict(lookahead=2), dict(profile_kernels=1), dict(enum_limit_now=4096, enum_limit_ahead=4096)]
+    for kw in variants[: 1 + seed % 4] if seed % 4 else variants[:1]:
+        try:
+            automaton = binding.solve(model, binding.default_options(**kw))
+        except binding.StcspError as e:
+            if e.status == binding.ERR_UNSUPPORTED:
+                pytest.skip("unsupported by the GPU path: %s" % e)
+            raise
+        got = binding.Solution(model, automaton).canonical_text()
+        assert got == want, "seed %d options %s\n%s" % (seed, kw, text)

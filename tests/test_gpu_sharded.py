@@ -89,3 +89,17 @@ def test_host_assembly_equals_device_merge(name):
     b = binding.Solution(model, solve_sharded_on_one_gpu(model, 4, merge="device"))
     assert a.canonical_text() == b.canonical_text()
     assert a.canonical_sha256() == g["sha256"]
+
+
+@pytest.mark.parametrize("seed", range(300, 380))
+def test_sharded_search_on_random_models(seed):
+    """Random models with real dynamics (tests/model_fuzz.py), 3 ranks emulated on one GPU, vs the oracle."""
+    import _oracle
+    from model_fuzz import random_model
+    model = binding.Model(random_model(seed))
+    oracle_automaton, _ = _oracle.solve(model, 2.0)
+    if oracle_automaton is None:
+        pytest.skip("oracle needs more than 2 s")
+    want = binding.Solution(model, oracle_automaton).canonical_text()
+    got = binding.Solution(model, solve_sharded_on_one_gpu(model, 3)).canonical_text()
+    assert got == want
