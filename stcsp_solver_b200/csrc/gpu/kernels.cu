@@ -169,7 +169,21 @@ struct NodeCtx {
     int lane;
     int expire;
     unsigned long long tuples;
+    unsigned long long *dbg;    // timeline of this node's propagation (one thread writes), or nullptr
+    int dbg_cap;
 };
+
+// Timeline entry (tag, time) -- only thread 0 of block 0 ever has a non-null dbg.
+__device__ __forceinline__ void dbg_stamp(unsigned long long *dbg, int cap, unsigned long long tag) {
+    if (!dbg) return;
+    const unsigned long long k = dbg[0];
+    if ((long long)(2 * k + 2) >= (long long)cap) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[1 + 2 * k] = tag;
+    dbg[2 + 2 * k] = t;
+    dbg[0] = k + 1;
+}
 
 // A domain of (var, off) shrank: every propagator watching it must run (again).
 template <bool CTA>
@@ -672,6 +686,7 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                 more = __any_sync(0xffffffffu, lane < S.n_words &&
                                                    (wm.dirty[lane] & cheap_mask(S, lane) & (held ? ~ahead[lane] : ~0u)) != 0u);
             }
+            dbg_stamp(ctx.dbg, ctx.dbg_cap, 10);           // scalar round done
             if (bad) return true;
             if (!more) break;
         }
@@ -742,6 +757,7 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                     st_rev += lane == 0;
                 }
             }
+            dbg_stamp(ctx.dbg, ctx.dbg_cap, 20 + (unsigned long long)wm.flag[1]);   // cooperative round done (20 + props)
             if (__syncthreads_or(!ok)) return true;
         }
     }
@@ -822,6 +838,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
     const long long probe = CTA ? (long long)blockIdx.x : (long long)blockIdx.x * kExpandWarps;
     const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1);
     const DevModel &Ms = *reinterpret_cast<const DevModel *>(stage_base(smem, Mg));
+    if (CTA && blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(P.dbg, P.dbg_cap, 0);     // wave entered, set staged
 
     for (long long ni = first; ni < n_in; ni += step) {
         const int32_t *src = P.in_nodes + ni * NW;
@@ -833,7 +850,9 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
         const int cid = wm.nodew[1], bvar = wm.nodew[3];
         const DevModel &M = cid == staged ? Ms : Mg;    // metadata from shared memory when this node's set is the staged one
         const DevSet S = Mg.sets[cid];
-        NodeCtx ctx{M, S, wm, reinterpret_cast<u64 *>(wm.nodew + 4), lane, wm.nodew[2], 0ull};
+        unsigned long long *dbg = (CTA && blockIdx.x == 0 && threadIdx.x == 0) ? P.dbg : nullptr;
+        NodeCtx ctx{M, S, wm, reinterpret_cast<u64 *>(wm.nodew + 4), lane, wm.nodew[2], 0ull, dbg, P.dbg_cap};
+        dbg_stamp(dbg, P.dbg_cap, 1);                   // node loaded
         u64 *dom = ctx.dom;
 
         bool empty = false;
@@ -853,6 +872,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
         if (CTA) __syncthreads(); else __syncwarp();
 
         if (!fail) fail = propagate<CTA>(ctx, gw, gtid, gthreads, st_rev, my_tuples);   // `fail` is uniform over the group
+        dbg_stamp(dbg, P.dbg_cap, 2);                   // propagated
         st_tuples += ctx.tuples;
         if (gw == 0) st_nodes++;
         if (fail) { if (gw == 0) st_fails++; continue; }
@@ -1232,6 +1252,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         ea.leaves = A.leaves;
         ea.leaf_cap = A.leaf_cap;
         ea.counters = A.counters;
+        ea.dbg = A.trace ? A.trace + 5 * A.trace_cap : nullptr;     // block 0's timeline follows the per-wave stamps
+        ea.dbg_cap = A.trace ? 4096 : 0;
         if (n_in <= 3ll * gridDim.x) expand_body<true>(M, ea, smem);
         else expand_body<false>(M, ea, smem);
         grid.sync();

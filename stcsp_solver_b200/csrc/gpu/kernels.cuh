@@ -75,6 +75,8 @@ struct ExpandArgs {
     int32_t *leaves;
     long long leaf_cap;
     unsigned long long *counters;
+    unsigned long long *dbg;    // optional timeline of block 0 (CTA mode): dbg[0] = entries used, then (tag, %globaltimer) pairs
+    int dbg_cap;
 };
 
 struct RouteArgs {

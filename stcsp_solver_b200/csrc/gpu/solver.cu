@@ -664,8 +664,8 @@ struct stcsp_session {
             DBuf<unsigned long long> trace;
             const long long trace_waves = 256;
             if (opt.verbosity > 2) {
-                trace.reserve((size_t)trace_waves * 5, 0, stream);
-                CK(cudaMemsetAsync(trace.p, 0, (size_t)trace_waves * 5 * 8, stream));
+                trace.reserve((size_t)trace_waves * 5 + 4096, 0, stream);
+                CK(cudaMemsetAsync(trace.p, 0, ((size_t)trace_waves * 5 + 4096) * 8, stream));
                 sa.trace = trace.p;
                 sa.trace_cap = trace_waves;
             }
@@ -687,8 +687,23 @@ struct stcsp_session {
                 t_expand_launches++;
             }
             if (opt.verbosity > 2) {
-                std::vector<unsigned long long> tr((size_t)trace_waves * 5);
+                std::vector<unsigned long long> tr((size_t)trace_waves * 5 + 4096);
                 CK(cudaMemcpy(tr.data(), trace.p, tr.size() * 8, cudaMemcpyDeviceToHost));
+                {
+                    // block 0's timeline in CTA mode: tags 0 wave entered, 1 node loaded, 10 scalar round, 20+n cooperative
+                    // round over n propagators, 2 node propagated
+                    const unsigned long long *d = tr.data() + trace_waves * 5;
+                    const unsigned long long cnt = std::min<unsigned long long>(d[0], 2040);
+                    std::string line;
+                    for (unsigned long long i = 0; i < cnt; i++) {
+                        const unsigned long long tag = d[1 + 2 * i], t = d[2 + 2 * i];
+                        const double dt = i ? (double)(t - d[2 * i]) / 1e3 : 0.0;
+                        char buf[64];
+                        snprintf(buf, sizeof buf, tag == 0 ? "\n[stcsp] block0: wave" : " %llu:+%.1f", tag, dt);
+                        line += buf;
+                    }
+                    fprintf(stderr, "%s\n", line.c_str());
+                }
                 for (long long w = 0; w < std::min<long long>(trace_waves, h_ctl->t_waves); w++)
                     fprintf(stderr, "[stcsp] kernel wave %lld: expand %.1f us, route %.1f us, ingest %.1f us, bookkeeping %.1f us, gap to next %.1f us\n",
                             w, (tr[w * 5 + 1] - tr[w * 5]) / 1e3, (tr[w * 5 + 2] - tr[w * 5 + 1]) / 1e3,
