@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--instance", default="juggling_b6_f6_nosym")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra workloads reported under `also`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -238,6 +239,27 @@ def main():
         a, _ = one_solve(profile=True)
         prof = (a.c.expand_ms, a.c.n_expand_launches, a.c.n_search_nodes, a.c.solve_ms)
 
+    # the other single-GPU configurations of BASELINE.json, a few steps each (context for the headline, not timed above)
+    also = []
+    if world == 1 and not args.no_also:
+        for other in ("juggling_b4_f4", "digitinvader9", "partialorder_14"):
+            if other == name:
+                continue
+            om = binding.Model(instances.by_name(other))
+            binding.solve(om)
+            dev, wall = [], []
+            for _ in range(3):
+                l2_flush(torch, scratch)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                oa = binding.solve(om)
+                wall.append(time.perf_counter() - t0)
+                dev.append(oa.c.solve_ms)
+            ost = oa.stats()
+            also.append({"workload": other, "device_ms": min(dev), "e2e_ms": min(wall) * 1e3, "states": ost["n_states"],
+                         "edges": ost["n_edges"], "search_nodes": ost["n_search_nodes"],
+                         "algorithmic_gbs": ost["algorithmic_bytes"] / (min(dev) / 1e3) / 1e9})
+
     if rank == 0:
         st = last.stats()
         steps = args.steps
@@ -291,6 +313,8 @@ def main():
             "gpu_launches": st["n_kernel_launches"] * steps,
             "clocks": clocks, "timed_region_s": region_s,
         }
+        if also:
+            line["also"] = also
         if roof:
             line["roofline"] = roof
         if cpu:
