@@ -1378,14 +1378,6 @@ __global__ void fill_kernel(int32_t *ptr, long long n, int32_t value) {
 
 uint32_t capmap_hash(int cid, const int32_t *vals, int n) { return cap_hash(cid, vals, n); }
 
-uint32_t state_key_hash(const int32_t *key, int key_words) {
-    uint32_t h = 0;
-    for (int j = 0; j < key_words; j++) h ^= key_word_hash(key[j], j);
-    return mix32(h);
-}
-
-int32_t owner_of_hash(uint32_t h, int32_t world) { return world > 1 ? (int32_t)(owner_hash(h) % (uint32_t)world) : 0; }
-
 size_t expand_smem_bytes(const DevModel &m) {
     return (node_bytes(m) + scratch_bytes(m)) * kExpandWarps + align8(sizeof(DevModel)) + align8((size_t)m.stage_bytes);
 }

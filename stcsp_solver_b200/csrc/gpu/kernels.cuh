@@ -195,7 +195,5 @@ void launch_state_rows(const int32_t *keys, long long n_states, int KW, int32_t 
                        cudaStream_t stream);
 
 uint32_t capmap_hash(int cid, const int32_t *vals, int n);
-uint32_t state_key_hash(const int32_t *key, int key_words);
-int32_t owner_of_hash(uint32_t h, int32_t world);
 
 }  // namespace stcsp
