@@ -1240,6 +1240,86 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             ctl->status = st;
         }
         grid.sync();
+        if (ctl->status == SEARCH_DONE) {
+            // ---- small automaton: group the edges by source and apply the fail rule right here (no further launches)
+            const long long ns = (long long)cnt[C_STATES], ne = (long long)cnt[C_EDGES];
+            const FinishArgs &F = A.fin;
+            if (F.deg == nullptr || ns > F.cap_states || ne > F.cap_edges) return;
+            const int V = M.V, KW = M.key_words;
+            const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long long)gridDim.x * blockDim.x;
+            const int lane = threadIdx.x & 31;
+            for (long long i = gtid; i <= ns; i += gsize) F.deg[i] = 0;
+            if (gtid == 0) { ctl->changed = 0; ctl->dead_edges = 0; }
+            grid.sync();
+            for (long long e = gtid; e < ne; e += gsize) atomicAdd(&F.deg[A.edge_src[e]], 1);
+            grid.sync();
+            if (blockIdx.x == 0) {              // exclusive scan of deg[0 .. ns] by one CTA
+                int32_t *partial = reinterpret_cast<int32_t *>(smem);
+                const int nt = blockDim.x, tid = threadIdx.x;
+                const long long n = ns + 1, chunk = (n + nt - 1) / nt;
+                const long long lo = min((long long)tid * chunk, n), hi = min(lo + chunk, n);
+                int sum = 0;
+                for (long long i = lo; i < hi; i++) sum += F.deg[i];
+                partial[tid] = sum;
+                __syncthreads();
+                for (int off = 1; off < nt; off <<= 1) {
+                    const int v = tid >= off ? partial[tid - off] : 0;
+                    __syncthreads();
+                    partial[tid] += v;
+                    __syncthreads();
+                }
+                int run = partial[tid] - sum;
+                bool any_failed = false;
+                for (long long i = lo; i < hi; i++) {
+                    const int d = F.deg[i];
+                    F.first[i] = run;
+                    F.cursor[i] = run;
+                    F.outdeg[i] = d;
+                    if (i < ns) {
+                        F.failed[i] = F.do_trim && d == 0;
+                        any_failed |= F.do_trim && d == 0;
+                    }
+                    run += d;
+                }
+                if (any_failed) ctl->changed = 1;
+            }
+            grid.sync();
+            {
+                const long long gwarp = gtid >> 5, nwarps = gsize >> 5;
+                for (long long e = gwarp; e < ne; e += nwarps) {
+                    const int s = A.edge_src[e];
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(&F.cursor[s], 1);
+                    pos = __shfl_sync(0xffffffffu, pos, 0);
+                    if (lane == 0) { F.s_src[pos] = s; F.s_dst[pos] = A.edge_dst[e]; F.alive[pos] = 1; }
+                    for (int v = lane; v < V; v += 32) F.s_label[(long long)pos * V + v] = A.edge_label[e * V + v];
+                }
+                for (long long i = gtid; i < ns * KW; i += gsize) {
+                    const long long s = i / KW;
+                    const int j = (int)(i % KW), v = A.state_key[i];
+                    if (j == 0) F.rows_cset[s] = v < 0 ? 0 : v;
+                    else F.rows_sig[s * (KW - 1) + (j - 1)] = v;
+                }
+            }
+            grid.sync();
+            while (ctl->changed) {              // fail rule: uniform over the grid (read between two barriers)
+                grid.sync();
+                if (gtid == 0) ctl->changed = 0;
+                grid.sync();
+                for (long long e = gtid; e < ne; e += gsize) {
+                    if (!F.alive[e] || !F.failed[F.s_dst[e]]) continue;
+                    F.alive[e] = 0;
+                    atomicAdd((int *)&ctl->dead_edges, 1);
+                    if (atomicSub(&F.outdeg[F.s_src[e]], 1) == 1) {
+                        F.failed[F.s_src[e]] = 1;
+                        ctl->changed = 1;
+                    }
+                }
+                grid.sync();
+            }
+            if (gtid == 0) ctl->finished = 1;
+            return;
+        }
         if (ctl->status != SEARCH_RUN) return;
         stamp(0);
         const long long n_in = ctl->n_in;

@@ -117,9 +117,20 @@ enum SearchStatus : int {
 };
 struct SearchCtl {
     long long n_in;
-    int cur, status, overflow, pad;
+    int cur, status, overflow;
+    int finished;           // 1: the kernel also grouped the edges by source and applied the fail rule (FinishArgs)
     long long waves_left;
     long long t_nodes, t_fails, t_tuples, t_revisions, t_dominance, t_leaves, t_waves;
+    int dead_edges, changed;
+};
+// Scratch for finishing a small automaton inside the search kernel (all null / 0: the host launches the finishing kernels).
+struct FinishArgs {
+    int32_t *deg, *first, *cursor, *outdeg;     // [cap_states + 1]
+    uint8_t *failed, *alive;                    // [cap_states], [cap_edges]
+    int32_t *s_src, *s_dst, *s_label;           // edges grouped by source
+    int32_t *rows_cset, *rows_sig;              // state rows
+    long long cap_states, cap_edges;
+    int do_trim;
 };
 struct SearchArgs {
     SearchCtl *ctl;
@@ -140,6 +151,7 @@ struct SearchArgs {
     int32_t *edge_src, *edge_dst, *edge_label;
     long long edge_cap;
     long long max_frontier;             // > 0: yield to the host when a wave is wider (it gives up there)
+    FinishArgs fin;
     unsigned long long *trace;          // optional: 5 %globaltimer stamps per wave (start, expanded, routed, ingested, end)
     long long trace_cap;                // in waves
 };

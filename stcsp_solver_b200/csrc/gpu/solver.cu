@@ -366,6 +366,12 @@ struct stcsp_session {
     DBuf<int32_t> d_jobs;
     std::string cache_key;
     DBuf<SearchCtl> d_ctl;
+    // finishing scratch (also handed to the search kernel, which finishes small automata itself)
+    DBuf<int32_t> fb_deg, fb_first, fb_fill, fb_outdeg, fb_src, fb_dst, fb_label, fb_cset, fb_sig, fb_flags;
+    DBuf<uint8_t> fb_failed, fb_alive, fb_scan;
+    bool finish_in_kernel = false, finish_trim = true;     // set by stcsp_gpu_solve (single rank)
+    bool prefinished = false;       // the search kernel already grouped + trimmed (fb_* hold the result)
+    long long prefinished_dead = 0;
     SearchCtl *h_ctl = nullptr;     // pinned, behind h_counters
     int search_grid = 0;
     // search pools
@@ -410,6 +416,9 @@ struct stcsp_session {
 
     void release_all() {
         model.reset();     // (if it was not handed to the cache) its device blocks go back to the block cache
+        fb_deg.release(); fb_first.release(); fb_fill.release(); fb_outdeg.release(); fb_src.release(); fb_dst.release();
+        fb_label.release(); fb_cset.release(); fb_sig.release(); fb_flags.release(); fb_failed.release(); fb_alive.release();
+        fb_scan.release();
         d_jobs.release(); d_ctl.release(); frontier[0].release(); frontier[1].release();
         leaves.release(); unresolved.release(); gathered.release(); table.release(); state_key.release();
         edge_src.release(); edge_dst.release(); edge_label.release(); counters.release(); d_offsets.release();
@@ -661,6 +670,28 @@ struct stcsp_session {
             sa.edge_label = edge_label.p;
             sa.edge_cap = (long long)std::min(edge_src.cap, edge_label.cap / (size_t)V);
             sa.max_frontier = opt.max_frontier_nodes;
+            // automata known (from the last solve of this model) to be small are finished inside the kernel
+            if (finish_in_kernel && model->hint_states > 0 && model->hint_edges <= (1ll << 18)) {
+                const long long cs = std::max<long long>(model->hint_states, 4096), ce = std::max<long long>(model->hint_edges, 8192);
+                const int SLm = std::max(dm.sig_len, 1);
+                fb_deg.reserve((size_t)cs + 1, 0, stream);
+                fb_first.reserve((size_t)cs + 1, 0, stream);
+                fb_fill.reserve((size_t)cs + 1, 0, stream);
+                fb_outdeg.reserve((size_t)cs + 1, 0, stream);
+                fb_failed.reserve((size_t)cs + 1, 0, stream);
+                fb_alive.reserve((size_t)ce + 1, 0, stream);
+                fb_src.reserve((size_t)ce + 1, 0, stream);
+                fb_dst.reserve((size_t)ce + 1, 0, stream);
+                fb_label.reserve((size_t)ce * V + 1, 0, stream);
+                fb_cset.reserve((size_t)cs + 1, 0, stream);
+                fb_sig.reserve((size_t)cs * SLm + 1, 0, stream);
+                sa.fin.deg = fb_deg.p; sa.fin.first = fb_first.p; sa.fin.cursor = fb_fill.p; sa.fin.outdeg = fb_outdeg.p;
+                sa.fin.failed = fb_failed.p; sa.fin.alive = fb_alive.p;
+                sa.fin.s_src = fb_src.p; sa.fin.s_dst = fb_dst.p; sa.fin.s_label = fb_label.p;
+                sa.fin.rows_cset = fb_cset.p; sa.fin.rows_sig = fb_sig.p;
+                sa.fin.cap_states = cs; sa.fin.cap_edges = ce;
+                sa.fin.do_trim = finish_trim ? 1 : 0;
+            }
             DBuf<unsigned long long> trace;
             const long long trace_waves = 256;
             if (opt.verbosity > 2) {
@@ -734,6 +765,8 @@ struct stcsp_session {
             switch (h_ctl->status) {
                 case SEARCH_DONE:
                     n_in = 0;
+                    prefinished = h_ctl->finished != 0;
+                    prefinished_dead = h_ctl->dead_edges;
                     break;
                 case SEARCH_YIELD:
                     break;
@@ -1237,8 +1270,9 @@ struct stcsp_session {
                        int32_t *elabel_p, long long ne) {
         memset(out, 0, sizeof *out);
         const int KW = dm.key_words, V = dm.V, SL = dm.sig_len;
-        DBuf<int32_t> deg, first, fill, s_src, s_dst, s_label, outdeg, flags, rows_cset, rows_sig;
-        DBuf<uint8_t> failed, alive, scan_tmp;
+        DBuf<int32_t> &deg = fb_deg, &first = fb_first, &fill = fb_fill, &s_src = fb_src, &s_dst = fb_dst, &s_label = fb_label,
+                      &outdeg = fb_outdeg, &flags = fb_flags, &rows_cset = fb_cset, &rows_sig = fb_sig;
+        DBuf<uint8_t> &failed = fb_failed, &alive = fb_alive, &scan_tmp = fb_scan;
         struct Release {        // return the scratch blocks only after the stream drained
             cudaStream_t st;
             ~Release() { cudaStreamSynchronize(st); }
@@ -1247,7 +1281,10 @@ struct stcsp_session {
         long long n_final = ne;
         // small automata: one single-CTA launch does all of it and the host learns afterwards whether any edge died
         const bool small = ns <= 2048 && ne <= 512;    // (one CTA is slower than six launches beyond that)
-        if (small) {
+        if (prefinished && keys_p == state_key.p) {
+            // the search kernel did it (FinishArgs): the grouped edges, flags and state rows are in fb_*
+            f_src = s_src.p; f_dst = s_dst.p; f_label = s_label.p;
+        } else if (small) {
             deg.reserve((size_t)ns + 1, 0, stream);
             first.reserve((size_t)ns + 1, 0, stream);
             fill.reserve((size_t)ns + 1, 0, stream);
@@ -1349,10 +1386,10 @@ struct stcsp_session {
                 download(st->edge_dst, f_dst, (size_t)n_final * 4);
                 download(st->edge_label, f_label, (size_t)n_final * V * 4);
             }
-            if (small) CK(cudaMemcpyAsync(h_counters, counters.p + C_OUT, 8, cudaMemcpyDeviceToHost, stream));
+            if (small && !prefinished) CK(cudaMemcpyAsync(h_counters, counters.p + C_OUT, 8, cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             if (timing_open) CK(cudaEventElapsedTime(&ms, ev0, ev1));
-            const long long dead = small ? (long long)(int32_t)h_counters[0] : 0;
+            const long long dead = prefinished ? prefinished_dead : (small ? (long long)(int32_t)h_counters[0] : 0);
             if (dead > 0) {
                 // rare (models with dead ends): compact the live edges into the append-order buffers and copy them again
                 flags.reserve((size_t)ne + 1, 0, stream);
@@ -1662,6 +1699,8 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
         int64_t frontier = s->n_in;
         std::vector<int32_t> req;
         if (!s->opt.profile_kernels && s->search_grid > 0) {       // default: the wave loop runs on the device
+            s->finish_in_kernel = true;
+            s->finish_trim = !(options && options->no_trim);
             s->run_persistent(deadline);
             frontier = 0;
         }
