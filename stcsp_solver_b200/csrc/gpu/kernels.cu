@@ -1226,18 +1226,38 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             A.trace[wave * 5 + k] = t;
         }
     };
+    // The controller (thread 0 of block 0) carries the wave state and the running totals in registers; the control
+    // block in memory is written once per wave (status, n_in, cur) and the totals only when the kernel returns.
+    const bool controller = blockIdx.x == 0 && threadIdx.x == 0;
+    long long c_n_in = 0, c_states = 0, c_edges = 0, c_waves_left = 0;
+    long long a_nodes = 0, a_fails = 0, a_tuples = 0, a_rev = 0, a_dom = 0, a_leaves = 0, a_waves = 0;
+    int c_cur = 0, a_overflow = 0;
+    if (controller) {
+        c_n_in = ctl->n_in;
+        c_cur = ctl->cur;
+        c_waves_left = ctl->waves_left;
+        c_states = (long long)cnt[C_STATES];
+        c_edges = (long long)cnt[C_EDGES];
+    }
+    auto flush_totals = [&]() {         // controller only, before the kernel returns
+        ctl->t_nodes = a_nodes; ctl->t_fails = a_fails; ctl->t_tuples = a_tuples; ctl->t_revisions = a_rev;
+        ctl->t_dominance = a_dom; ctl->t_leaves = a_leaves; ctl->t_waves = a_waves;
+        ctl->waves_left = c_waves_left;
+        ctl->overflow = a_overflow;
+    };
     for (;;) {
         // ---- wave start: can this wave run without the host?
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            const long long n_in = ctl->n_in;
-            const long long states = (long long)cnt[C_STATES], edges = (long long)cnt[C_EDGES];
+        if (controller) {
             int st = SEARCH_RUN;
-            if (n_in == 0) st = SEARCH_DONE;
-            else if (ctl->waves_left <= 0 || (A.max_frontier > 0 && n_in > A.max_frontier)) st = SEARCH_YIELD;
-            else if (n_in > A.leaf_cap || n_in > A.unresolved_cap || states + n_in > A.state_cap ||
-                     edges + n_in > A.edge_cap || 2 * (states + n_in) > A.table_mask + 1 || 2 * n_in > A.out_cap)
+            if (c_n_in == 0) st = SEARCH_DONE;
+            else if (c_waves_left <= 0 || (A.max_frontier > 0 && c_n_in > A.max_frontier)) st = SEARCH_YIELD;
+            else if (c_n_in > A.leaf_cap || c_n_in > A.unresolved_cap || c_states + c_n_in > A.state_cap ||
+                     c_edges + c_n_in > A.edge_cap || 2 * (c_states + c_n_in) > A.table_mask + 1 || 2 * c_n_in > A.out_cap)
                 st = SEARCH_GROW;
             ctl->status = st;
+            ctl->n_in = c_n_in;
+            ctl->cur = c_cur;
+            if (st != SEARCH_RUN) flush_totals();
         }
         grid.sync();
         if (ctl->status == SEARCH_DONE) {
@@ -1340,7 +1360,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         stamp(1);
         // ---- the frontier buffer overflowed: only scratch was written, the host grows it and the wave runs again
         if (cnt[C_OVERFLOW] & 1ull) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->status = SEARCH_RETRY;
+            if (controller) { ctl->status = SEARCH_RETRY; flush_totals(); }
             return;
         }
         // Every block must take the same exit decisions, so they may only depend on values that no block is changing
@@ -1350,7 +1370,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         const long long n_leaves = (long long)cnt[C_LEAVES];
         if (out_after_expand + n_leaves > A.out_cap) {
             // no room for the first nodes of new states: the host grows the frontier and finishes the wave (route + ingest)
-            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->status = SEARCH_INGEST;
+            if (controller) { ctl->status = SEARCH_INGEST; flush_totals(); }
             return;
         }
         RouteArgs ra;
@@ -1383,25 +1403,37 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         stamp(3);
         if (cnt[C_UNRESOLVED] != 0ull) {
             // leaves with an unseen constraint-set transition are still pending: the host resolves and ingests them
-            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->status = SEARCH_RESOLVE;
+            if (controller) { ctl->status = SEARCH_RESOLVE; flush_totals(); }
             return;
         }
-        // ---- wave end: totals, swap, reset the wave counters
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            ctl->t_nodes += (long long)cnt[C_NODES];
-            ctl->t_fails += (long long)cnt[C_FAILS];
-            ctl->t_tuples += (long long)cnt[C_TUPLES];
-            ctl->t_revisions += (long long)cnt[C_REVISIONS];
-            ctl->t_dominance += (long long)cnt[C_DOMINANCE];
-            ctl->t_leaves += n_leaves;
-            ctl->t_waves += 1;
-            ctl->waves_left -= 1;
-            ctl->overflow |= (int)cnt[C_OVERFLOW];
-            ctl->n_in = (long long)cnt[C_OUT];
-            ctl->cur = cur ^ 1;
-            for (int i = C_OUT; i < C_COUNT; i++) cnt[i] = 0ull;
-            __threadfence();
-        }
+        // ---- wave end: totals, swap, reset the wave counters.  Warp 0 of block 0 reads the counters with one parallel
+        // load (a single thread would pay the L2 latency once per counter).
+        if (blockIdx.x == 0 && threadIdx.x < 32) {
+            const int ln = threadIdx.x;
+            const unsigned long long c = ln < C_COUNT ? cnt[ln] : 0ull;
+            if (ln >= C_OUT && ln < C_COUNT) cnt[ln] = 0ull;
+            const long long v_out = (long long)__shfl_sync(0xffffffffu, c, C_OUT);
+            const long long v_nodes = (long long)__shfl_sync(0xffffffffu, c, C_NODES);
+            const long long v_fails = (long long)__shfl_sync(0xffffffffu, c, C_FAILS);
+            const long long v_tuples = (long long)__shfl_sync(0xffffffffu, c, C_TUPLES);
+            const long long v_rev = (long long)__shfl_sync(0xffffffffu, c, C_REVISIONS);
+            const long long v_dom = (long long)__shfl_sync(0xffffffffu, c, C_DOMINANCE);
+            const long long v_ovf = (long long)__shfl_sync(0xffffffffu, c, C_OVERFLOW);
+            const long long v_states = (long long)__shfl_sync(0xffffffffu, c, C_STATES);
+            const long long v_edges = (long long)__shfl_sync(0xffffffffu, c, C_EDGES);
+            if (ln == 0) {
+                a_nodes += v_nodes; a_fails += v_fails; a_tuples += v_tuples; a_rev += v_rev; a_dom += v_dom;
+                a_leaves += n_leaves;
+                a_waves += 1;
+                a_overflow |= (int)v_ovf;
+                c_waves_left -= 1;
+                c_n_in = v_out;
+                c_cur = cur ^ 1;
+                c_states = v_states;
+                c_edges = v_edges;
+            }
+            static_assert(C_COUNT <= 32, "one warp reads all counters");
+        }       // (the grid barrier at the top of the loop orders these writes before anybody reads them)
         stamp(4);
         wave++;
         // the barrier at the top of the loop publishes the new control block
