@@ -96,7 +96,9 @@ typedef struct stcsp_options {
                                         driver uses it to keep small instances on one GPU); 0: no limit */
     int64_t max_states;              /* reserved */
     int64_t max_edges;               /* reserved */
-    int32_t reserved0;
+    int32_t expand_mode;             /* mapping of search nodes to threads: 0 automatic (a CTA per node on narrow waves, four nodes
+                                        per warp on wide ones, a warp per node in between), 1 warp per node always, 2 CTA per
+                                        node always, 3 four nodes per warp always (testing / tuning; never changes results) */
     int32_t profile_kernels;         /* 1: step-wise path (one expand / route / ingest launch per wave) with every expand launch
                                         timed by CUDA events, instead of the persistent search kernel */
     int32_t no_trim;                 /* 1: stcsp_gpu_solve returns the untrimmed automaton */

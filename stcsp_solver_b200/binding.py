@@ -40,7 +40,7 @@ class Options(C.Structure):
         ("device", C.c_int32), ("use_current_device", C.c_int32), ("time_limit_s", C.c_int32),
         ("verbosity", C.c_int32), ("enum_limit_now", C.c_int64), ("enum_limit_ahead", C.c_int64),
         ("max_frontier_nodes", C.c_int64), ("max_states", C.c_int64), ("max_edges", C.c_int64),
-        ("reserved0", C.c_int32), ("profile_kernels", C.c_int32), ("no_trim", C.c_int32),
+        ("expand_mode", C.c_int32), ("profile_kernels", C.c_int32), ("no_trim", C.c_int32),
         ("lookahead", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 

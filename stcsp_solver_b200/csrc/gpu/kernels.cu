@@ -69,7 +69,7 @@ __host__ __device__ inline size_t scratch_bytes(const DevModel &m) {
     return align8(b);
 }
 
-// layout of a CTA's dynamic shared memory: kExpandWarps node blocks, then kExpandWarps scratch blocks
+// layout of a CTA's dynamic shared memory: m.node_slots node blocks, then kExpandWarps scratch blocks, then the staged set
 __device__ inline WarpMem carve(unsigned char *smem, const DevModel &m, int node_slot, int warp) {
     WarpMem w;
     unsigned char *p = smem + (size_t)node_slot * node_bytes(m);
@@ -78,7 +78,7 @@ __device__ inline WarpMem carve(unsigned char *smem, const DevModel &m, int node
     w.dcur = (uint32_t *)p; p += align8((size_t)m.max_words * 4);
     w.hvy = (uint32_t *)p; p += align8((size_t)m.max_words * 4);
     w.flag = (int32_t *)p;
-    p = smem + (size_t)kExpandWarps * node_bytes(m) + (size_t)warp * scratch_bytes(m);
+    p = smem + (size_t)m.node_slots * node_bytes(m) + (size_t)warp * scratch_bytes(m);
     w.supp = (u64 *)p; p += (size_t)m.max_scope * 8;
     w.flb = (int32_t *)p; p += align8((size_t)m.max_scope * 4);
     w.fdi = (int32_t *)p; p += align8((size_t)m.max_scope * 4);
@@ -768,7 +768,7 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
 // over by every revision; the CTA copies the set most of its nodes belong to into shared memory once per wave and
 // hands the revisions a DevModel whose pointers are biased so that the ABSOLUTE pool indices still work.
 __device__ __forceinline__ unsigned char *stage_base(unsigned char *smem, const DevModel &m) {
-    return smem + (size_t)kExpandWarps * (node_bytes(m) + scratch_bytes(m));
+    return smem + (size_t)m.node_slots * node_bytes(m) + (size_t)kExpandWarps * scratch_bytes(m);
 }
 
 // Called by every thread of the CTA (contains barriers).  Returns the constraint set staged, -1 if none.
@@ -942,6 +942,190 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
         if (st_tuples) atomicAdd(&P.counters[C_TUPLES], st_tuples);
         if (st_rev) atomicAdd(&P.counters[C_REVISIONS], st_rev);
     }
+}
+
+// ---- wide waves: FOUR search nodes per warp, eight lanes each ----------------------------------------------------
+// A scalar round rarely has more than a handful of dirty propagators per node, so with one node per warp most lanes
+// idle.  Here the four groups of a warp run their scalar rounds side by side (lanes that execute the same revision
+// code converge regardless of their group); the rare revisions that need 32 lanes are served one group at a time.
+__device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const ExpandArgs &P, unsigned char *smem) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+    const unsigned gmask = 0xffu << (8 * g);
+    WarpMem wm = carve(smem, Mg, warp * 4 + g, warp);           // my group's node slot, the warp's scratch
+    const long long n_in = P.n_in;
+    const int V = Mg.V, k = Mg.k, NW = Mg.node_words;
+    unsigned long long st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;
+    const long long probe = (long long)blockIdx.x * kExpandWarps * 4;
+    const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1);
+    const DevModel &Ms = *reinterpret_cast<const DevModel *>(stage_base(smem, Mg));
+    const long long first = ((long long)blockIdx.x * kExpandWarps + warp) * 4, step = (long long)gridDim.x * kExpandWarps * 4;
+
+    for (long long q4 = first; q4 < n_in; q4 += step) {
+        const long long ni = q4 + g;
+        const bool have = ni < n_in;
+        __syncwarp();
+        if (have) {
+            const int32_t *src = P.in_nodes + ni * NW;
+            for (int w = gl; w < NW; w += 8) wm.nodew[w] = src[w];
+        } else if (gl < 4) {
+            wm.nodew[gl] = gl == 3 ? -1 : 0;                    // a harmless header for the idle group
+        }
+        for (int w = gl; w < Mg.max_words; w += 8) { wm.hvy[w] = 0u; wm.dirty[w] = 0u; }
+        __syncwarp();
+        const int cid = wm.nodew[1], bvar = wm.nodew[3], expire = wm.nodew[2];
+        const DevModel &M = cid == staged ? Ms : Mg;
+        const DevSet S = Mg.sets[cid];
+        u64 *dom = reinterpret_cast<u64 *>(wm.nodew + 4);
+        bool empty = false;
+        if (have)
+            for (int i = gl; i < V * k; i += 8) empty |= dom[i] == 0ull;
+        bool fail = (__ballot_sync(0xffffffffu, empty) & gmask) != 0u;
+        if (have) {
+            for (int w = gl; w < S.n_words; w += 8) {
+                uint32_t m;
+                if (bvar < 0) {
+                    const int left = S.n_prop - w * 32;
+                    m = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+                } else {
+                    m = M.wake[S.wake_off + ((size_t)bvar * k) * S.n_words + w];
+                }
+                wm.dirty[w] = m;
+            }
+        }
+        __syncwarp();
+
+        // ---- propagate the four nodes in lock step (the host never picks this mode with lazy look-ahead)
+        bool done = !have || fail;
+        for (;;) {
+            // phase A: one scalar round for every group that still has cheap work
+            bool myfail = false;
+            if (!done) {
+                for (int q = gl; q < S.n_cheap; q += 8) {
+                    const uint32_t bit = 1u << (q & 31);
+                    if (!(wm.dirty[q >> 5] & bit)) continue;
+                    atomicAnd(&wm.dirty[q >> 5], ~bit);
+                    const int r = scalar_revise(M, S, q, dom, wm.dirty, expire, my_tuples);
+                    st_rev++;
+                    if (r == SR_FAIL) myfail = true;
+                    else if (r == SR_HEAVY) atomicOr(&wm.hvy[q >> 5], bit);
+                }
+            }
+            __syncwarp();
+            bool p_more = false, p_heavy = false;
+            if (!done) {
+                for (int w = gl; w < S.n_words; w += 8) {
+                    const uint32_t cm = cheap_mask(S, w);
+                    p_more |= (wm.dirty[w] & cm) != 0u;
+                    p_heavy |= (wm.hvy[w] | (wm.dirty[w] & ~cm)) != 0u;
+                }
+            }
+            const unsigned bf = __ballot_sync(0xffffffffu, myfail);
+            const unsigned bm = __ballot_sync(0xffffffffu, p_more);
+            const unsigned bh = __ballot_sync(0xffffffffu, p_heavy);
+            if (!done && (bf & gmask)) { fail = true; done = true; }
+            const bool more = !done && (bm & gmask) != 0u;
+            const bool heavy = !done && !more && (bh & gmask) != 0u;
+            if (!done && !more && !heavy) done = true;          // this node is at its fixpoint
+            const unsigned any_more = __ballot_sync(0xffffffffu, more);
+            const unsigned any_heavy = __ballot_sync(0xffffffffu, heavy);
+            if (any_more) continue;                             // some group has another scalar round to run
+            if (!any_heavy) break;                              // every node is at its fixpoint (or failed)
+            // phase B: revisions that need 32 lanes, one group at a time
+            for (int gg = 0; gg < 4; gg++) {
+                if (!(any_heavy & (0xffu << (8 * gg)))) continue;       // uniform
+                WarpMem wq = carve(smem, Mg, warp * 4 + gg, warp);
+                const int cq = wq.nodew[1];
+                const DevModel &Mq = cq == staged ? Ms : Mg;
+                const DevSet Sq = Mg.sets[cq];
+                int q = -1;
+                for (int base = 0; base < Sq.n_words; base += 32) {
+                    const uint32_t w = base + lane < Sq.n_words ? (wq.hvy[base + lane] | (wq.dirty[base + lane] & ~cheap_mask(Sq, base + lane))) : 0u;
+                    const unsigned b = __ballot_sync(0xffffffffu, w != 0u);
+                    if (b) {
+                        const int l = __ffs(b) - 1;
+                        const uint32_t ww = __shfl_sync(0xffffffffu, w, l);
+                        q = (base + l) * 32 + __ffs(ww) - 1;
+                        break;
+                    }
+                }
+                if (q < 0) continue;
+                __syncwarp();
+                if (lane == 0) {
+                    wq.hvy[q >> 5] &= ~(1u << (q & 31));
+                    wq.dirty[q >> 5] &= ~(1u << (q & 31));
+                }
+                __syncwarp();
+                NodeCtx cx{Mq, Sq, wq, reinterpret_cast<u64 *>(wq.nodew + 4), lane, wq.nodew[2], 0ull, nullptr, 0};
+                const bool ok = revise<false>(cx, q);
+                __syncwarp();
+                if (lane == 0) wq.dirty[q >> 5] &= ~(1u << (q & 31));
+                __syncwarp();
+                st_rev += lane == 0;
+                st_tuples += cx.tuples;
+                if (!ok && g == gg) { fail = true; done = true; }
+            }
+        }
+
+        // ---- emit: eight lanes per node
+        if (have && gl == 0) { st_nodes++; st_fails += fail; }
+        const bool live = have && !fail;
+        int bv = -1;
+        for (int base = 0; base < V; base += 8) {               // uniform trip count
+            const int v = base + gl;
+            const bool unbound = live && v < V && __popcll(dom[v * k]) > 1;
+            const unsigned b = (__ballot_sync(0xffffffffu, unbound) & gmask) >> (8 * g);
+            if (bv < 0 && b) bv = base + __ffs(b) - 1;
+        }
+        const bool leaf = live && bv < 0, branch = live && bv >= 0;
+        const u64 D = branch ? dom[bv * k] : 0ull;
+        const int d = __popcll(D);
+        unsigned long long slot = 0;
+        if (gl == 0 && leaf) slot = atomicAdd(&P.counters[C_LEAVES], 1ull);
+        if (gl == 0 && branch) slot = atomicAdd(&P.counters[C_OUT], (unsigned long long)d);
+        slot = __shfl_sync(0xffffffffu, slot, g * 8);
+        if (leaf) {
+            if ((long long)slot >= P.leaf_cap) {
+                if (gl == 0) atomicOr(&P.counters[C_OVERFLOW], 2ull);
+            } else {
+                int32_t *rec = P.leaves + slot * M.rec_words;
+                if (gl < 4) rec[gl] = gl == 3 ? 0 : wm.nodew[gl];
+                for (int v = gl; v < V; v += 8) rec[4 + v] = M.lb[v] + __ffsll((long long)dom[v * k]) - 1;
+            }
+        } else if (branch) {
+            if ((long long)(slot + d) > P.out_cap) {
+                if (gl == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
+            } else {
+                const int dw = 4 + 2 * (bv * k);
+                int j = 0;
+                for (u64 w = D; w; w &= w - 1, j++) {
+                    const u64 one = w & (~w + 1ull);
+                    int32_t *dst = P.out_nodes + (slot + j) * NW;
+                    for (int i = gl; i < NW; i += 8) {
+                        int32_t val = wm.nodew[i];
+                        if (i == 3) val = bv;
+                        else if (i == dw) val = (int32_t)(uint32_t)(one & 0xffffffffull);
+                        else if (i == dw + 1) val = (int32_t)(uint32_t)(one >> 32);
+                        dst[i] = val;
+                    }
+                }
+            }
+        }
+    }
+    st_rev = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_rev);
+    st_nodes = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_nodes);
+    st_fails = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_fails);
+    st_tuples += (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)my_tuples);
+    if (lane == 0 && (st_nodes | st_tuples | st_rev)) {
+        if (st_nodes) atomicAdd(&P.counters[C_NODES], st_nodes);
+        if (st_fails) atomicAdd(&P.counters[C_FAILS], st_fails);
+        if (st_tuples) atomicAdd(&P.counters[C_TUPLES], st_tuples);
+        if (st_rev) atomicAdd(&P.counters[C_REVISIONS], st_rev);
+    }
+}
+
+__global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_quad_kernel(const DevModel M, const ExpandArgs P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    expand_body_quad(M, P, smem);
 }
 
 template <bool CTA>
@@ -1354,7 +1538,9 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         ea.counters = A.counters;
         ea.dbg = A.trace ? A.trace + 5 * A.trace_cap : nullptr;     // block 0's timeline follows the per-wave stamps
         ea.dbg_cap = A.trace ? 4096 : 0;
-        if (n_in <= 3ll * gridDim.x) expand_body<true>(M, ea, smem);
+        const int mode = pick_expand_mode(M, n_in, gridDim.x);
+        if (mode == EXPAND_CTA) expand_body<true>(M, ea, smem);
+        else if (mode == EXPAND_QUAD) expand_body_quad(M, ea, smem);
         else expand_body<false>(M, ea, smem);
         grid.sync();
         stamp(1);
@@ -1491,7 +1677,7 @@ __global__ void fill_kernel(int32_t *ptr, long long n, int32_t value) {
 uint32_t capmap_hash(int cid, const int32_t *vals, int n) { return cap_hash(cid, vals, n); }
 
 size_t expand_smem_bytes(const DevModel &m) {
-    return (node_bytes(m) + scratch_bytes(m)) * kExpandWarps + align8(sizeof(DevModel)) + align8((size_t)m.stage_bytes);
+    return node_bytes(m) * m.node_slots + scratch_bytes(m) * kExpandWarps + align8(sizeof(DevModel)) + align8((size_t)m.stage_bytes);
 }
 
 static void configure_expand(size_t smem) {
@@ -1503,6 +1689,8 @@ static void configure_expand(size_t smem) {
         }
         cudaFuncSetAttribute(expand_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(expand_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(expand_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(expand_quad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = smem;
     }
 }
@@ -1522,10 +1710,11 @@ int expand_max_grid(const DevModel &m, int sm_count) {
     return per_sm * sm_count;
 }
 
-void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, bool cta_per_node, cudaStream_t stream) {
+void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, int mode, cudaStream_t stream) {
     const size_t smem = expand_smem_bytes(m);
     configure_expand(smem);
-    if (cta_per_node) expand_kernel<true><<<grid, kExpandWarps * 32, smem, stream>>>(m, a);
+    if (mode == EXPAND_CTA) expand_kernel<true><<<grid, kExpandWarps * 32, smem, stream>>>(m, a);
+    else if (mode == EXPAND_QUAD) expand_quad_kernel<<<grid, kExpandWarps * 32, smem, stream>>>(m, a);
     else expand_kernel<false><<<grid, kExpandWarps * 32, smem, stream>>>(m, a);
 }
 

@@ -45,6 +45,8 @@ struct DevModel {
     int32_t n_sig, sig_len;
     int32_t max_scope, max_stack, max_words;
     int32_t stage_bytes;        // shared memory reserved per CTA for one constraint set's metadata (0: never staged)
+    int32_t node_slots;         // node blocks per CTA in shared memory: 8 (one per warp) or 32 (four per warp, quad mode)
+    int32_t force_mode;         // 0 automatic, else ExpandMode + 1
     int32_t lazy_ahead;         // 1: pointwise propagators at look-ahead offsets run only once the current point is bound
     long long enum_now, enum_ahead;
     const int32_t *lb, *width, *sig_vars;
@@ -160,8 +162,18 @@ constexpr int kExpandWarps = 8;      // warps per CTA of the expand kernel
 
 size_t expand_smem_bytes(const DevModel &m);
 int expand_max_grid(const DevModel &m, int sm_count);      // resident CTAs of the expand kernel on this device
-// cta_per_node: one CTA (8 warps) per search node instead of one warp -- for waves narrower than the GPU
-void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, bool cta_per_node, cudaStream_t stream);
+// mode: a warp per search node, a whole CTA per node (waves narrower than the GPU), or four nodes per warp (wide waves)
+enum ExpandMode : int { EXPAND_WARP = 0, EXPAND_CTA = 1, EXPAND_QUAD = 2 };
+void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, int mode, cudaStream_t stream);
+// the mode the automatic policy picks for a wave of n_in nodes on a grid of `ctas` resident CTAs
+__host__ __device__ inline int pick_expand_mode(const DevModel &m, long long n_in, long long ctas) {
+    const bool quad_ok = m.node_slots >= 4 * 8 && !m.lazy_ahead;
+    if (m.force_mode == EXPAND_QUAD + 1) return quad_ok ? EXPAND_QUAD : EXPAND_WARP;
+    if (m.force_mode) return m.force_mode - 1;
+    if (n_in <= 3 * ctas) return EXPAND_CTA;
+    if (quad_ok && n_in >= 4ll * 8 * ctas) return EXPAND_QUAD;
+    return EXPAND_WARP;
+}
 // persistent wave loop (cooperative launch); search_max_grid = co-resident CTAs, 0 if unavailable
 int search_max_grid(const DevModel &m, int sm_count);
 cudaError_t launch_search(const DevModel &m, const SearchArgs &a, int grid, cudaStream_t stream);

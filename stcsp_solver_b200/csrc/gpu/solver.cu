@@ -490,6 +490,10 @@ struct stcsp_session {
             dm.stage_bytes = sb <= 40 * 1024 ? (int32_t)sb : 0;     // larger model->sets stay in global memory / L1
         }
         dm.lazy_ahead = opt.lookahead == 2 ? 1 : 0;
+        // four node blocks per warp (quad mode for wide waves) when three CTAs still fit an SM
+        dm.node_slots = 4 * kExpandWarps;
+        if (expand_smem_bytes(dm) > 72 * 1024) dm.node_slots = kExpandWarps;
+        dm.force_mode = opt.expand_mode >= 1 && opt.expand_mode <= 3 ? opt.expand_mode : 0;
         dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : 8;
         dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : 4;
         dm.lb = model->d_lb.p;
@@ -877,11 +881,12 @@ struct stcsp_session {
                 ea.leaf_cap = (long long)(leaves.cap / RW);
                 ea.counters = counters.p;
                 // narrow wave: a whole CTA per node (intra-node parallelism); wide wave: a warp per node
-                const bool cta_mode = n_in <= 3ll * expand_grid_max;
-                const int grid = cta_mode ? (int)std::min<long long>(n_in, expand_grid_max)
-                                          : (int)std::min<long long>((n_in + kExpandWarps - 1) / kExpandWarps, expand_grid_max);
+                const int mode = pick_expand_mode(dm, n_in, expand_grid_max);
+                const int grid = mode == EXPAND_CTA ? (int)std::min<long long>(n_in, expand_grid_max)
+                               : mode == EXPAND_QUAD ? (int)std::min<long long>((n_in + 4 * kExpandWarps - 1) / (4 * kExpandWarps), expand_grid_max)
+                                                     : (int)std::min<long long>((n_in + kExpandWarps - 1) / kExpandWarps, expand_grid_max);
                 if (opt.profile_kernels) CK(cudaEventRecord(evk0, stream));
-                launch_expand(dm, ea, grid, cta_mode, stream);
+                launch_expand(dm, ea, grid, mode, stream);
                 if (opt.profile_kernels) CK(cudaEventRecord(evk1, stream));
                 RouteArgs ra{};
                 ra.leaves = leaves.p;

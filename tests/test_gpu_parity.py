@@ -86,6 +86,16 @@ def test_stepwise_path_equals_persistent_kernel(name):
     assert st1["n_kernel_launches"] < st2["n_kernel_launches"]
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("name", ["juggling_b5_f6_nosym", "digitinvader4", "partialorder_12", "probe_until_two", "probe_first_capture"])
+def test_every_node_mapping_gives_the_same_automaton(name, mode):
+    """expand_mode: a warp per node, a CTA per node, four nodes per warp -- forced for every wave."""
+    g = GOLDENS[name]
+    for extra in (dict(), dict(profile_kernels=1)):
+        _, _, sol = run_gpu(golden_text(g), (), expand_mode=mode, **extra)
+        assert sol.canonical_sha256() == g["sha256"], (name, mode, extra)
+
+
 def test_session_api_single_rank_matches_solve():
     """create / expand / [resolve] / ingest / finish / assemble / trim by hand == stcsp_gpu_solve."""
     g = GOLDENS["probe_first_capture"]
