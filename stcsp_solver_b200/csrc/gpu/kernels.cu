@@ -1079,10 +1079,26 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
         const bool leaf = live && bv < 0, branch = live && bv >= 0;
         const u64 D = branch ? dom[bv * k] : 0ull;
         const int d = __popcll(D);
+        // one cursor update per warp and kind (single-address atomics are the scarce resource on wide waves)
         unsigned long long slot = 0;
-        if (gl == 0 && leaf) slot = atomicAdd(&P.counters[C_LEAVES], 1ull);
-        if (gl == 0 && branch) slot = atomicAdd(&P.counters[C_OUT], (unsigned long long)d);
-        slot = __shfl_sync(0xffffffffu, slot, g * 8);
+        {
+            const unsigned lb = __ballot_sync(0xffffffffu, leaf && gl == 0);
+            int before = 0, total = 0;                          // children of the groups below mine / of the warp
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int dq = __shfl_sync(0xffffffffu, d, q * 8);
+                if (q < g) before += dq;
+                total += dq;
+            }
+            unsigned long long lbase = 0, obase = 0;
+            if (lane == 0) {
+                if (lb) lbase = atomicAdd(&P.counters[C_LEAVES], (unsigned long long)__popc(lb));
+                if (total) obase = atomicAdd(&P.counters[C_OUT], (unsigned long long)total);
+            }
+            lbase = __shfl_sync(0xffffffffu, lbase, 0);
+            obase = __shfl_sync(0xffffffffu, obase, 0);
+            slot = leaf ? lbase + (unsigned long long)__popc(lb & ((1u << (g * 8)) - 1u)) : obase + (unsigned long long)before;
+        }
         if (leaf) {
             if ((long long)slot >= P.leaf_cap) {
                 if (gl == 0) atomicOr(&P.counters[C_OVERFLOW], 2ull);
@@ -1392,6 +1408,164 @@ __device__ __forceinline__ void leaf_body(const DevModel &M, const RouteArgs &R,
 
 __global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const IngestArgs P) { ingest_body(M, P); }
 
+// ---- wide waves: route + merge FOUR leaves per warp, eight lanes each ---------------------------------------------
+// One leaf is a chain of dependent global round trips (table slot, state key, edge cursor); with one leaf per warp the
+// chain's latency is all there is.  Four independent chains per warp overlap it.  Same results as leaf_body.
+__device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArgs &R, const IngestArgs &P, long long n_leaves) {
+    const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7, lead = g * 8;
+    const unsigned gmask = 0xffu << lead;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int V = M.V, k = M.k, KW = M.key_words, NW = M.node_words;
+    unsigned long long st_dom = 0;
+    for (long long l4 = warp_id * 4; l4 < n_leaves; l4 += total_warps * 4) {
+        const long long li = l4 + g;
+        const bool have = li < n_leaves;
+        int32_t *rec = R.leaves + (have ? li : 0) * M.rec_words;
+        // ---- route (reference src/solveralgorithm.cpp:755-837)
+        int ncid = -1, nexp = 0;
+        bool routed = false;
+        if (have) {
+            const int cid = rec[1];
+            nexp = rec[2];
+            const DevSet S = M.sets[cid];
+            ncid = S.static_next;
+            if (ncid < 0) {
+                if (gl == 0) {
+                    if (R.capmap_mask >= 0) {
+                        const int32_t *cap = M.aux + S.cap_off;
+                        uint32_t h = cap_hash_begin(cid);
+                        for (int i = 0; i < S.n_cap; i++) h = cap_hash_step(h, rec[4 + cap[i]]);
+                        h = cap_hash_end(h) & (uint32_t)R.capmap_mask;
+                        for (;;) {
+                            const CapEntry e = R.capmap[h];
+                            if (e.cid == -1) break;
+                            bool eq = e.cid == cid;
+                            for (int i = 0; eq && i < S.n_cap; i++) eq = R.capvals[e.off + i] == rec[4 + cap[i]];
+                            if (eq) { ncid = e.next; break; }
+                            h = (h + 1) & (uint32_t)R.capmap_mask;
+                        }
+                    }
+                    if (ncid < 0) {
+                        const unsigned long long u = atomicAdd(&R.counters[C_UNRESOLVED], 1ull);
+                        if ((long long)u < R.unresolved_cap) R.unresolved[u] = (int32_t)li;
+                        else atomicOr(&R.counters[C_OVERFLOW], 16ull);
+                    }
+                }
+            }
+        }
+        ncid = __shfl_sync(0xffffffffu, ncid, lead);
+        routed = have && ncid >= 0;
+        uint32_t h = 0;
+        if (routed) {
+            const DevSet NS = M.sets[ncid];
+            for (int u = 0; u < NS.n_until; u++)
+                if (rec[4 + M.aux[NS.until_off + u]] == 1) nexp |= 1 << u;
+            for (int j = gl; j < KW; j += 8) h ^= key_word_hash(key_word(M, rec, ncid, nexp, j), j);
+        }
+        h ^= __shfl_xor_sync(0xffffffffu, h, 4);
+        h ^= __shfl_xor_sync(0xffffffffu, h, 2);
+        h ^= __shfl_xor_sync(0xffffffffu, h, 1);
+        h = mix32(h);
+        if (routed && gl == 0) {
+            rec[1] = ncid;
+            rec[2] = nexp;
+            rec[3] = (int32_t)h;
+        }
+        {   // one counter update per warp, not per leaf: these are single-address atomics
+            const unsigned rb = __ballot_sync(0xffffffffu, routed && gl == 0);
+            if (lane == 0 && rb) atomicAdd(&R.counters[C_OWNER0], (unsigned long long)__popc(rb));
+        }
+        // ---- find or insert the successor state (reference vertexTableGetVertex / AddVertex)
+        long long slot = (long long)h & P.table_mask;
+        int dst = -1;
+        bool is_new = false, searching = routed;
+        while (__any_sync(0xffffffffu, searching)) {
+            int v = 0;
+            if (searching && gl == 0) v = atomicCAS(&P.table[slot], -1, -2);
+            v = __shfl_sync(0xffffffffu, v, lead);
+            if (searching && v == -1) {                     // slot claimed: this leaf creates the state
+                unsigned long long id = 0;
+                if (gl == 0) id = atomicAdd(&P.counters[C_STATES], 1ull);
+                id = __shfl_sync(gmask, id, lead);
+                if ((long long)id >= P.state_cap) {
+                    if (gl == 0) { atomicOr(&P.counters[C_OVERFLOW], 4ull); atomicExch(&P.table[slot], -3); }
+                    searching = false;
+                    routed = false;
+                } else {
+                    for (int j = gl; j < KW; j += 8) P.state_key[id * KW + j] = key_word(M, rec, ncid, nexp, j);
+                    __threadfence();
+                    __syncwarp(gmask);
+                    if (gl == 0) atomicExch(&P.table[slot], (int)id);
+                    dst = (int)id;
+                    is_new = true;
+                    searching = false;
+                }
+            } else if (searching && v == -3) {
+                searching = false;
+                routed = false;
+            } else if (searching && v >= 0) {
+                __threadfence();
+                bool eq = true;
+                for (int j = gl; j < KW; j += 8)
+                    eq &= __ldcg(&P.state_key[(long long)v * KW + j]) == key_word(M, rec, ncid, nexp, j);
+                const unsigned be = __ballot_sync(gmask, eq);
+                if ((be & gmask) == gmask) { dst = v; searching = false; }
+                else slot = (slot + 1) & P.table_mask;
+            }
+            // v == -2: another group or warp is writing this slot's key -- look again in the next turn
+        }
+        // ---- first search node of a new state, and the edge
+        unsigned long long o = 0, e = 0;
+        {
+            const unsigned rb = __ballot_sync(0xffffffffu, routed && gl == 0);
+            const unsigned nb = __ballot_sync(0xffffffffu, routed && is_new && gl == 0);
+            if (lane == 0) {
+                if (rb) e = atomicAdd(&P.counters[C_EDGES], (unsigned long long)__popc(rb));
+                if (nb) o = atomicAdd(&P.counters[C_OUT], (unsigned long long)__popc(nb));
+            }
+            const unsigned below = (1u << lead) - 1u;
+            e = __shfl_sync(0xffffffffu, e, 0) + (unsigned long long)__popc(rb & below);
+            o = __shfl_sync(0xffffffffu, o, 0) + (unsigned long long)__popc(nb & below);
+        }
+        if (routed) {
+            const int dst_global = dst * M.world + M.rank;
+            if (is_new) {
+                if ((long long)o >= P.out_cap) {
+                    if (gl == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
+                } else {
+                    const DevSet NS = M.sets[ncid];
+                    int32_t *node = P.out_nodes + o * NW;
+                    if (gl == 0) { node[0] = dst_global; node[1] = ncid; node[2] = nexp; node[3] = -1; }
+                    u64 *nd = reinterpret_cast<u64 *>(node + 4);
+                    for (int i = gl; i < V * k; i += 8) {
+                        const int v = i / k, p = i % k;
+                        u64 m = width_mask(M.width[v]);
+                        if (p == 0 && k > 1) {
+                            for (int t = 0; t < NS.n_next; t++) {
+                                if (M.aux[NS.next_off + 2 * t + 1] != v) continue;
+                                const long long b = (long long)rec[4 + M.aux[NS.next_off + 2 * t]] - (long long)M.lb[v];
+                                m &= (b >= 0 && b < 64) ? (1ull << b) : 0ull;
+                            }
+                        }
+                        nd[i] = m;
+                    }
+                }
+            } else if (gl == 0) {
+                st_dom++;
+            }
+            if ((long long)e >= P.edge_cap) {
+                if (gl == 0) atomicOr(&P.counters[C_OVERFLOW], 8ull);
+            } else {
+                if (gl == 0) { P.edge_src[e] = rec[0]; P.edge_dst[e] = dst_global; }
+                for (int v = gl; v < V; v += 8) P.edge_label[e * V + v] = rec[4 + v];
+            }
+        }
+    }
+    st_dom = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_dom);
+    if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+}
+
 // ---- the whole wave loop in one cooperative launch -------------------------------------------------------
 // Waves of a small or deep search cost more in launches and host synchronisation than in work.  search_kernel
 // runs expand -> route -> ingest -> bookkeeping for wave after wave with grid-wide barriers in between and
@@ -1583,7 +1757,9 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         ia.out_nodes = A.frontier[cur ^ 1];
         ia.out_cap = A.out_cap;
         ia.counters = A.counters;
-        leaf_body(M, ra, ia, n_leaves);                 // route + ingest in one pass
+        if (n_leaves >= 4ll * kExpandWarps * gridDim.x || M.force_mode == EXPAND_QUAD + 1)
+            leaf_body_quad(M, ra, ia, n_leaves);        // four leaves per warp
+        else leaf_body(M, ra, ia, n_leaves);            // route + ingest in one pass
         grid.sync();
         stamp(2);
         stamp(3);
