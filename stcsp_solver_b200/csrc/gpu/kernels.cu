@@ -1260,7 +1260,6 @@ __device__ __forceinline__ void route_body(const DevModel &M, const RouteArgs &P
     }
 }
 
-__global__ void __launch_bounds__(256) route_kernel(const DevModel M, const RouteArgs P) { route_body(M, P); }
 
 // ---- scatter: group routed leaves by owner rank (multi-GPU only) ---------------------------------------
 __global__ void __launch_bounds__(256) scatter_kernel(const DevModel M, const int32_t *leaves, long long n,
@@ -1270,14 +1269,24 @@ __global__ void __launch_bounds__(256) scatter_kernel(const DevModel M, const in
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int RW = M.rec_words;
-    for (long long li = warp_id; li < n; li += total_warps) {
-        const int32_t *rec = leaves + li * RW;
-        const int owner = leaf_owner(M, rec[1], (uint32_t)rec[3]);
+    // 32 leaves per warp and turn: lanes with the same owner share one cursor update, then the warp copies row by row
+    for (long long base = warp_id * 32; base < n; base += total_warps * 32) {
+        const long long li = base + lane;
+        const bool have = li < n;
+        const int owner = have ? leaf_owner(M, leaves[li * RW + 1], (uint32_t)leaves[li * RW + 3]) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, owner);
+        const int leader = __ffs(peers) - 1;
         unsigned long long pos = 0;
-        if (lane == 0) pos = atomicAdd(&fill[owner], 1ull);
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        int32_t *dst = outbox + (offsets[owner] + (long long)pos) * RW;
-        for (int w = lane; w < RW; w += 32) dst[w] = rec[w];
+        if (have && lane == leader) pos = atomicAdd(&fill[owner], (unsigned long long)__popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader) + (unsigned long long)__popc(peers & ((1u << lane) - 1u));
+        const long long row = have ? offsets[owner] + (long long)pos : -1;
+        const int cnt = (int)min(32ll, n - base);
+        for (int t = 0; t < cnt; t++) {
+            const long long r = __shfl_sync(0xffffffffu, row, t);
+            const int32_t *rec = leaves + (base + t) * RW;
+            int32_t *dst = outbox + r * RW;
+            for (int w = lane; w < RW; w += 32) dst[w] = rec[w];
+        }
     }
 }
 
@@ -1406,11 +1415,12 @@ __device__ __forceinline__ void leaf_body(const DevModel &M, const RouteArgs &R,
     if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
 }
 
-__global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const IngestArgs P) { ingest_body(M, P); }
 
 // ---- wide waves: route + merge FOUR leaves per warp, eight lanes each ---------------------------------------------
 // One leaf is a chain of dependent global round trips (table slot, state key, edge cursor); with one leaf per warp the
 // chain's latency is all there is.  Four independent chains per warp overlap it.  Same results as leaf_body.
+// ROUTE without INGEST is the producing rank's half (multi-GPU), INGEST without ROUTE the owner's half over its inbox.
+template <bool ROUTE, bool INGEST>
 __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArgs &R, const IngestArgs &P, long long n_leaves) {
     const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7, lead = g * 8;
     const unsigned gmask = 0xffu << lead;
@@ -1419,12 +1429,19 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
     const int V = M.V, k = M.k, KW = M.key_words, NW = M.node_words;
     unsigned long long st_dom = 0;
     for (long long l4 = warp_id * 4; l4 < n_leaves; l4 += total_warps * 4) {
-        const long long li = l4 + g;
-        const bool have = li < n_leaves;
-        int32_t *rec = R.leaves + (have ? li : 0) * M.rec_words;
+        const long long it = l4 + g;
+        const bool have = it < n_leaves;
+        long long li = have ? it : 0;
+        if (ROUTE && R.list) li = R.list[li];
+        int32_t *rec = ROUTE ? R.leaves + li * M.rec_words : const_cast<int32_t *>(P.records) + li * M.rec_words;
         // ---- route (reference src/solveralgorithm.cpp:755-837)
         int ncid = -1, nexp = 0;
         bool routed = false;
+        uint32_t h = 0;
+        if (!ROUTE) {
+            if (have) { ncid = rec[1]; nexp = rec[2]; h = (uint32_t)rec[3]; }
+            routed = have;
+        } else {
         if (have) {
             const int cid = rec[1];
             nexp = rec[2];
@@ -1434,16 +1451,16 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
                 if (gl == 0) {
                     if (R.capmap_mask >= 0) {
                         const int32_t *cap = M.aux + S.cap_off;
-                        uint32_t h = cap_hash_begin(cid);
-                        for (int i = 0; i < S.n_cap; i++) h = cap_hash_step(h, rec[4 + cap[i]]);
-                        h = cap_hash_end(h) & (uint32_t)R.capmap_mask;
+                        uint32_t ch = cap_hash_begin(cid);
+                        for (int i = 0; i < S.n_cap; i++) ch = cap_hash_step(ch, rec[4 + cap[i]]);
+                        ch = cap_hash_end(ch) & (uint32_t)R.capmap_mask;
                         for (;;) {
-                            const CapEntry e = R.capmap[h];
+                            const CapEntry e = R.capmap[ch];
                             if (e.cid == -1) break;
                             bool eq = e.cid == cid;
                             for (int i = 0; eq && i < S.n_cap; i++) eq = R.capvals[e.off + i] == rec[4 + cap[i]];
                             if (eq) { ncid = e.next; break; }
-                            h = (h + 1) & (uint32_t)R.capmap_mask;
+                            ch = (ch + 1) & (uint32_t)R.capmap_mask;
                         }
                     }
                     if (ncid < 0) {
@@ -1456,7 +1473,6 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
         }
         ncid = __shfl_sync(0xffffffffu, ncid, lead);
         routed = have && ncid >= 0;
-        uint32_t h = 0;
         if (routed) {
             const DevSet NS = M.sets[ncid];
             for (int u = 0; u < NS.n_until; u++)
@@ -1472,10 +1488,15 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
             rec[2] = nexp;
             rec[3] = (int32_t)h;
         }
-        {   // one counter update per warp, not per leaf: these are single-address atomics
+        if (M.world <= 1) {   // one counter update per warp, not per leaf: these are single-address atomics
             const unsigned rb = __ballot_sync(0xffffffffu, routed && gl == 0);
             if (lane == 0 && rb) atomicAdd(&R.counters[C_OWNER0], (unsigned long long)__popc(rb));
+        } else if (routed && gl == 0) {
+            atomicAdd(&R.counters[C_OWNER0 + leaf_owner(M, ncid, h)], 1ull);
         }
+        }
+        if (!INGEST) continue;
+        __syncwarp();
         // ---- find or insert the successor state (reference vertexTableGetVertex / AddVertex)
         long long slot = (long long)h & P.table_mask;
         int dst = -1;
@@ -1564,6 +1585,22 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
     }
     st_dom = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_dom);
     if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+}
+
+// Step-wise launches (multi-GPU sessions, profile_kernels): wide lists take the four-per-warp path too.
+__device__ __forceinline__ bool wide_leaf_list(const DevModel &M, long long n) {
+    return n >= 4ll * ((long long)gridDim.x * blockDim.x >> 5) || M.force_mode == EXPAND_QUAD + 1;
+}
+
+__global__ void __launch_bounds__(256) route_kernel(const DevModel M, const RouteArgs P) {
+    const long long n = P.list ? P.count : (long long)P.counters[C_LEAVES];
+    if (wide_leaf_list(M, n)) leaf_body_quad<true, false>(M, P, IngestArgs{}, n);
+    else route_body(M, P);
+}
+
+__global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const IngestArgs P) {
+    if (wide_leaf_list(M, P.count)) leaf_body_quad<false, true>(M, RouteArgs{}, P, P.count);
+    else ingest_body(M, P);
 }
 
 // ---- the whole wave loop in one cooperative launch -------------------------------------------------------
@@ -1758,7 +1795,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         ia.out_cap = A.out_cap;
         ia.counters = A.counters;
         if (n_leaves >= 4ll * kExpandWarps * gridDim.x || M.force_mode == EXPAND_QUAD + 1)
-            leaf_body_quad(M, ra, ia, n_leaves);        // four leaves per warp
+            leaf_body_quad<true, true>(M, ra, ia, n_leaves);    // four leaves per warp
         else leaf_body(M, ra, ia, n_leaves);            // route + ingest in one pass
         grid.sync();
         stamp(2);

@@ -12,9 +12,9 @@ from stcsp_solver_b200 import binding
 pytestmark = pytest.mark.gpu
 
 
-def solve_sharded_on_one_gpu(model, world, merge="device"):
+def solve_sharded_on_one_gpu(model, world, merge="device", **options):
     dev = torch.device("cuda", 0)
-    opts = binding.default_options(device=0)
+    opts = binding.default_options(device=0, **options)
     sessions = [binding.Session(model, opts, r, world) for r in range(world)]
     words = sessions[0].record_words
     frontier = [1] + [0] * (world - 1)
@@ -81,6 +81,16 @@ def test_sharded_search_matches_reference(name, world):
     assert sol.canonical_sha256() == g["sha256"]
 
 
+@pytest.mark.parametrize("name", ["juggling_b5_f6", "digitinvader3", "partialorder_11", "probe_first_capture",
+                                  "probe_until_two", "probe_stateless"])
+def test_sharded_search_four_leaves_per_warp(name):
+    """expand_mode=3 also forces the four-leaves-per-warp route and ingest kernels, whatever the wave width."""
+    g = GOLDENS[name]
+    model = binding.Model(golden_text(g))
+    sol = binding.Solution(model, solve_sharded_on_one_gpu(model, 3, expand_mode=3))
+    assert sol.canonical_sha256() == g["sha256"]
+
+
 @pytest.mark.parametrize("name", ["juggling_b4_f6", "probe_dead_branch", "partialorder_10"])
 def test_host_assembly_equals_device_merge(name):
     g = GOLDENS[name]
@@ -101,5 +111,5 @@ def test_sharded_search_on_random_models(seed):
     if oracle_automaton is None:
         pytest.skip("oracle needs more than 2 s")
     want = binding.Solution(model, oracle_automaton).canonical_text()
-    got = binding.Solution(model, solve_sharded_on_one_gpu(model, 3)).canonical_text()
+    got = binding.Solution(model, solve_sharded_on_one_gpu(model, 3, expand_mode=3 if seed % 2 else 0)).canonical_text()
     assert got == want
