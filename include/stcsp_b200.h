@@ -105,7 +105,9 @@ typedef struct stcsp_options {
     int32_t lookahead;               /* pointwise constraints at time offsets >= 1: 0 default, 1 eager (propagated like the
                                         current point, the reference's prefix-k consistency), 2 lazy (checked once, when every
                                         variable of the current point is bound).  Never changes the automaton. */
-    int32_t reserved[4];
+    int32_t wide_wave_nodes;         /* waves wider than this run as separate full-occupancy launches instead of inside the
+                                        persistent search kernel: 0 = default (32768), < 0 = never */
+    int32_t reserved[3];
 } stcsp_options_t;
 
 /* ---------------------------------------------------------------------------------------------

@@ -168,7 +168,7 @@ struct NodeCtx {
     u64 *dom;
     int lane;
     int expire;
-    unsigned long long tuples;
+    unsigned tuples;            // per launch and thread: 32 bits are plenty, and registers are scarce here
     unsigned long long *dbg;    // timeline of this node's propagation (one thread writes), or nullptr
     int dbg_cap;
 };
@@ -556,7 +556,7 @@ __device__ __forceinline__ bool scalar_shrink(const DevModel &M, const DevSet &S
 }
 
 __device__ int scalar_revise(const DevModel &M, const DevSet &S, int q, u64 *dom, uint32_t *dirty, int expire,
-                             unsigned long long &tuples) {
+                             unsigned &tuples) {
     const DevProp pr = M.props[S.prop_off + q];
     const DevCon con = M.cons[pr.con];
     const int k = M.k, off = pr.offset;
@@ -639,8 +639,7 @@ __device__ __forceinline__ uint32_t cheap_mask(const DevSet &S, int w) {
 //   phase B  what needs 32 lanes (bytecode enumerations, tables with many unbound variables): warp-cooperative,
 //            one at a time (warp per node) or dealt to the warps of the CTA (CTA per node); then back to A
 template <bool CTA>
-__device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned long long &st_rev,
-                          unsigned long long &my_tuples) {
+__device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned &st_rev, unsigned &my_tuples) {
     const DevModel &M = ctx.M;
     const DevSet &S = ctx.S;
     WarpMem &wm = ctx.wm;
@@ -833,7 +832,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
     const int gwarps = CTA ? kExpandWarps : 1;          // warps working on one node
     const int gw = CTA ? warp : 0;                      // this warp's index among them
     const int gtid = CTA ? threadIdx.x : lane, gthreads = gwarps * 32;
-    unsigned long long st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;
+    unsigned st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;    // per launch and thread
     // stage the constraint set of this CTA's first node (waves are almost always homogeneous)
     const long long probe = CTA ? (long long)blockIdx.x : (long long)blockIdx.x * kExpandWarps;
     const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1);
@@ -934,13 +933,13 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
         }
     }
     // st_rev / my_tuples are per thread (scalar revisions), st_tuples is warp-uniform (cooperative revisions)
-    st_rev = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_rev);
-    st_tuples += (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)my_tuples);
+    st_rev = __reduce_add_sync(0xffffffffu, st_rev);
+    st_tuples += __reduce_add_sync(0xffffffffu, my_tuples);
     if (lane == 0 && (st_nodes | st_tuples | st_rev)) {
-        if (st_nodes) atomicAdd(&P.counters[C_NODES], st_nodes);
-        if (st_fails) atomicAdd(&P.counters[C_FAILS], st_fails);
-        if (st_tuples) atomicAdd(&P.counters[C_TUPLES], st_tuples);
-        if (st_rev) atomicAdd(&P.counters[C_REVISIONS], st_rev);
+        if (st_nodes) atomicAdd(&P.counters[C_NODES], (unsigned long long)st_nodes);
+        if (st_fails) atomicAdd(&P.counters[C_FAILS], (unsigned long long)st_fails);
+        if (st_tuples) atomicAdd(&P.counters[C_TUPLES], (unsigned long long)st_tuples);
+        if (st_rev) atomicAdd(&P.counters[C_REVISIONS], (unsigned long long)st_rev);
     }
 }
 
@@ -954,7 +953,7 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
     WarpMem wm = carve(smem, Mg, warp * 4 + g, warp);           // my group's node slot, the warp's scratch
     const long long n_in = P.n_in;
     const int V = Mg.V, k = Mg.k, NW = Mg.node_words;
-    unsigned long long st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;
+    unsigned st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;    // per launch and thread
     const long long probe = (long long)blockIdx.x * kExpandWarps * 4;
     const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1);
     const DevModel &Ms = *reinterpret_cast<const DevModel *>(stage_base(smem, Mg));
@@ -1127,15 +1126,15 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
             }
         }
     }
-    st_rev = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_rev);
-    st_nodes = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_nodes);
-    st_fails = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_fails);
-    st_tuples += (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)my_tuples);
+    st_rev = __reduce_add_sync(0xffffffffu, st_rev);
+    st_nodes = __reduce_add_sync(0xffffffffu, st_nodes);
+    st_fails = __reduce_add_sync(0xffffffffu, st_fails);
+    st_tuples += __reduce_add_sync(0xffffffffu, my_tuples);
     if (lane == 0 && (st_nodes | st_tuples | st_rev)) {
-        if (st_nodes) atomicAdd(&P.counters[C_NODES], st_nodes);
-        if (st_fails) atomicAdd(&P.counters[C_FAILS], st_fails);
-        if (st_tuples) atomicAdd(&P.counters[C_TUPLES], st_tuples);
-        if (st_rev) atomicAdd(&P.counters[C_REVISIONS], st_rev);
+        if (st_nodes) atomicAdd(&P.counters[C_NODES], (unsigned long long)st_nodes);
+        if (st_fails) atomicAdd(&P.counters[C_FAILS], (unsigned long long)st_fails);
+        if (st_tuples) atomicAdd(&P.counters[C_TUPLES], (unsigned long long)st_tuples);
+        if (st_rev) atomicAdd(&P.counters[C_REVISIONS], (unsigned long long)st_rev);
     }
 }
 
@@ -1612,46 +1611,48 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     volatile SearchCtl *ctl = A.ctl;                    // written by one thread, read by all after a grid barrier
     volatile unsigned long long *cnt = A.counters;
-    const bool tracer = A.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-    long long wave = 0;
+    // The controller (thread 0 of block 0) carries the wave state and the running totals in SHARED memory: nothing of it
+    // may stay live in registers across the expand bodies, whose inner loops need every register the launch bounds
+    // allow.  The control block in global memory is written once per wave (status, n_in, cur) and the totals only
+    // when the kernel returns.
+    enum { S_N_IN, S_STATES, S_EDGES, S_WAVES_LEFT, S_NODES, S_FAILS, S_TUPLES, S_REV, S_DOM, S_LEAVES, S_WAVES, S_CUR,
+           S_OVERFLOW, S_WAVE, S_COUNT };
+    __shared__ long long cs[S_COUNT];
+    const bool controller = blockIdx.x == 0 && threadIdx.x == 0;
     auto stamp = [&](int k) {
-        if (tracer && wave < A.trace_cap) {
+        if (A.trace != nullptr && controller && cs[S_WAVE] < A.trace_cap) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            A.trace[wave * 5 + k] = t;
+            A.trace[cs[S_WAVE] * 5 + k] = t;
         }
     };
-    // The controller (thread 0 of block 0) carries the wave state and the running totals in registers; the control
-    // block in memory is written once per wave (status, n_in, cur) and the totals only when the kernel returns.
-    const bool controller = blockIdx.x == 0 && threadIdx.x == 0;
-    long long c_n_in = 0, c_states = 0, c_edges = 0, c_waves_left = 0;
-    long long a_nodes = 0, a_fails = 0, a_tuples = 0, a_rev = 0, a_dom = 0, a_leaves = 0, a_waves = 0;
-    int c_cur = 0, a_overflow = 0;
     if (controller) {
-        c_n_in = ctl->n_in;
-        c_cur = ctl->cur;
-        c_waves_left = ctl->waves_left;
-        c_states = (long long)cnt[C_STATES];
-        c_edges = (long long)cnt[C_EDGES];
+        for (int i = 0; i < S_COUNT; i++) cs[i] = 0;
+        cs[S_N_IN] = ctl->n_in;
+        cs[S_CUR] = ctl->cur;
+        cs[S_WAVES_LEFT] = ctl->waves_left;
+        cs[S_STATES] = (long long)cnt[C_STATES];
+        cs[S_EDGES] = (long long)cnt[C_EDGES];
     }
     auto flush_totals = [&]() {         // controller only, before the kernel returns
-        ctl->t_nodes = a_nodes; ctl->t_fails = a_fails; ctl->t_tuples = a_tuples; ctl->t_revisions = a_rev;
-        ctl->t_dominance = a_dom; ctl->t_leaves = a_leaves; ctl->t_waves = a_waves;
-        ctl->waves_left = c_waves_left;
-        ctl->overflow = a_overflow;
+        ctl->t_nodes = cs[S_NODES]; ctl->t_fails = cs[S_FAILS]; ctl->t_tuples = cs[S_TUPLES]; ctl->t_revisions = cs[S_REV];
+        ctl->t_dominance = cs[S_DOM]; ctl->t_leaves = cs[S_LEAVES]; ctl->t_waves = cs[S_WAVES];
+        ctl->waves_left = cs[S_WAVES_LEFT];
+        ctl->overflow = (int)cs[S_OVERFLOW];
     };
     for (;;) {
         // ---- wave start: can this wave run without the host?
         if (controller) {
+            const long long c_n_in = cs[S_N_IN], c_states = cs[S_STATES], c_edges = cs[S_EDGES];
             int st = SEARCH_RUN;
             if (c_n_in == 0) st = SEARCH_DONE;
-            else if (c_waves_left <= 0 || (A.max_frontier > 0 && c_n_in > A.max_frontier)) st = SEARCH_YIELD;
+            else if (cs[S_WAVES_LEFT] <= 0 || (A.max_frontier > 0 && c_n_in > A.max_frontier)) st = SEARCH_YIELD;
             else if (c_n_in > A.leaf_cap || c_n_in > A.unresolved_cap || c_states + c_n_in > A.state_cap ||
                      c_edges + c_n_in > A.edge_cap || 2 * (c_states + c_n_in) > A.table_mask + 1 || 2 * c_n_in > A.out_cap)
                 st = SEARCH_GROW;
             ctl->status = st;
             ctl->n_in = c_n_in;
-            ctl->cur = c_cur;
+            ctl->cur = (int)cs[S_CUR];
             if (st != SEARCH_RUN) flush_totals();
         }
         grid.sync();
@@ -1737,19 +1738,23 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         }
         if (ctl->status != SEARCH_RUN) return;
         stamp(0);
-        const long long n_in = ctl->n_in;
-        const int cur = ctl->cur;
-        ExpandArgs ea;
-        ea.in_nodes = A.frontier[cur];
-        ea.n_in = n_in;
-        ea.out_nodes = A.frontier[cur ^ 1];
-        ea.out_cap = A.out_cap;
-        ea.leaves = A.leaves;
-        ea.leaf_cap = A.leaf_cap;
-        ea.counters = A.counters;
-        ea.dbg = A.trace ? A.trace + 5 * A.trace_cap : nullptr;     // block 0's timeline follows the per-wave stamps
-        ea.dbg_cap = A.trace ? 4096 : 0;
-        const int mode = pick_expand_mode(M, n_in, gridDim.x);
+        // The wave's arguments live in shared memory: as a local struct their fields stay in registers right through
+        // the expand bodies (in the stand-alone kernels they are launch parameters, i.e. constant-bank operands).
+        __shared__ ExpandArgs ea;
+        if (threadIdx.x == 0) {
+            const int cur = ctl->cur;
+            ea.in_nodes = A.frontier[cur];
+            ea.n_in = ctl->n_in;
+            ea.out_nodes = A.frontier[cur ^ 1];
+            ea.out_cap = A.out_cap;
+            ea.leaves = A.leaves;
+            ea.leaf_cap = A.leaf_cap;
+            ea.counters = A.counters;
+            ea.dbg = A.trace ? A.trace + 5 * A.trace_cap : nullptr;     // block 0's timeline follows the per-wave stamps
+            ea.dbg_cap = A.trace ? 4096 : 0;
+        }
+        __syncthreads();
+        const int mode = pick_expand_mode(M, ea.n_in, gridDim.x);
         if (mode == EXPAND_CTA) expand_body<true>(M, ea, smem);
         else if (mode == EXPAND_QUAD) expand_body_quad(M, ea, smem);
         else expand_body<false>(M, ea, smem);
@@ -1791,7 +1796,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         ia.edge_dst = A.edge_dst;
         ia.edge_label = A.edge_label;
         ia.edge_cap = A.edge_cap;
-        ia.out_nodes = A.frontier[cur ^ 1];
+        ia.out_nodes = A.frontier[ctl->cur ^ 1];
         ia.out_cap = A.out_cap;
         ia.counters = A.counters;
         if (n_leaves >= 4ll * kExpandWarps * gridDim.x || M.force_mode == EXPAND_QUAD + 1)
@@ -1820,21 +1825,23 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             const long long v_ovf = (long long)__shfl_sync(0xffffffffu, c, C_OVERFLOW);
             const long long v_states = (long long)__shfl_sync(0xffffffffu, c, C_STATES);
             const long long v_edges = (long long)__shfl_sync(0xffffffffu, c, C_EDGES);
+            const long long v_leaves = (long long)__shfl_sync(0xffffffffu, c, C_LEAVES);
             if (ln == 0) {
-                a_nodes += v_nodes; a_fails += v_fails; a_tuples += v_tuples; a_rev += v_rev; a_dom += v_dom;
-                a_leaves += n_leaves;
-                a_waves += 1;
-                a_overflow |= (int)v_ovf;
-                c_waves_left -= 1;
-                c_n_in = v_out;
-                c_cur = cur ^ 1;
-                c_states = v_states;
-                c_edges = v_edges;
+                cs[S_NODES] += v_nodes; cs[S_FAILS] += v_fails; cs[S_TUPLES] += v_tuples; cs[S_REV] += v_rev;
+                cs[S_DOM] += v_dom;
+                cs[S_LEAVES] += v_leaves;
+                cs[S_WAVES] += 1;
+                cs[S_OVERFLOW] |= v_ovf;
+                cs[S_WAVES_LEFT] -= 1;
+                cs[S_N_IN] = v_out;
+                cs[S_CUR] ^= 1;
+                cs[S_STATES] = v_states;
+                cs[S_EDGES] = v_edges;
             }
             static_assert(C_COUNT <= 32, "one warp reads all counters");
         }       // (the grid barrier at the top of the loop orders these writes before anybody reads them)
         stamp(4);
-        wave++;
+        if (controller) cs[S_WAVE]++;
         // the barrier at the top of the loop publishes the new control block
     }
 }

@@ -152,7 +152,7 @@ struct SearchArgs {
     long long state_cap;
     int32_t *edge_src, *edge_dst, *edge_label;
     long long edge_cap;
-    long long max_frontier;             // > 0: yield to the host when a wave is wider (it gives up there)
+    long long max_frontier;             // > 0: yield to the host when a wave is wider (it gives up, or runs the wave step-wise)
     FinishArgs fin;
     unsigned long long *trace;          // optional: 5 %globaltimer stamps per wave (start, expanded, routed, ingested, end)
     long long trace_cap;                // in waves

@@ -370,6 +370,8 @@ struct stcsp_session {
     DBuf<int32_t> fb_deg, fb_first, fb_fill, fb_outdeg, fb_src, fb_dst, fb_label, fb_cset, fb_sig, fb_flags;
     DBuf<uint8_t> fb_failed, fb_alive, fb_scan;
     bool finish_in_kernel = false, finish_trim = true;     // set by stcsp_gpu_solve (single rank)
+    bool time_expand = false;                               // expand launches of run_persistent's wide waves are timed
+    static constexpr long long kWideWaveNodes = 32768;     // default of stcsp_options_t::wide_wave_nodes
     bool prefinished = false;       // the search kernel already grouped + trimmed (fb_* hold the result)
     long long prefinished_dead = 0;
     SearchCtl *h_ctl = nullptr;     // pinned, behind h_counters
@@ -673,7 +675,8 @@ struct stcsp_session {
             sa.edge_dst = edge_dst.p;
             sa.edge_label = edge_label.p;
             sa.edge_cap = (long long)std::min(edge_src.cap, edge_label.cap / (size_t)V);
-            sa.max_frontier = opt.max_frontier_nodes;
+            const long long wide = opt.wide_wave_nodes < 0 ? 0 : opt.wide_wave_nodes > 0 ? opt.wide_wave_nodes : kWideWaveNodes;
+            sa.max_frontier = opt.max_frontier_nodes > 0 && (wide == 0 || opt.max_frontier_nodes < wide) ? opt.max_frontier_nodes : wide;
             // automata known (from the last solve of this model) to be small are finished inside the kernel
             if (finish_in_kernel && model->hint_states > 0 && model->hint_edges <= (1ll << 18)) {
                 const long long cs = std::max<long long>(model->hint_states, 4096), ce = std::max<long long>(model->hint_edges, 8192);
@@ -773,6 +776,22 @@ struct stcsp_session {
                     prefinished_dead = h_ctl->dead_edges;
                     break;
                 case SEARCH_YIELD:
+                    // Waves this wide run faster as separate launches: the stand-alone expand kernels keep their inner
+                    // loops in registers (inside search_kernel ptxas spills there) and route/ingest run at full occupancy;
+                    // at this width the launches and the two host round trips per wave no longer matter.
+                    while (wide > 0 && n_in > wide && !(opt.max_frontier_nodes > 0 && n_in > opt.max_frontier_nodes)) {
+                        if (deadline > 0 && now_s() > deadline) throw Failure(STCSP_ERR_TIMEOUT, "time limit reached");
+                        int64_t nl = 0, np = 0, next = 0;
+                        time_expand = true;
+                        expand(&nl, &np);
+                        time_expand = false;
+                        if (np > 0) {
+                            std::vector<int32_t> req = pending;
+                            resolve(req.data(), np);
+                        }
+                        ingest(nullptr, 0, &next);
+                        zero_wave_counters();
+                    }
                     break;
                 case SEARCH_GROW:
                     ensure_wave_capacity(n_in);
@@ -885,9 +904,9 @@ struct stcsp_session {
                 const int grid = mode == EXPAND_CTA ? (int)std::min<long long>(n_in, expand_grid_max)
                                : mode == EXPAND_QUAD ? (int)std::min<long long>((n_in + 4 * kExpandWarps - 1) / (4 * kExpandWarps), expand_grid_max)
                                                      : (int)std::min<long long>((n_in + kExpandWarps - 1) / kExpandWarps, expand_grid_max);
-                if (opt.profile_kernels) CK(cudaEventRecord(evk0, stream));
+                if (opt.profile_kernels || time_expand) CK(cudaEventRecord(evk0, stream));
                 launch_expand(dm, ea, grid, mode, stream);
-                if (opt.profile_kernels) CK(cudaEventRecord(evk1, stream));
+                if (opt.profile_kernels || time_expand) CK(cudaEventRecord(evk1, stream));
                 RouteArgs ra{};
                 ra.leaves = leaves.p;
                 ra.list = nullptr;
@@ -907,7 +926,7 @@ struct stcsp_session {
                     fprintf(stderr, "[stcsp r%d]   expand kernel wall %.1f us, route+read %.1f us\n", rank, (te2 - te1) * 1e6, (now_s() - te2) * 1e6);
                 t_launches += 2;
                 t_expand_launches++;
-                if (opt.profile_kernels) {
+                if (opt.profile_kernels || time_expand) {
                     float ms = 0;
                     CK(cudaEventElapsedTime(&ms, evk0, evk1));
                     expand_ms += ms;

@@ -23,7 +23,8 @@ def test_random_model_matches_oracle(seed):
         pytest.skip("oracle needs more than 5 s")
     want = binding.Solution(model, oracle_automaton).canonical_text()
     variants = [dict(), dict(lookahead=2), dict(profile_kernels=1), dict(enum_limit_now=4096, enum_limit_ahead=4096),
-                dict(expand_mode=3), dict(expand_mode=1), dict(expand_mode=2, profile_kernels=1), dict(expand_mode=3, profile_kernels=1)]
+                dict(expand_mode=3), dict(expand_mode=1), dict(expand_mode=2, profile_kernels=1), dict(expand_mode=3, profile_kernels=1),
+                dict(wide_wave_nodes=2), dict(wide_wave_nodes=8, expand_mode=3), dict(wide_wave_nodes=-1)]
     for kw in [variants[0], variants[1 + seed % (len(variants) - 1)]]:
         try:
             automaton = binding.solve(model, binding.default_options(**kw))

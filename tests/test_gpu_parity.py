@@ -96,6 +96,20 @@ def test_every_node_mapping_gives_the_same_automaton(name, mode):
         assert sol.canonical_sha256() == g["sha256"], (name, mode, extra)
 
 
+@pytest.mark.parametrize("wide", [1, 64, 4096, -1])
+@pytest.mark.parametrize("name", ["juggling_b5_f6_nosym", "digitinvader4", "partialorder_13", "probe_until_two", "probe_first_capture"])
+def test_wide_waves_leaving_the_persistent_kernel(name, wide):
+    """wide_wave_nodes: waves wider than this run as stand-alone launches between two runs of the search kernel;
+    the automaton and the search statistics do not depend on where the switch happens."""
+    g = GOLDENS[name]
+    _, base, _ = run_gpu(golden_text(g), ())
+    _, automaton, sol = run_gpu(golden_text(g), (), wide_wave_nodes=wide)
+    assert sol.canonical_sha256() == g["sha256"], (name, wide)
+    st0, st1 = base.stats(), automaton.stats()
+    for key in ("n_states", "n_edges", "n_search_nodes", "n_fails", "n_leaves", "n_dominance", "n_waves"):
+        assert st0[key] == st1[key], (key, wide)
+
+
 def test_session_api_single_rank_matches_solve():
     """create / expand / [resolve] / ingest / finish / assemble / trim by hand == stcsp_gpu_solve."""
     g = GOLDENS["probe_first_capture"]
