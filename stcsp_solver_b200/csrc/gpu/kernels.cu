@@ -1320,7 +1320,7 @@ __device__ __forceinline__ void ingest_leaf(const DevModel &M, const IngestArgs 
         v = __shfl_sync(0xffffffffu, v, 0);
         if (v == -1) {                                // slot claimed: this leaf creates the state
             unsigned long long id = 0;
-            if (lane == 0) id = atomicAdd(&P.counters[C_STATES], 1ull);
+            if (lane == 0) id = atomicAdd(&P.totals[C_STATES], 1ull);
             id = __shfl_sync(0xffffffffu, id, 0);
             if ((long long)id >= P.state_cap) {
                 if (lane == 0) { atomicOr(&P.counters[C_OVERFLOW], 4ull); atomicExch(&P.table[slot], -3); }
@@ -1357,10 +1357,10 @@ __device__ __forceinline__ void ingest_leaf(const DevModel &M, const IngestArgs 
         // first search node of the new state: next-linked variables take the values just chosen,
         // everything else restarts from its declared range
         unsigned long long o = 0;
-        if (lane == 0) o = atomicAdd(&P.counters[C_OUT], 1ull);
+        if (lane == 0) o = (unsigned long long)P.out_base + atomicAdd(&P.counters[C_NEW], 1ull);
         o = __shfl_sync(0xffffffffu, o, 0);
         if ((long long)o >= P.out_cap) {
-            if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
+            if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 32ull);
         } else {
             int32_t *node = P.out_nodes + o * NW;
             if (lane == 0) { node[0] = dst_global; node[1] = ncid; node[2] = nexp; node[3] = -1; }
@@ -1382,7 +1382,7 @@ __device__ __forceinline__ void ingest_leaf(const DevModel &M, const IngestArgs 
         st_dom++;
     }
     unsigned long long e = 0;
-    if (lane == 0) e = atomicAdd(&P.counters[C_EDGES], 1ull);
+    if (lane == 0) e = atomicAdd(&P.totals[C_EDGES], 1ull);
     e = __shfl_sync(0xffffffffu, e, 0);
     if ((long long)e >= P.edge_cap) {
         if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 8ull);
@@ -1506,7 +1506,7 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
             v = __shfl_sync(0xffffffffu, v, lead);
             if (searching && v == -1) {                     // slot claimed: this leaf creates the state
                 unsigned long long id = 0;
-                if (gl == 0) id = atomicAdd(&P.counters[C_STATES], 1ull);
+                if (gl == 0) id = atomicAdd(&P.totals[C_STATES], 1ull);
                 id = __shfl_sync(gmask, id, lead);
                 if ((long long)id >= P.state_cap) {
                     if (gl == 0) { atomicOr(&P.counters[C_OVERFLOW], 4ull); atomicExch(&P.table[slot], -3); }
@@ -1541,8 +1541,8 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
             const unsigned rb = __ballot_sync(0xffffffffu, routed && gl == 0);
             const unsigned nb = __ballot_sync(0xffffffffu, routed && is_new && gl == 0);
             if (lane == 0) {
-                if (rb) e = atomicAdd(&P.counters[C_EDGES], (unsigned long long)__popc(rb));
-                if (nb) o = atomicAdd(&P.counters[C_OUT], (unsigned long long)__popc(nb));
+                if (rb) e = atomicAdd(&P.totals[C_EDGES], (unsigned long long)__popc(rb));
+                if (nb) o = (unsigned long long)P.out_base + atomicAdd(&P.counters[C_NEW], (unsigned long long)__popc(nb));
             }
             const unsigned below = (1u << lead) - 1u;
             e = __shfl_sync(0xffffffffu, e, 0) + (unsigned long long)__popc(rb & below);
@@ -1552,7 +1552,7 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
             const int dst_global = dst * M.world + M.rank;
             if (is_new) {
                 if ((long long)o >= P.out_cap) {
-                    if (gl == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
+                    if (gl == 0) atomicOr(&P.counters[C_OVERFLOW], 32ull);
                 } else {
                     const DevSet NS = M.sets[ncid];
                     int32_t *node = P.out_nodes + o * NW;
@@ -1604,21 +1604,29 @@ __global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const Ing
 
 // ---- the whole wave loop in one cooperative launch -------------------------------------------------------
 // Waves of a small or deep search cost more in launches and host synchronisation than in work.  search_kernel
-// runs expand -> route -> ingest -> bookkeeping for wave after wave with grid-wide barriers in between and
-// returns to the host only when it is done or needs it (buffers to grow, an unseen constraint-set transition).
+// runs expand -> route + ingest -> bookkeeping for wave after wave and returns to the host only when it is done or
+// needs it (buffers to grow, an unseen constraint-set transition, a wave wide enough for stand-alone launches).
+//
+// Grid barriers are what a narrow wave pays for, so there are as few as possible: ONE after expand, and one more after
+// the leaf phase only if the wave produced leaves.  There is no controller block: every block keeps the wave state in
+// its own shared memory and takes every decision itself, from counters that are frozen while they are read, so all
+// blocks decide alike without another barrier.  That needs the wave counters THREE times over (wave w uses set w % 3):
+// block 0 clears the set of wave w-1 after the barrier of wave w -- every block has finished reading it by then --
+// and no block touches that set again before it has passed the barrier of wave w+1, which block 0 reaches only after
+// the clearing.  C_STATES and C_EDGES (never reset) live in set 0.
 __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevModel M, SearchArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    volatile SearchCtl *ctl = A.ctl;                    // written by one thread, read by all after a grid barrier
-    volatile unsigned long long *cnt = A.counters;
-    // The controller (thread 0 of block 0) carries the wave state and the running totals in SHARED memory: nothing of it
-    // may stay live in registers across the expand bodies, whose inner loops need every register the launch bounds
-    // allow.  The control block in global memory is written once per wave (status, n_in, cur) and the totals only
-    // when the kernel returns.
+    volatile SearchCtl *ctl = A.ctl;
+    volatile unsigned long long *tot = A.counters;
+    // Wave state and running totals of THIS block (thread 0), in shared memory: nothing of it may stay live in
+    // registers across the expand bodies, whose inner loops need every register the launch bounds allow.
     enum { S_N_IN, S_STATES, S_EDGES, S_WAVES_LEFT, S_NODES, S_FAILS, S_TUPLES, S_REV, S_DOM, S_LEAVES, S_WAVES, S_CUR,
            S_OVERFLOW, S_WAVE, S_COUNT };
     __shared__ long long cs[S_COUNT];
-    const bool controller = blockIdx.x == 0 && threadIdx.x == 0;
+    __shared__ ExpandArgs ea;           // the wave's arguments (launch parameters in the stand-alone kernels)
+    __shared__ int s_status, s_set;
+    const bool controller = blockIdx.x == 0 && threadIdx.x == 0;    // the one thread that reports to the host
     auto stamp = [&](int k) {
         if (A.trace != nullptr && controller && cs[S_WAVE] < A.trace_cap) {
             unsigned long long t;
@@ -1626,23 +1634,32 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             A.trace[cs[S_WAVE] * 5 + k] = t;
         }
     };
-    if (controller) {
+    if (threadIdx.x == 0) {
         for (int i = 0; i < S_COUNT; i++) cs[i] = 0;
         cs[S_N_IN] = ctl->n_in;
         cs[S_CUR] = ctl->cur;
         cs[S_WAVES_LEFT] = ctl->waves_left;
-        cs[S_STATES] = (long long)cnt[C_STATES];
-        cs[S_EDGES] = (long long)cnt[C_EDGES];
+        cs[S_STATES] = (long long)tot[C_STATES];
+        cs[S_EDGES] = (long long)tot[C_EDGES];
     }
-    auto flush_totals = [&]() {         // controller only, before the kernel returns
-        ctl->t_nodes = cs[S_NODES]; ctl->t_fails = cs[S_FAILS]; ctl->t_tuples = cs[S_TUPLES]; ctl->t_revisions = cs[S_REV];
-        ctl->t_dominance = cs[S_DOM]; ctl->t_leaves = cs[S_LEAVES]; ctl->t_waves = cs[S_WAVES];
-        ctl->waves_left = cs[S_WAVES_LEFT];
-        ctl->overflow = (int)cs[S_OVERFLOW];
+    // Leave the kernel (all threads call it, every block with the same status).  The host reads set 0.
+    auto leave = [&](int st, bool mid_wave) {
+        if (blockIdx.x != 0) return;
+        if (mid_wave && s_set != 0 && threadIdx.x >= C_OUT && threadIdx.x < C_COUNT)
+            A.counters[threadIdx.x] = A.counters[s_set * kCounterStride + threadIdx.x];
+        if (threadIdx.x == 0) {
+            ctl->status = st;
+            ctl->n_in = cs[S_N_IN];
+            ctl->cur = (int)cs[S_CUR];
+            ctl->t_nodes = cs[S_NODES]; ctl->t_fails = cs[S_FAILS]; ctl->t_tuples = cs[S_TUPLES]; ctl->t_revisions = cs[S_REV];
+            ctl->t_dominance = cs[S_DOM]; ctl->t_leaves = cs[S_LEAVES]; ctl->t_waves = cs[S_WAVES];
+            ctl->waves_left = cs[S_WAVES_LEFT];
+            ctl->overflow = (int)cs[S_OVERFLOW];
+        }
     };
     for (;;) {
         // ---- wave start: can this wave run without the host?
-        if (controller) {
+        if (threadIdx.x == 0) {
             const long long c_n_in = cs[S_N_IN], c_states = cs[S_STATES], c_edges = cs[S_EDGES];
             int st = SEARCH_RUN;
             if (c_n_in == 0) st = SEARCH_DONE;
@@ -1650,15 +1667,24 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             else if (c_n_in > A.leaf_cap || c_n_in > A.unresolved_cap || c_states + c_n_in > A.state_cap ||
                      c_edges + c_n_in > A.edge_cap || 2 * (c_states + c_n_in) > A.table_mask + 1 || 2 * c_n_in > A.out_cap)
                 st = SEARCH_GROW;
-            ctl->status = st;
-            ctl->n_in = c_n_in;
-            ctl->cur = (int)cs[S_CUR];
-            if (st != SEARCH_RUN) flush_totals();
+            s_status = st;
+            const int set = (int)(cs[S_WAVE] % 3), cur = (int)cs[S_CUR];
+            s_set = set;
+            ea.in_nodes = A.frontier[cur];
+            ea.n_in = c_n_in;
+            ea.out_nodes = A.frontier[cur ^ 1];
+            ea.out_cap = A.out_cap;
+            ea.leaves = A.leaves;
+            ea.leaf_cap = A.leaf_cap;
+            ea.counters = A.counters + set * kCounterStride;
+            ea.dbg = A.trace ? A.trace + 5 * A.trace_cap : nullptr;     // block 0's timeline follows the per-wave stamps
+            ea.dbg_cap = A.trace ? 4096 : 0;
         }
-        grid.sync();
-        if (ctl->status == SEARCH_DONE) {
+        __syncthreads();
+        if (s_status == SEARCH_DONE) {
+            leave(SEARCH_DONE, false);
             // ---- small automaton: group the edges by source and apply the fail rule right here (no further launches)
-            const long long ns = (long long)cnt[C_STATES], ne = (long long)cnt[C_EDGES];
+            const long long ns = (long long)tot[C_STATES], ne = (long long)tot[C_EDGES];
             const FinishArgs &F = A.fin;
             if (F.deg == nullptr || ns > F.cap_states || ne > F.cap_edges) return;
             const int V = M.V, KW = M.key_words;
@@ -1736,87 +1762,70 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             if (gtid == 0) ctl->finished = 1;
             return;
         }
-        if (ctl->status != SEARCH_RUN) return;
+        if (s_status != SEARCH_RUN) { leave(s_status, false); return; }
         stamp(0);
-        // The wave's arguments live in shared memory: as a local struct their fields stay in registers right through
-        // the expand bodies (in the stand-alone kernels they are launch parameters, i.e. constant-bank operands).
-        __shared__ ExpandArgs ea;
-        if (threadIdx.x == 0) {
-            const int cur = ctl->cur;
-            ea.in_nodes = A.frontier[cur];
-            ea.n_in = ctl->n_in;
-            ea.out_nodes = A.frontier[cur ^ 1];
-            ea.out_cap = A.out_cap;
-            ea.leaves = A.leaves;
-            ea.leaf_cap = A.leaf_cap;
-            ea.counters = A.counters;
-            ea.dbg = A.trace ? A.trace + 5 * A.trace_cap : nullptr;     // block 0's timeline follows the per-wave stamps
-            ea.dbg_cap = A.trace ? 4096 : 0;
-        }
-        __syncthreads();
+        volatile unsigned long long *cnt = ea.counters;         // this wave's counter set
         const int mode = pick_expand_mode(M, ea.n_in, gridDim.x);
         if (mode == EXPAND_CTA) expand_body<true>(M, ea, smem);
         else if (mode == EXPAND_QUAD) expand_body_quad(M, ea, smem);
         else expand_body<false>(M, ea, smem);
         grid.sync();
         stamp(1);
-        // ---- the frontier buffer overflowed: only scratch was written, the host grows it and the wave runs again
-        if (cnt[C_OVERFLOW] & 1ull) {
-            if (controller) { ctl->status = SEARCH_RETRY; flush_totals(); }
-            return;
-        }
+        // the previous wave's counter set is no longer read by anybody: clear it for the wave after this one
+        // (the same threads that copy the current set for the host when the kernel leaves in mid-wave: program order)
+        if (blockIdx.x == 0 && threadIdx.x >= C_OUT && threadIdx.x < C_COUNT)
+            A.counters[((s_set + 2) % 3) * kCounterStride + threadIdx.x] = 0ull;
         // Every block must take the same exit decisions, so they may only depend on values that no block is changing
-        // while they are read: C_OUT is frozen during route (ingest moves it again), C_LEAVES after expand,
-        // C_UNRESOLVED after route.
-        const long long out_after_expand = (long long)cnt[C_OUT];
-        const long long n_leaves = (long long)cnt[C_LEAVES];
+        // while they are read: bit 0 of C_OVERFLOW, C_OUT and C_LEAVES are written by expand only (the leaf phase, which
+        // faster blocks may already be in, appends through C_NEW and flags its own overflow bit).
+        // ---- the frontier buffer overflowed: only scratch was written, the host grows it and the wave runs again
+        if (cnt[C_OVERFLOW] & 1ull) { leave(SEARCH_RETRY, true); return; }
+        const long long n_leaves = (long long)cnt[C_LEAVES], out_after_expand = (long long)cnt[C_OUT];
         if (out_after_expand + n_leaves > A.out_cap) {
             // no room for the first nodes of new states: the host grows the frontier and finishes the wave (route + ingest)
-            if (controller) { ctl->status = SEARCH_INGEST; flush_totals(); }
+            leave(SEARCH_INGEST, true);
             return;
         }
-        RouteArgs ra;
-        ra.leaves = A.leaves;
-        ra.list = nullptr;
-        ra.count = 0;
-        ra.capmap = A.capmap;
-        ra.capvals = A.capvals;
-        ra.capmap_mask = A.capmap_mask;
-        ra.unresolved = A.unresolved;
-        ra.unresolved_cap = A.unresolved_cap;
-        ra.counters = A.counters;
-        IngestArgs ia;
-        ia.records = A.leaves;
-        ia.count = n_leaves;
-        ia.table = A.table;
-        ia.table_mask = A.table_mask;
-        ia.state_key = A.state_key;
-        ia.state_cap = A.state_cap;
-        ia.edge_src = A.edge_src;
-        ia.edge_dst = A.edge_dst;
-        ia.edge_label = A.edge_label;
-        ia.edge_cap = A.edge_cap;
-        ia.out_nodes = A.frontier[ctl->cur ^ 1];
-        ia.out_cap = A.out_cap;
-        ia.counters = A.counters;
-        if (n_leaves >= 4ll * kExpandWarps * gridDim.x || M.force_mode == EXPAND_QUAD + 1)
-            leaf_body_quad<true, true>(M, ra, ia, n_leaves);    // four leaves per warp
-        else leaf_body(M, ra, ia, n_leaves);            // route + ingest in one pass
-        grid.sync();
+        if (n_leaves > 0) {
+            RouteArgs ra;
+            ra.leaves = A.leaves;
+            ra.list = nullptr;
+            ra.count = 0;
+            ra.capmap = A.capmap;
+            ra.capvals = A.capvals;
+            ra.capmap_mask = A.capmap_mask;
+            ra.unresolved = A.unresolved;
+            ra.unresolved_cap = A.unresolved_cap;
+            ra.counters = ea.counters;
+            IngestArgs ia;
+            ia.records = A.leaves;
+            ia.count = n_leaves;
+            ia.table = A.table;
+            ia.table_mask = A.table_mask;
+            ia.state_key = A.state_key;
+            ia.state_cap = A.state_cap;
+            ia.edge_src = A.edge_src;
+            ia.edge_dst = A.edge_dst;
+            ia.edge_label = A.edge_label;
+            ia.edge_cap = A.edge_cap;
+            ia.out_nodes = ea.out_nodes;
+            ia.out_base = out_after_expand;
+            ia.out_cap = A.out_cap;
+            ia.counters = ea.counters;
+            ia.totals = A.counters;
+            if (n_leaves >= 4ll * kExpandWarps * gridDim.x || M.force_mode == EXPAND_QUAD + 1)
+                leaf_body_quad<true, true>(M, ra, ia, n_leaves);    // four leaves per warp
+            else leaf_body(M, ra, ia, n_leaves);            // route + ingest in one pass
+            grid.sync();
+        }
         stamp(2);
         stamp(3);
-        if (cnt[C_UNRESOLVED] != 0ull) {
-            // leaves with an unseen constraint-set transition are still pending: the host resolves and ingests them
-            if (controller) { ctl->status = SEARCH_RESOLVE; flush_totals(); }
-            return;
-        }
-        // ---- wave end: totals, swap, reset the wave counters.  Warp 0 of block 0 reads the counters with one parallel
-        // load (a single thread would pay the L2 latency once per counter).
-        if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // ---- wave end: totals and the next wave's input, by warp 0 of EVERY block (one parallel load of all counters;
+        // they are frozen until the next wave's barrier has been passed)
+        if (threadIdx.x < 32) {
             const int ln = threadIdx.x;
-            const unsigned long long c = ln < C_COUNT ? cnt[ln] : 0ull;
-            if (ln >= C_OUT && ln < C_COUNT) cnt[ln] = 0ull;
-            const long long v_out = (long long)__shfl_sync(0xffffffffu, c, C_OUT);
+            const unsigned long long c = ln < C_COUNT ? (ln < C_OUT ? tot[ln] : cnt[ln]) : 0ull;
+            const long long v_out = (long long)(__shfl_sync(0xffffffffu, c, C_OUT) + __shfl_sync(0xffffffffu, c, C_NEW));
             const long long v_nodes = (long long)__shfl_sync(0xffffffffu, c, C_NODES);
             const long long v_fails = (long long)__shfl_sync(0xffffffffu, c, C_FAILS);
             const long long v_tuples = (long long)__shfl_sync(0xffffffffu, c, C_TUPLES);
@@ -1826,23 +1835,32 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             const long long v_states = (long long)__shfl_sync(0xffffffffu, c, C_STATES);
             const long long v_edges = (long long)__shfl_sync(0xffffffffu, c, C_EDGES);
             const long long v_leaves = (long long)__shfl_sync(0xffffffffu, c, C_LEAVES);
+            const long long v_unres = (long long)__shfl_sync(0xffffffffu, c, C_UNRESOLVED);
             if (ln == 0) {
-                cs[S_NODES] += v_nodes; cs[S_FAILS] += v_fails; cs[S_TUPLES] += v_tuples; cs[S_REV] += v_rev;
-                cs[S_DOM] += v_dom;
-                cs[S_LEAVES] += v_leaves;
-                cs[S_WAVES] += 1;
-                cs[S_OVERFLOW] |= v_ovf;
-                cs[S_WAVES_LEFT] -= 1;
-                cs[S_N_IN] = v_out;
-                cs[S_CUR] ^= 1;
-                cs[S_STATES] = v_states;
-                cs[S_EDGES] = v_edges;
+                s_status = v_unres != 0 ? SEARCH_RESOLVE : SEARCH_RUN;
+                if (v_unres == 0) {
+                    cs[S_NODES] += v_nodes; cs[S_FAILS] += v_fails; cs[S_TUPLES] += v_tuples; cs[S_REV] += v_rev;
+                    cs[S_DOM] += v_dom;
+                    cs[S_LEAVES] += v_leaves;
+                    cs[S_WAVES] += 1;
+                    cs[S_OVERFLOW] |= v_ovf;
+                    cs[S_WAVES_LEFT] -= 1;
+                    cs[S_N_IN] = v_out;
+                    cs[S_CUR] ^= 1;
+                    cs[S_STATES] = v_states;
+                    cs[S_EDGES] = v_edges;
+                }
             }
             static_assert(C_COUNT <= 32, "one warp reads all counters");
-        }       // (the grid barrier at the top of the loop orders these writes before anybody reads them)
+        }
+        __syncthreads();
+        if (s_status == SEARCH_RESOLVE) {
+            // leaves with an unseen constraint-set transition are still pending: the host resolves and ingests them
+            leave(SEARCH_RESOLVE, true);
+            return;
+        }
         stamp(4);
-        if (controller) cs[S_WAVE]++;
-        // the barrier at the top of the loop publishes the new control block
+        if (threadIdx.x == 0) cs[S_WAVE]++;
     }
 }
 

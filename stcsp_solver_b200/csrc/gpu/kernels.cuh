@@ -24,10 +24,11 @@ enum Counter : int {
     C_STATES = 0,      // states allocated on this rank
     C_EDGES,           // edges appended on this rank
     // per wave (zeroed by the host before each expand)
-    C_OUT,             // nodes written to the output frontier
+    C_OUT,             // nodes written to the output frontier by expand (frozen once expand is over)
+    C_NEW,             // first nodes of new states appended behind them by ingest
     C_LEAVES,          // leaf records written
     C_UNRESOLVED,      // leaves whose successor constraint set the host must compute
-    C_OVERFLOW,        // bit flags: 1 frontier, 2 leaves, 4 states, 8 edges, 16 unresolved list
+    C_OVERFLOW,        // bit flags: 1 frontier (expand), 2 leaves, 4 states, 8 edges, 16 unresolved list, 32 frontier (ingest)
     C_NODES,           // statistics: search nodes propagated
     C_FAILS,
     C_TUPLES,
@@ -36,6 +37,8 @@ enum Counter : int {
     C_OWNER0,          // C_OWNER0 + r: routed leaves owned by rank r
     C_COUNT = C_OWNER0 + 16
 };
+constexpr int kCounterStride = 32;      // the session's counter block holds three sets (see search_kernel)
+constexpr int kCounterSets = 3;
 constexpr int kMaxWorld = 16;
 
 struct DevModel {
@@ -103,8 +106,10 @@ struct IngestArgs {
     int32_t *edge_src, *edge_dst, *edge_label;
     long long edge_cap;
     int32_t *out_nodes;
+    long long out_base;             // nodes expand wrote (C_OUT after expand): new states' first nodes go behind them
     long long out_cap;
-    unsigned long long *counters;
+    unsigned long long *counters;   // the wave's counter set
+    unsigned long long *totals;     // C_STATES, C_EDGES: never reset (set 0 of the session's counter block)
 };
 
 // Control block of the persistent search kernel (device memory, mirrored to the host when the kernel returns).

@@ -518,7 +518,8 @@ struct stcsp_session {
     }
 
     void zero_wave_counters() {
-        CK(cudaMemsetAsync(counters.p + C_OUT, 0, (C_COUNT - C_OUT) * sizeof(unsigned long long), stream));
+        // all three sets of wave counters (search_kernel rotates through them; everything else uses set 0)
+        CK(cudaMemsetAsync(counters.p + C_OUT, 0, (kCounterSets * kCounterStride - C_OUT) * sizeof(unsigned long long), stream));
     }
     void read_counters() {
         CK(cudaMemcpyAsync(h_counters, counters.p, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -587,8 +588,8 @@ struct stcsp_session {
         }
         if (!model->uploaded || model->sets.dirty()) upload_model();
         else refresh_model();
-        counters.reserve(C_COUNT, 0, stream);
-        CK(cudaMemsetAsync(counters.p, 0, C_COUNT * sizeof(unsigned long long), stream));
+        counters.reserve(kCounterSets * kCounterStride, 0, stream);
+        CK(cudaMemsetAsync(counters.p, 0, kCounterSets * kCounterStride * sizeof(unsigned long long), stream));
         h_counters = pinned_cache().acquire();       // C_COUNT counters + room for the search control block
         d_offsets.reserve(2 * kMaxWorld, 0, stream);
 
@@ -649,7 +650,6 @@ struct stcsp_session {
     void run_persistent(double deadline) {
         begin_timing();
         const int NW = dm.node_words, KW = dm.key_words, V = dm.V, RW = dm.rec_words;
-        zero_wave_counters();
         while (n_in > 0) {
             if (deadline > 0 && now_s() > deadline) throw Failure(STCSP_ERR_TIMEOUT, "time limit reached");
             if (opt.max_frontier_nodes > 0 && n_in > opt.max_frontier_nodes)
@@ -713,6 +713,7 @@ struct stcsp_session {
             h_ctl->status = SEARCH_RUN;
             h_ctl->waves_left = deadline > 0 ? 256 : (1ll << 40);
             CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof *h_ctl, cudaMemcpyHostToDevice, stream));
+            zero_wave_counters();
             CK(cudaEventRecord(evk0, stream));
             CK(launch_search(dm, sa, search_grid, stream));
             CK(cudaEventRecord(evk1, stream));
@@ -820,7 +821,7 @@ struct stcsp_session {
                         read_counters();
                         t_launches++;
                     }
-                    n_out = (long long)h_counters[C_OUT];
+                    n_out = (long long)(h_counters[C_OUT] + h_counters[C_NEW]);
                     n_leaves = (long long)h_counters[C_LEAVES];
                     n_unres = (long long)h_counters[C_UNRESOLVED];
                     t_nodes += (long long)h_counters[C_NODES];
@@ -843,7 +844,7 @@ struct stcsp_session {
                                           (int)std::min<long long>((listed + 7) / 8, sm_count * 8), stream);
                             t_launches++;
                             CK(cudaMemsetAsync(counters.p + C_DOMINANCE, 0, sizeof(unsigned long long), stream));
-                            n_out = (long long)h_counters[C_OUT];
+                            n_out = (long long)(h_counters[C_OUT] + h_counters[C_NEW]);
                             n_states = (long long)h_counters[C_STATES];
                             n_edges = (long long)h_counters[C_EDGES];
                             int64_t next = 0;
@@ -945,7 +946,7 @@ struct stcsp_session {
                 if (ov) throw Failure(STCSP_ERR_CAPACITY, "internal: leaf buffers overflowed");
                 break;
             }
-            n_out = (long long)h_counters[C_OUT];
+            n_out = (long long)(h_counters[C_OUT] + h_counters[C_NEW]);
             n_leaves = (long long)h_counters[C_LEAVES];
             n_unres = (long long)h_counters[C_UNRESOLVED];
             t_nodes += (long long)h_counters[C_NODES];
@@ -1112,14 +1113,16 @@ struct stcsp_session {
             ia.edge_label = edge_label.p;
             ia.edge_cap = (long long)std::min(edge_src.cap, edge_label.cap / (size_t)V);
             ia.out_nodes = out.p;
+            ia.out_base = (long long)h_counters[C_OUT];         // what expand wrote; C_NEW counts on from earlier ingests of this wave
             ia.out_cap = (long long)(out.cap / NW);
             ia.counters = counters.p;
+            ia.totals = counters.p;
             launch_ingest(dm, ia, (int)std::min<long long>((n + 7) / 8, sm_count * 8), stream);
             CK(cudaGetLastError());
             read_counters();
             t_launches++;
             if (h_counters[C_OVERFLOW]) throw Failure(STCSP_ERR_CAPACITY, "internal: automaton pools overflowed during ingest");
-            n_out = (long long)h_counters[C_OUT];
+            n_out = (long long)(h_counters[C_OUT] + h_counters[C_NEW]);
             n_states = (long long)h_counters[C_STATES];
             n_edges = (long long)h_counters[C_EDGES];
             t_dominance += (long long)h_counters[C_DOMINANCE];
