@@ -1660,6 +1660,46 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             ctl->overflow = (int)cs[S_OVERFLOW];
         }
     };
+    // Warp 0: one parallel load of the wave's counters (frozen while it runs).  after_expand: publish expand's results
+    // for the block's decisions, and if the wave has no leaves finish it right away; else: end of a wave with leaves.
+    __shared__ long long s_leaves, s_out;
+    __shared__ int s_ovf;
+    auto wave_counters = [&](volatile unsigned long long *cnt, bool after_expand) {
+        const int ln = threadIdx.x;
+        const unsigned long long c = ln < C_COUNT ? (ln < C_OUT ? tot[ln] : cnt[ln]) : 0ull;
+        const long long v_out = (long long)__shfl_sync(0xffffffffu, c, C_OUT);
+        const long long v_new = (long long)__shfl_sync(0xffffffffu, c, C_NEW);
+        const long long v_nodes = (long long)__shfl_sync(0xffffffffu, c, C_NODES);
+        const long long v_fails = (long long)__shfl_sync(0xffffffffu, c, C_FAILS);
+        const long long v_tuples = (long long)__shfl_sync(0xffffffffu, c, C_TUPLES);
+        const long long v_rev = (long long)__shfl_sync(0xffffffffu, c, C_REVISIONS);
+        const long long v_dom = (long long)__shfl_sync(0xffffffffu, c, C_DOMINANCE);
+        const long long v_ovf = (long long)__shfl_sync(0xffffffffu, c, C_OVERFLOW);
+        const long long v_states = (long long)__shfl_sync(0xffffffffu, c, C_STATES);
+        const long long v_edges = (long long)__shfl_sync(0xffffffffu, c, C_EDGES);
+        const long long v_leaves = (long long)__shfl_sync(0xffffffffu, c, C_LEAVES);
+        const long long v_unres = (long long)__shfl_sync(0xffffffffu, c, C_UNRESOLVED);
+        static_assert(C_COUNT <= 32, "one warp reads all counters");
+        if (ln != 0) return;
+        if (after_expand) {
+            s_ovf = (int)(v_ovf & 1);
+            s_leaves = v_leaves;
+            s_out = v_out;
+            if ((v_ovf & 1) || v_out + v_leaves > A.out_cap || v_leaves > 0) return;    // leaving, or the leaf phase comes first
+        }
+        s_status = v_unres != 0 ? SEARCH_RESOLVE : SEARCH_RUN;
+        if (v_unres != 0) return;               // the host finishes this wave and counts it
+        cs[S_NODES] += v_nodes; cs[S_FAILS] += v_fails; cs[S_TUPLES] += v_tuples; cs[S_REV] += v_rev;
+        cs[S_DOM] += v_dom;
+        cs[S_LEAVES] += v_leaves;
+        cs[S_WAVES] += 1;
+        cs[S_OVERFLOW] |= v_ovf;
+        cs[S_WAVES_LEFT] -= 1;
+        cs[S_N_IN] = v_out + v_new;
+        cs[S_CUR] ^= 1;
+        cs[S_STATES] = v_states;
+        cs[S_EDGES] = v_edges;
+    };
     for (;;) {
         // ---- wave start: can this wave run without the host?
         if (threadIdx.x == 0) {
@@ -1781,10 +1821,15 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         // Every block must take the same exit decisions, so they may only depend on values that no block is changing
         // while they are read: bit 0 of C_OVERFLOW, C_OUT and C_LEAVES are written by expand only (the leaf phase, which
         // faster blocks may already be in, appends through C_NEW and flags its own overflow bit).
-        // ---- the frontier buffer overflowed: only scratch was written, the host grows it and the wave runs again
-        if (cnt[C_OVERFLOW] & 1ull) { leave(SEARCH_RETRY, true); return; }
-        const long long n_leaves = (long long)cnt[C_LEAVES], out_after_expand = (long long)cnt[C_OUT];
-        if (out_after_expand + n_leaves > A.out_cap) {
+        // Warp 0 reads all counters with one parallel load and publishes what the block needs; on a wave without leaves
+        // that load also serves the end-of-wave bookkeeping (nothing changes any more), so such a wave costs one grid
+        // barrier and one L2 round trip.
+        if (threadIdx.x < 32) wave_counters(cnt, true);
+        __syncthreads();
+        // the frontier buffer overflowed: only scratch was written, the host grows it and the wave runs again
+        if (s_ovf) { leave(SEARCH_RETRY, true); return; }
+        const long long n_leaves = s_leaves;
+        if (s_out + n_leaves > A.out_cap) {
             // no room for the first nodes of new states: the host grows the frontier and finishes the wave (route + ingest)
             leave(SEARCH_INGEST, true);
             return;
@@ -1812,7 +1857,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
             ia.edge_label = A.edge_label;
             ia.edge_cap = A.edge_cap;
             ia.out_nodes = ea.out_nodes;
-            ia.out_base = out_after_expand;
+            ia.out_base = s_out;
             ia.out_cap = A.out_cap;
             ia.counters = ea.counters;
             ia.totals = A.counters;
@@ -1820,48 +1865,18 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
                 leaf_body_quad<true, true>(M, ra, ia, n_leaves);    // four leaves per warp
             else leaf_body(M, ra, ia, n_leaves);            // route + ingest in one pass
             grid.sync();
-        }
-        stamp(2);
-        stamp(3);
-        // ---- wave end: totals and the next wave's input, by warp 0 of EVERY block (one parallel load of all counters;
-        // they are frozen until the next wave's barrier has been passed)
-        if (threadIdx.x < 32) {
-            const int ln = threadIdx.x;
-            const unsigned long long c = ln < C_COUNT ? (ln < C_OUT ? tot[ln] : cnt[ln]) : 0ull;
-            const long long v_out = (long long)(__shfl_sync(0xffffffffu, c, C_OUT) + __shfl_sync(0xffffffffu, c, C_NEW));
-            const long long v_nodes = (long long)__shfl_sync(0xffffffffu, c, C_NODES);
-            const long long v_fails = (long long)__shfl_sync(0xffffffffu, c, C_FAILS);
-            const long long v_tuples = (long long)__shfl_sync(0xffffffffu, c, C_TUPLES);
-            const long long v_rev = (long long)__shfl_sync(0xffffffffu, c, C_REVISIONS);
-            const long long v_dom = (long long)__shfl_sync(0xffffffffu, c, C_DOMINANCE);
-            const long long v_ovf = (long long)__shfl_sync(0xffffffffu, c, C_OVERFLOW);
-            const long long v_states = (long long)__shfl_sync(0xffffffffu, c, C_STATES);
-            const long long v_edges = (long long)__shfl_sync(0xffffffffu, c, C_EDGES);
-            const long long v_leaves = (long long)__shfl_sync(0xffffffffu, c, C_LEAVES);
-            const long long v_unres = (long long)__shfl_sync(0xffffffffu, c, C_UNRESOLVED);
-            if (ln == 0) {
-                s_status = v_unres != 0 ? SEARCH_RESOLVE : SEARCH_RUN;
-                if (v_unres == 0) {
-                    cs[S_NODES] += v_nodes; cs[S_FAILS] += v_fails; cs[S_TUPLES] += v_tuples; cs[S_REV] += v_rev;
-                    cs[S_DOM] += v_dom;
-                    cs[S_LEAVES] += v_leaves;
-                    cs[S_WAVES] += 1;
-                    cs[S_OVERFLOW] |= v_ovf;
-                    cs[S_WAVES_LEFT] -= 1;
-                    cs[S_N_IN] = v_out;
-                    cs[S_CUR] ^= 1;
-                    cs[S_STATES] = v_states;
-                    cs[S_EDGES] = v_edges;
-                }
+            stamp(2);
+            if (threadIdx.x < 32) wave_counters(cnt, false);
+            __syncthreads();
+            if (s_status == SEARCH_RESOLVE) {
+                // leaves with an unseen constraint-set transition are still pending: the host resolves and ingests them
+                leave(SEARCH_RESOLVE, true);
+                return;
             }
-            static_assert(C_COUNT <= 32, "one warp reads all counters");
+        } else {
+            stamp(2);
         }
-        __syncthreads();
-        if (s_status == SEARCH_RESOLVE) {
-            // leaves with an unseen constraint-set transition are still pending: the host resolves and ingests them
-            leave(SEARCH_RESOLVE, true);
-            return;
-        }
+        stamp(3);
         stamp(4);
         if (threadIdx.x == 0) cs[S_WAVE]++;
     }

@@ -8,9 +8,12 @@ out = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "-
 rows = list(csv.reader(out.splitlines()))
 lines = {}
 func = ""
+path = ""
 for r in rows:
+    if len(r) >= 2 and r[0] == "File Path":
+        path = r[1].split("/")[-1]
     if len(r) >= 2 and r[0] == "Function Name":
-        func = r[1][:60]
+        func = path + " " + r[1][:40]
     if len(r) >= 8 and r[0].isdigit() and r[7].replace(",", "").isdigit():
         key = (func, int(r[0]))
         ins = int(r[7].replace(",", ""))
@@ -23,4 +26,4 @@ tot_i = sum(v[0] for v in lines.values())
 tot_s = sum(v[1] for v in lines.values())
 print("total warp instructions %d, samples %d" % (tot_i, tot_s))
 for (f, ln), v in sorted(lines.items(), key=lambda kv: -kv[1][1])[:top]:
-    print("%5d  inst %5.1f%%  samples %5.1f%%  %s" % (ln, 100.0 * v[0] / max(tot_i, 1), 100.0 * v[1] / max(tot_s, 1), v[2][:120]))
+    print("%-22s %5d  inst %5.1f%%  samples %5.1f%%  %s" % (f.split(" ")[0][:22], ln, 100.0 * v[0] / max(tot_i, 1), 100.0 * v[1] / max(tot_s, 1), v[2][:110]))
