@@ -176,7 +176,7 @@ __host__ __device__ inline int pick_expand_mode(const DevModel &m, long long n_i
     if (m.force_mode == EXPAND_QUAD + 1) return quad_ok ? EXPAND_QUAD : EXPAND_WARP;
     if (m.force_mode) return m.force_mode - 1;
     if (n_in <= ctas) return EXPAND_CTA;          // every node gets a CTA of its own (measured: a second node per CTA loses to a warp per node)
-    if (quad_ok && n_in >= 4ll * 8 * ctas) return EXPAND_QUAD;
+    if (quad_ok && n_in >= 2ll * 8 * ctas) return EXPAND_QUAD;       // two nodes per resident warp or more
     return EXPAND_WARP;
 }
 // persistent wave loop (cooperative launch); search_max_grid = co-resident CTAs, 0 if unavailable

@@ -6,8 +6,8 @@ names = sys.argv[1:] or ["juggling_b6_f6_nosym", "partialorder_14", "digitinvade
 for name in names:
     m = binding.Model(instances.by_name(name))
     binding.solve(m)
-    for now in (8, 64, 512, 4096):
-        for ahead in (1, 8, 64):
+    for now in (2, 4, 8, 16, 64):
+        for ahead in (1, 2, 4, 8):
             best = None
             for _ in range(3):
                 a = binding.solve(m, binding.default_options(enum_limit_now=now, enum_limit_ahead=ahead))
