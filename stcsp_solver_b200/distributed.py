@@ -94,8 +94,10 @@ class WaveExchange:
         return out
 
 
-# A wave this wide keeps one B200 busy; below it, sharding only adds two collectives per wave.
-SINGLE_GPU_FRONTIER = 262144
+# Below this wave width one B200 is faster than several: sharding adds two host-synchronised collectives per wave
+# (measured: partialorder_16, widest wave 0.5 M nodes, 14.7 ms on one GPU and 20-23 ms sharded over 2 or 4;
+# partialorder_18, 2.4 M nodes, 58.7 ms on one, 55.6 on two, 40.3 on four).
+SINGLE_GPU_FRONTIER = 1 << 20
 
 
 def solve_distributed(model: binding.Model, options: Optional[binding.Options] = None, group=None,

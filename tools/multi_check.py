@@ -18,7 +18,7 @@ for name in names:
     text = g["model"] if g and "model" in g else instances.by_name(name)
     model = binding.Model(text)
     a = None
-    for rep in range(2):
+    for rep in range(4):
         a = None                # release the previous automaton (its pinned blocks go back to the cache)
         dist.barrier(); torch.cuda.synchronize(); t0 = time.time()
         a = distributed.solve_distributed(model, adaptive=os.environ.get("ADAPTIVE", "1") == "1")
