@@ -270,10 +270,10 @@ def main():
         e2e = work / (wall_total / steps)
         peak, peak_src = measured_peak()
         roof = None
-        if world == 1:
+        k_ms = sum(x[0] for x in kern) / steps      # N > 1: rank 0's launches (the adaptive driver keeps small instances there)
+        k_launches = sum(x[1] for x in kern) / steps
+        if k_ms > 0:
             bytes_per_node = 2 * V * K * 8          # one domain block read + one written, (lb, ub) int32 pairs
-            k_ms = sum(x[0] for x in kern) / steps
-            k_launches = sum(x[1] for x in kern) / steps
             achieved = st["algorithmic_bytes"] / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -287,8 +287,9 @@ def main():
                     "bytes_per_unit": bytes_per_node, "units_per_launch": st["n_search_nodes"] / max(k_launches, 1),
                     "launches_per_step": k_launches, "avg_launch_us": k_ms / max(k_launches, 1) * 1e3,
                     "share_of_step": k_ms / ms_dev if ms_dev else None,
-                    "expand_only": {"ms_per_step": prof[0], "launches": prof[1], "step_ms_stepwise": prof[3],
-                                    "achieved_gbs": prof[2] * bytes_per_node / (prof[0] / 1e3) / 1e9 if prof[0] > 0 else 0.0},
+                    "expand_only": None if prof is None else {
+                        "ms_per_step": prof[0], "launches": prof[1], "step_ms_stepwise": prof[3],
+                        "achieved_gbs": prof[2] * bytes_per_node / (prof[0] / 1e3) / 1e9 if prof[0] > 0 else 0.0},
                     "note": "integer-issue and latency bound: %d tuple evaluations and %d propagator runs per %d-byte node"
                             % (st["n_tuples"] // max(st["n_search_nodes"], 1),
                                st["n_revisions"] // max(st["n_search_nodes"], 1), bytes_per_node)}
@@ -302,7 +303,10 @@ def main():
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": name, "unit_of_work": "reference generalisedArcConsistent calls (%s per solve)" % work,
                        "l2": "flushed between steps (192 MiB write)", "timing": "CUDA events on the library stream around the whole search, per step" + ("" if world == 1 else ", max over ranks"),
-                       "vars": V, "prefix_k": K, "parallelism": "states sharded by signature hash x%d" % world},
+                       "vars": V, "prefix_k": K,
+                       "parallelism": "states sharded by signature hash x%d" % world + (
+                           " (adaptive driver: every wave of this instance fits one GPU, so rank 0 solved it alone)"
+                           if getattr(last, "exchange_stats", {}).get("single_gpu") else "")},
             "solve_time_s": ms_dev / 1e3,
             "own_search_nodes_per_s": st["n_search_nodes"] / (ms_dev / 1e3),
             "states_per_s": st["n_states"] / (ms_dev / 1e3), "edges_per_s": st["n_edges"] / (ms_dev / 1e3),
