@@ -774,9 +774,11 @@ __device__ __forceinline__ unsigned char *stage_base(unsigned char *smem, const 
 }
 
 // Called by every thread of the CTA (contains barriers).  Returns the constraint set staged, -1 if none.
-__device__ int stage_set(const DevModel &M, unsigned char *smem, int cid) {
+// resident (search_kernel only): the set this CTA staged in an earlier wave of the same launch is still there.
+__device__ int stage_set(const DevModel &M, unsigned char *smem, int cid, int *resident) {
     DevModel *sm = reinterpret_cast<DevModel *>(stage_base(smem, M));
     if (M.stage_bytes == 0 || cid < 0) return -1;
+    if (resident && *resident == cid) return cid;       // (read before the barrier below, written after it)
     unsigned char *p = reinterpret_cast<unsigned char *>(sm) + align8(sizeof(DevModel));
     const DevSet S = M.sets[cid];
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -816,6 +818,7 @@ __device__ int stage_set(const DevModel &M, unsigned char *smem, int cid) {
         m.width = s_width;
         m.code = reinterpret_cast<const Instr *>(s_code) - S.code_off;
         *sm = m;
+        if (resident) *resident = cid;
     }
     __syncthreads();
     return cid;
@@ -825,7 +828,7 @@ __device__ int stage_set(const DevModel &M, unsigned char *smem, int cid) {
 //              (narrow waves: fewer nodes than resident CTAs, the latency of one node is the wave's duration).
 // CTA = false: one warp per search node (wide waves: throughput).
 template <bool CTA>
-__device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs &P, unsigned char *smem) {
+__device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs &P, unsigned char *smem, int *resident = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpMem wm = carve(smem, Mg, CTA ? 0 : warp, warp);
     const long long n_in = P.n_in;
@@ -838,7 +841,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
     unsigned st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;    // per launch and thread
     // stage the constraint set of this CTA's first node (waves are almost always homogeneous)
     const long long probe = CTA ? (long long)blockIdx.x : (long long)blockIdx.x * kExpandWarps;
-    const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1);
+    const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1, resident);
     const DevModel &Ms = *reinterpret_cast<const DevModel *>(stage_base(smem, Mg));
     if (CTA && blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(P.dbg, P.dbg_cap, 0);     // wave entered, set staged
 
@@ -950,7 +953,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
 // A scalar round rarely has more than a handful of dirty propagators per node, so with one node per warp most lanes
 // idle.  Here the four groups of a warp run their scalar rounds side by side (lanes that execute the same revision
 // code converge regardless of their group); the rare revisions that need 32 lanes are served one group at a time.
-__device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const ExpandArgs &P, unsigned char *smem) {
+__device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const ExpandArgs &P, unsigned char *smem, int *resident = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
     const unsigned gmask = 0xffu << (8 * g);
     WarpMem wm = carve(smem, Mg, warp * 4 + g, warp);           // my group's node slot, the warp's scratch
@@ -958,7 +961,7 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
     const int V = Mg.V, k = Mg.k, NW = Mg.node_words;
     unsigned st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;    // per launch and thread
     const long long probe = (long long)blockIdx.x * kExpandWarps * 4;
-    const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1);
+    const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1, resident);
     const DevModel &Ms = *reinterpret_cast<const DevModel *>(stage_base(smem, Mg));
     const long long first = ((long long)blockIdx.x * kExpandWarps + warp) * 4, step = (long long)gridDim.x * kExpandWarps * 4;
 
@@ -1629,6 +1632,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
     __shared__ long long cs[S_COUNT];
     __shared__ ExpandArgs ea;           // the wave's arguments (launch parameters in the stand-alone kernels)
     __shared__ int s_status, s_set;
+    __shared__ int s_resident;          // constraint set whose metadata this CTA holds in shared memory (kept across waves)
     const bool controller = blockIdx.x == 0 && threadIdx.x == 0;    // the one thread that reports to the host
     auto stamp = [&](int k) {
         if (A.trace != nullptr && controller && cs[S_WAVE] < A.trace_cap) {
@@ -1638,6 +1642,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         }
     };
     if (threadIdx.x == 0) {
+        s_resident = -1;
         for (int i = 0; i < S_COUNT; i++) cs[i] = 0;
         cs[S_N_IN] = ctl->n_in;
         cs[S_CUR] = ctl->cur;
@@ -1809,9 +1814,9 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevM
         stamp(0);
         volatile unsigned long long *cnt = ea.counters;         // this wave's counter set
         const int mode = pick_expand_mode(M, ea.n_in, gridDim.x);
-        if (mode == EXPAND_CTA) expand_body<true>(M, ea, smem);
-        else if (mode == EXPAND_QUAD) expand_body_quad(M, ea, smem);
-        else expand_body<false>(M, ea, smem);
+        if (mode == EXPAND_CTA) expand_body<true>(M, ea, smem, &s_resident);
+        else if (mode == EXPAND_QUAD) expand_body_quad(M, ea, smem, &s_resident);
+        else expand_body<false>(M, ea, smem, &s_resident);
         grid.sync();
         stamp(1);
         // the previous wave's counter set is no longer read by anybody: clear it for the wave after this one
