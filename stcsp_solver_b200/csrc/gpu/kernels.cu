@@ -1359,12 +1359,17 @@ __device__ __forceinline__ void ingest_leaf(const DevModel &M, const IngestArgs 
     if (abort_leaf) return;
     const int dst_global = dst * M.world + M.rank;
 
+    // both cursors at once: two atomics in flight instead of two round trips one after the other
+    unsigned long long o = 0, e = 0;
+    if (lane == 0) {
+        if (is_new) o = (unsigned long long)P.out_base + atomicAdd(&P.counters[C_NEW], 1ull);
+        e = atomicAdd(&P.totals[C_EDGES], 1ull);
+    }
+    o = __shfl_sync(0xffffffffu, o, 0);
+    e = __shfl_sync(0xffffffffu, e, 0);
     if (is_new) {
         // first search node of the new state: next-linked variables take the values just chosen,
         // everything else restarts from its declared range
-        unsigned long long o = 0;
-        if (lane == 0) o = (unsigned long long)P.out_base + atomicAdd(&P.counters[C_NEW], 1ull);
-        o = __shfl_sync(0xffffffffu, o, 0);
         if ((long long)o >= P.out_cap) {
             if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 32ull);
         } else {
@@ -1387,9 +1392,6 @@ __device__ __forceinline__ void ingest_leaf(const DevModel &M, const IngestArgs 
     } else {
         st_dom++;
     }
-    unsigned long long e = 0;
-    if (lane == 0) e = atomicAdd(&P.totals[C_EDGES], 1ull);
-    e = __shfl_sync(0xffffffffu, e, 0);
     if ((long long)e >= P.edge_cap) {
         if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 8ull);
         return;

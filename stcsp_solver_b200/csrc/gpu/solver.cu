@@ -544,7 +544,7 @@ struct stcsp_session {
         std::swap(table.cap, fresh.cap);
         std::swap(table.bytes, fresh.bytes);
         std::swap(table.device, fresh.device);
-        CK(cudaStreamSynchronize(stream));      // the old table returns to the cache when `fresh` goes out of scope
+        if (fresh.p) CK(cudaStreamSynchronize(stream));     // the old table returns to the cache when `fresh` goes out of scope
         table_size = want;
     }
     void init(const stcsp_problem_t *problem, const stcsp_options_t *options, int r, int w) {
@@ -624,7 +624,7 @@ struct stcsp_session {
             CK(cudaMemcpyAsync(frontier[0].p, node.data(), NW * 4, cudaMemcpyHostToDevice, stream));
             const unsigned long long one = 1;
             CK(cudaMemcpyAsync(counters.p + C_STATES, &one, 8, cudaMemcpyHostToDevice, stream));
-            CK(cudaStreamSynchronize(stream));
+            // (no synchronize: copies from pageable memory return once the source has been staged)
             h2d += (KW + NW) * 4 + 8;
             n_states = 1;
             n_in = 1;
