@@ -1144,13 +1144,13 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
     }
 }
 
-__global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_quad_kernel(const DevModel M, const ExpandArgs P) {
+__global__ void __launch_bounds__(kExpandWarps * 32, kExpandCtasPerSm) expand_quad_kernel(const DevModel M, const ExpandArgs P) {
     extern __shared__ __align__(16) unsigned char smem[];
     expand_body_quad(M, P, smem);
 }
 
 template <bool CTA>
-__global__ void __launch_bounds__(kExpandWarps * 32, 3) expand_kernel(const DevModel M, const ExpandArgs P) {
+__global__ void __launch_bounds__(kExpandWarps * 32, kExpandCtasPerSm) expand_kernel(const DevModel M, const ExpandArgs P) {
     extern __shared__ __align__(16) unsigned char smem[];
     expand_body<CTA>(M, P, smem);
 }
@@ -1622,7 +1622,7 @@ __global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const Ing
 // block 0 clears the set of wave w-1 after the barrier of wave w -- every block has finished reading it by then --
 // and no block touches that set again before it has passed the barrier of wave w+1, which block 0 reaches only after
 // the clearing.  C_STATES and C_EDGES (never reset) live in set 0.
-__global__ void __launch_bounds__(kExpandWarps * 32, 3) search_kernel(const DevModel M, SearchArgs A) {
+__global__ void __launch_bounds__(kExpandWarps * 32, kExpandCtasPerSm) search_kernel(const DevModel M, SearchArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     volatile SearchCtl *ctl = A.ctl;

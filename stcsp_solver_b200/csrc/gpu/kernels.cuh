@@ -163,7 +163,8 @@ struct SearchArgs {
     long long trace_cap;                // in waves
 };
 
-constexpr int kExpandWarps = 8;      // warps per CTA of the expand kernel
+constexpr int kExpandWarps = 8;      // warps per CTA of the expand kernel (measured: 4 warps x 6 CTAs per SM is a wash)
+constexpr int kExpandCtasPerSm = 3;  // resident CTAs the launch bounds allow for (24 warps per SM, 80 registers per thread)
 
 size_t expand_smem_bytes(const DevModel &m);
 int expand_max_grid(const DevModel &m, int sm_count);      // resident CTAs of the expand kernel on this device
@@ -172,11 +173,11 @@ enum ExpandMode : int { EXPAND_WARP = 0, EXPAND_CTA = 1, EXPAND_QUAD = 2 };
 void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, int mode, cudaStream_t stream);
 // the mode the automatic policy picks for a wave of n_in nodes on a grid of `ctas` resident CTAs
 __host__ __device__ inline int pick_expand_mode(const DevModel &m, long long n_in, long long ctas) {
-    const bool quad_ok = m.node_slots >= 4 * 8 && !m.lazy_ahead;
+    const bool quad_ok = m.node_slots >= 4 * kExpandWarps && !m.lazy_ahead;
     if (m.force_mode == EXPAND_QUAD + 1) return quad_ok ? EXPAND_QUAD : EXPAND_WARP;
     if (m.force_mode) return m.force_mode - 1;
     if (n_in <= ctas) return EXPAND_CTA;          // every node gets a CTA of its own (measured: a second node per CTA loses to a warp per node)
-    if (quad_ok && n_in >= 2ll * 8 * ctas) return EXPAND_QUAD;       // two nodes per resident warp or more
+    if (quad_ok && n_in >= 2ll * kExpandWarps * ctas) return EXPAND_QUAD;       // two nodes per resident warp or more
     return EXPAND_WARP;
 }
 // persistent wave loop (cooperative launch); search_max_grid = co-resident CTAs, 0 if unavailable

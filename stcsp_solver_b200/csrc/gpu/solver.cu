@@ -494,7 +494,7 @@ struct stcsp_session {
         dm.lazy_ahead = opt.lookahead == 2 ? 1 : 0;
         // four node blocks per warp (quad mode for wide waves) when three CTAs still fit an SM
         dm.node_slots = 4 * kExpandWarps;
-        if (expand_smem_bytes(dm) > 72 * 1024) dm.node_slots = kExpandWarps;
+        if (expand_smem_bytes(dm) > (216 / kExpandCtasPerSm) * 1024) dm.node_slots = kExpandWarps;
         dm.force_mode = opt.expand_mode >= 1 && opt.expand_mode <= 3 ? opt.expand_mode : 0;
         dm.enum_now = opt.enum_limit_now > 0 ? opt.enum_limit_now : 8;
         dm.enum_ahead = opt.enum_limit_ahead > 0 ? opt.enum_limit_ahead : 4;
