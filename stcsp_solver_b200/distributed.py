@@ -146,6 +146,23 @@ def solve_distributed(model: binding.Model, options: Optional[binding.Options] =
     stats = {"waves": 0, "records_sent": 0}
     header = torch.zeros(2 + world, dtype=torch.int64, device=ex.device)
     headers = torch.zeros((world, 2 + world), dtype=torch.int64, device=ex.device)
+    # the header travels host -> device -> all-gather -> host once or twice per wave: pinned staging, one copy each way
+    on_gpu = ex.device.type == "cuda"
+    header_host = torch.zeros(2 + world, dtype=torch.int64)
+    headers_host = torch.zeros((world, 2 + world), dtype=torch.int64)
+    if on_gpu:
+        header_host, headers_host = header_host.pin_memory(), headers_host.pin_memory()
+
+    def gather_headers(frontier_now, pending_now, counts_now):
+        hh = header_host.numpy()
+        hh[0], hh[1] = frontier_now, pending_now
+        hh[2:] = counts_now
+        header.copy_(header_host, non_blocking=on_gpu)
+        dist.all_gather_into_tensor(headers.view(-1), header, group=ex.group)
+        headers_host.copy_(headers, non_blocking=on_gpu)
+        if on_gpu:
+            torch.cuda.current_stream().synchronize()
+        return headers_host.numpy().copy()
     frontier = 1 if rank == 0 else 0
     try:
         while True:
@@ -155,11 +172,7 @@ def solve_distributed(model: binding.Model, options: Optional[binding.Options] =
             if n_pending == 0 and n_leaves > 0:
                 outbox = torch.empty((n_leaves, words), dtype=torch.int32, device=ex.device)
                 send_counts = session.outbox(outbox.data_ptr(), n_leaves)
-            header[0] = frontier
-            header[1] = n_pending
-            header[2:] = torch.as_tensor(send_counts)
-            dist.all_gather_into_tensor(headers.view(-1), header, group=ex.group)
-            h = headers.cpu().numpy()
+            h = gather_headers(frontier, n_pending, send_counts)
             if h[:, 0].sum() == 0:
                 break                                   # no rank had anything to expand: the search is over
             if h[:, 1].sum() > 0:
@@ -169,10 +182,7 @@ def solve_distributed(model: binding.Model, options: Optional[binding.Options] =
                 if n_leaves > 0 and outbox is None:
                     outbox = torch.empty((n_leaves, words), dtype=torch.int32, device=ex.device)
                     send_counts = session.outbox(outbox.data_ptr(), n_leaves)
-                header[1] = 0
-                header[2:] = torch.as_tensor(send_counts)
-                dist.all_gather_into_tensor(headers.view(-1), header, group=ex.group)
-                h = headers.cpu().numpy()
+                h = gather_headers(frontier, 0, send_counts)
             recv_counts = h[:, 2 + rank].copy()
             if h[:, 2:].sum() > 0:
                 if outbox is None:
