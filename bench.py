@@ -66,17 +66,24 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.sm, self.reasons, self.sm_max = index, False, [], set(), None
-
-    def run(self):
-        try:
+        self.nv = self.handle = None
+        try:                                # NVML is initialised here, not in the thread: the timed region is short
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            self.nv, self.handle = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        except Exception as e:              # NVML missing: report it instead of inventing numbers
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def run(self):
+        nv, h = self.nv, self.handle
+        if nv is None:
+            return
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        try:
             while True:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
@@ -86,8 +93,8 @@ class ClockSampler(threading.Thread):
                 if self.stop_flag:
                     break
                 time.sleep(0.002)
-        except Exception as e:      # NVML missing: report it instead of inventing numbers
-            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+        except Exception as e:
+            self.reasons.add("nvml_error:%s" % type(e).__name__)
 
     def result(self):
         self.stop_flag = True
@@ -204,11 +211,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
     for _ in range(args.warmup):
         one_solve()
         l2_flush(torch, scratch)
-    sampler = ClockSampler(local)
     sampler.start()
+    t_wait = time.perf_counter()
+    while sampler.nv is not None and not sampler.sm and time.perf_counter() - t_wait < 0.5:
+        time.sleep(0.0005)                  # the first sample is in before the timed region starts
     barrier()
     dev_ms, wall_s, last, kern = [], [], None, []
     region0 = time.perf_counter()
