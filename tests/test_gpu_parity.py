@@ -110,6 +110,32 @@ def test_wide_waves_leaving_the_persistent_kernel(name, wide):
         assert st0[key] == st1[key], (key, wide)
 
 
+LONG_CHAIN = """var C : [0, 63];
+var D : [0, 7];
+first C == 0;
+first D == 0;
+next C == if C eq 63 then 0 else (C + 1);
+next D == if C eq 63 then (if D eq 7 then 0 else (D + 1)) else D;
+"""
+
+
+def test_time_limit_slices_the_search_without_changing_it():
+    """With a time limit the search kernel comes back to the host every 256 waves (the deadline is checked there);
+    a 512-state cycle, one state per wave or two, needs several such slices and must give the same automaton."""
+    model = binding.Model(LONG_CHAIN)
+    binding.solve(model)                # first solve of a model: pools grow, the kernel comes back for that too
+    a0 = binding.solve(model)
+    a1 = binding.solve(model, binding.default_options(time_limit_s=1000))
+    s0, s1 = binding.Solution(model, a0), binding.Solution(model, a1)
+    assert (s0.n_states, s0.n_edges) == (513, 513)      # the start state and the 512-cycle (the reference prints 513 too)
+    assert s0.canonical_text() == s1.canonical_text()
+    assert a0.stats()["n_waves"] > 256
+    assert a1.stats()["n_kernel_launches"] > a0.stats()["n_kernel_launches"]
+    import _oracle
+    oracle_automaton, _ = _oracle.solve(model, 20.0)
+    assert binding.Solution(model, oracle_automaton).canonical_text() == s0.canonical_text()
+
+
 def test_session_api_single_rank_matches_solve():
     """create / expand / [resolve] / ingest / finish / assemble / trim by hand == stcsp_gpu_solve."""
     g = GOLDENS["probe_first_capture"]
