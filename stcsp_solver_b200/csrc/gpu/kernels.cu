@@ -1630,7 +1630,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, kExpandCtasPerSm) search_ke
     // Wave state and running totals of THIS block (thread 0), in shared memory: nothing of it may stay live in
     // registers across the expand bodies, whose inner loops need every register the launch bounds allow.
     enum { S_N_IN, S_STATES, S_EDGES, S_WAVES_LEFT, S_NODES, S_FAILS, S_TUPLES, S_REV, S_DOM, S_LEAVES, S_WAVES, S_CUR,
-           S_OVERFLOW, S_WAVE, S_COUNT };
+           S_OVERFLOW, S_WAVE, S_MAX_IN, S_COUNT };
     __shared__ long long cs[S_COUNT];
     __shared__ ExpandArgs ea;           // the wave's arguments (launch parameters in the stand-alone kernels)
     __shared__ int s_status, s_set;
@@ -1665,6 +1665,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, kExpandCtasPerSm) search_ke
             ctl->t_dominance = cs[S_DOM]; ctl->t_leaves = cs[S_LEAVES]; ctl->t_waves = cs[S_WAVES];
             ctl->waves_left = cs[S_WAVES_LEFT];
             ctl->overflow = (int)cs[S_OVERFLOW];
+            ctl->t_max_in = cs[S_MAX_IN];
         }
     };
     // Warp 0: one parallel load of the wave's counters (frozen while it runs).  after_expand: publish expand's results
@@ -1718,6 +1719,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, kExpandCtasPerSm) search_ke
                      c_edges + c_n_in > A.edge_cap || 2 * (c_states + c_n_in) > A.table_mask + 1 || 2 * c_n_in > A.out_cap)
                 st = SEARCH_GROW;
             s_status = st;
+            if (st == SEARCH_RUN && c_n_in > cs[S_MAX_IN]) cs[S_MAX_IN] = c_n_in;
             const int set = (int)(cs[S_WAVE] % 3), cur = (int)cs[S_CUR];
             s_set = set;
             ea.in_nodes = A.frontier[cur];

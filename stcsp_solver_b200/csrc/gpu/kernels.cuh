@@ -128,6 +128,7 @@ struct SearchCtl {
     int finished;           // 1: the kernel also grouped the edges by source and applied the fail rule (FinishArgs)
     long long waves_left;
     long long t_nodes, t_fails, t_tuples, t_revisions, t_dominance, t_leaves, t_waves;
+    long long t_max_in;     // widest wave this launch ran
     int dead_edges, changed;
 };
 // Scratch for finishing a small automaton inside the search kernel (all null / 0: the host launches the finishing kernels).

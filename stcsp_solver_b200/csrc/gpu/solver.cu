@@ -159,6 +159,7 @@ struct ModelState {
     bool uploaded = false;
     // pool sizes the last solve of this model ended with: the next one starts there and never has to grow
     long long hint_frontier = 0, hint_states = 0, hint_edges = 0, hint_table = 0;
+    long long hint_max_wave = 0;        // widest wave of the last solve (0: unknown)
 };
 
 struct ModelCache {
@@ -372,6 +373,8 @@ struct stcsp_session {
     bool finish_in_kernel = false, finish_trim = true;     // set by stcsp_gpu_solve (single rank)
     bool time_expand = false;                               // expand launches of run_persistent's wide waves are timed
     static constexpr long long kWideWaveNodes = 32768;     // default of stcsp_options_t::wide_wave_nodes
+    static constexpr long long kNarrowInstanceWave = 2048; // widest wave of an instance that runs on one CTA per SM
+    bool search_complete = false;                           // the wave loop ran to the end (max_wave is the instance's)
     bool prefinished = false;       // the search kernel already grouped + trimmed (fb_* hold the result)
     long long prefinished_dead = 0;
     SearchCtl *h_ctl = nullptr;     // pinned, behind h_counters
@@ -385,6 +388,7 @@ struct stcsp_session {
     unsigned long long *h_counters = nullptr;       // pinned
     long long table_size = 0;
     long long n_in = 0, n_out = 0, n_leaves = 0, n_unres = 0, n_states = 0, n_edges = 0;
+    long long max_wave = 0;             // widest wave so far
     int expand_grid_max = 148;
     std::vector<int32_t> pending;                   // flat requests [cid, values[V]]
     // statistics
@@ -402,6 +406,7 @@ struct stcsp_session {
             model->hint_states = (long long)state_key.cap / dm.key_words;
             model->hint_edges = (long long)edge_src.cap;
             model->hint_table = table_size;
+            if (search_complete) model->hint_max_wave = max_wave;
             model_cache().put(cache_key, std::move(model));       // the compiled model stays resident for the next solve
         }
         release_all();
@@ -714,8 +719,13 @@ struct stcsp_session {
             h_ctl->waves_left = deadline > 0 ? 256 : (1ll << 40);
             CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof *h_ctl, cudaMemcpyHostToDevice, stream));
             zero_wave_counters();
+            // An instance whose waves stay narrow (known from the last solve of this model) gets one CTA per SM: with a
+            // third of the CTAs the grid barrier is cheaper and a node's CTA has the SM to itself (b6_nosym -7 %,
+            // b5_f6 -8 %); anything wider needs all resident warps (digitinvader7 with 148 CTAs: +22 %).
+            const int grid = model->hint_max_wave > 0 && model->hint_max_wave <= kNarrowInstanceWave ? std::min(search_grid, sm_count)
+                                                                                                     : search_grid;
             CK(cudaEventRecord(evk0, stream));
-            CK(launch_search(dm, sa, search_grid, stream));
+            CK(launch_search(dm, sa, grid, stream));
             CK(cudaEventRecord(evk1, stream));
             CK(cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof *h_ctl, cudaMemcpyDeviceToHost, stream));
             read_counters();
@@ -760,6 +770,7 @@ struct stcsp_session {
             t_dominance += h_ctl->t_dominance;
             t_leaves += h_ctl->t_leaves;
             t_waves += h_ctl->t_waves;
+            max_wave = std::max<long long>(max_wave, h_ctl->t_max_in);
             if (opt.verbosity > 0)
                 fprintf(stderr, "[stcsp r%d] t=%.3f ms search kernel returned: status %d after %lld waves, n_in %lld, states %llu, edges %llu, "
                                 "out %llu leaves %llu overflow %d\n",
@@ -883,6 +894,7 @@ struct stcsp_session {
         if (n_in > 0) {
             const int NW = dm.node_words, RW = dm.rec_words;
             const double te0 = now_s();
+            max_wave = std::max(max_wave, n_in);
             leaves.reserve((size_t)n_in * RW, 0, stream);
             unresolved.reserve((size_t)n_in, 0, stream);
             DBuf<int32_t> &out = frontier[cur ^ 1];
@@ -1743,6 +1755,7 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
             }
             s->ingest(nullptr, 0, &frontier);
         }
+        s->search_complete = true;
         t_loop = now_s();
         s->finish_device(out, !(options && options->no_trim));
         t_finish = now_s();
