@@ -163,7 +163,9 @@ def run_reference_arm(args, name, text):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed solves (default: 200 for the B200 arm -- a timed region long enough for the clock sampler; "
+                         "50 bounded samples for the reference arm)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--instance", default="juggling_b6_f6_nosym")
@@ -172,6 +174,8 @@ def main():
     ap.add_argument("--no-also", action="store_true", help="skip the extra workloads reported under `also`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.steps is None:
+        args.steps = 200 if args.impl == "b200" else 50
 
     from stcsp_solver_b200 import binding, instances
     name = args.instance
