@@ -60,6 +60,12 @@ char *stcsp_solution_dot(const stcsp_problem_t *problem, const stcsp_solution_t 
 /* Canonical text; "EMPTY" when the root is not valid. */
 char *stcsp_solution_canonical(const stcsp_problem_t *problem, const stcsp_solution_t *s);
 void stcsp_string_free(char *s);
+/* The same two texts streamed to a file (the reference writes ./solutions.dot, src/solveralgorithm.cpp:709-730; at
+ * partialorder_20 size the text is ~10 GB and must not exist as one string), and the SHA-256 of the canonical text
+ * computed line by line (65 bytes incl. the terminating NUL). */
+int stcsp_solution_write_dot(const stcsp_problem_t *problem, const stcsp_solution_t *s, const char *path);
+int stcsp_solution_write_canonical(const stcsp_problem_t *problem, const stcsp_solution_t *s, const char *path);
+int stcsp_solution_canonical_sha256(const stcsp_problem_t *problem, const stcsp_solution_t *s, char out_hex[65]);
 
 #ifdef __cplusplus
 }

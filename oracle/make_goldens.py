@@ -9,6 +9,7 @@ feature probes below, canonicalises the ``solutions.dot`` it writes
 SHA-256 and -- for small automata -- the canonical text itself.
 
 Usage:  python oracle/make_goldens.py [--jobs N] [--only REGEX] [--max-seconds S]
+(REGEX is searched in the case key, e.g. "digitinvader[6-9]_[az]".)
 The big instances take long on one core (digitinvader9 ~35 min, digitinvader8 ~13 min).
 """
 from __future__ import annotations
@@ -91,7 +92,7 @@ TEXT_LIMIT = 400                     # keep the canonical text for automata up t
 def cases():
     for name in instances.SHIPPED:
         text = instances.by_name(name)
-        flagsets = DI_FLAGS if name.startswith("digitinvader") and int(name[12:]) <= 5 else [""]
+        flagsets = DI_FLAGS if name.startswith("digitinvader") else [""]   # digitinvader1-9, BASELINE config 2
         for fl in flagsets:
             yield name, text, fl, False
     for name, (text, flagsets) in PROBES.items():
@@ -147,7 +148,7 @@ def main():
     ap.add_argument("--max-seconds", type=int, default=5400)
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
-    todo = [c for c in cases() if re.search(args.only, c[0])]
+    todo = [c for c in cases() if re.search(args.only, c[0] + ("" if not c[2] else "_" + c[2].strip("-")))]
     with cf.ThreadPoolExecutor(args.jobs) as ex:
         futs = [ex.submit(run_case, *c, args.max_seconds) for c in todo]
         for fu in cf.as_completed(futs):

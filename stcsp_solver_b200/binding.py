@@ -111,6 +111,9 @@ def lib() -> C.CDLL:
         L.stcsp_solution_dot.restype = C.c_void_p
         L.stcsp_solution_canonical.argtypes = [C.POINTER(Problem), C.POINTER(SolutionC)]
         L.stcsp_solution_canonical.restype = C.c_void_p
+        L.stcsp_solution_write_dot.argtypes = [C.POINTER(Problem), C.POINTER(SolutionC), C.c_char_p]
+        L.stcsp_solution_write_canonical.argtypes = [C.POINTER(Problem), C.POINTER(SolutionC), C.c_char_p]
+        L.stcsp_solution_canonical_sha256.argtypes = [C.POINTER(Problem), C.POINTER(SolutionC), C.c_char_p]
         L.stcsp_gpu_device_count.restype = C.c_int
         L.stcsp_gpu_release_caches.restype = None
         L.stcsp_session_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.c_int32, C.c_int32,
@@ -250,6 +253,15 @@ class Solution:
     def canonical_sha256(self) -> str:
         import hashlib
         return hashlib.sha256(self.canonical_text().encode()).hexdigest()
+
+    def canonical_sha256_streamed(self) -> str:
+        """SHA-256 of the canonical text computed line by line in the library (no text is materialised)."""
+        buf = C.create_string_buffer(65)
+        _check(lib().stcsp_solution_canonical_sha256(self.model.problem, C.byref(self.c), buf))
+        return buf.value.decode()
+
+    def write_dot(self, path: str) -> None:
+        _check(lib().stcsp_solution_write_dot(self.model.problem, C.byref(self.c), path.encode()))
 
     def to_python(self) -> canonical.Automaton:
         """Re-parse the DOT text with the independent Python canonicaliser."""

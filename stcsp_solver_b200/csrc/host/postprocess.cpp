@@ -19,7 +19,10 @@
 #include <string>
 #include <vector>
 
+#include <cstdio>
+
 #include "error.h"
+#include "sha256.h"
 #include "stcsp_host.h"
 
 namespace {
@@ -266,50 +269,130 @@ void stcsp_solution_free(stcsp_solution_t *s) {
     memset(s, 0, sizeof *s);
 }
 
-char *stcsp_solution_dot(const stcsp_problem_t *p, const stcsp_solution_t *s) {
+}  // extern "C"
+
+// Both texts are produced line by line through a sink, so they can be streamed to a file or into SHA-256 without
+// ever holding the whole text (82 MB at partialorder_14, ~10 GB at partialorder_20).
+namespace {
+
+template <class Sink>
+void emit_dot(const stcsp_problem_t *p, const stcsp_solution_t *s, Sink &&sink) {
     const Impl *impl = (const Impl *)s->impl;
-    std::ostringstream os;
-    os << "# Number of nodes = " << s->n_table_states << "\n";
-    os << header_line(p, s, false, nullptr, 0) << "\n";
-    os << header_line(p, s, true, impl->sig_vars.data(), (int32_t)impl->sig_vars.size()) << "\n";
-    os << "digraph \"StCSP\" {\n";
+    std::string line;
+    line = "# Number of nodes = " + std::to_string(s->n_table_states) + "\n";
+    sink(line);
+    sink(header_line(p, s, false, nullptr, 0) + "\n");
+    sink(header_line(p, s, true, impl->sig_vars.data(), (int32_t)impl->sig_vars.size()) + "\n");
+    sink(std::string("digraph \"StCSP\" {\n"));
     int64_t e = 0;
     // the reference prints numSignVar + numUntil(distinct variables) values per vertex label
     for (int64_t v = 0; v < s->n_states; v++) {
-        os << v << " [shape=" << (s->state_final[v] ? "doublecircle" : "circle") << ", label=\"" << s->state_cset[v] << ": ";
-        if (v == 0) os << "S";
+        line = std::to_string(v) + " [shape=" + (s->state_final[v] ? "doublecircle" : "circle") + ", label=\"" +
+               std::to_string(s->state_cset[v]) + ": ";
+        if (v == 0) line += "S";
         else
-            for (int32_t k = 0; k < s->sig_len; k++) os << (k ? ", " : "") << s->state_sig[v * s->sig_len + k];
-        os << "\"];\n";
+            for (int32_t k = 0; k < s->sig_len; k++) {
+                if (k) line += ", ";
+                line += std::to_string(s->state_sig[v * s->sig_len + k]);
+            }
+        line += "\"];\n";
+        sink(line);
         for (; e < s->n_edges && s->edge_src[e] == v; e++) {
-            os << v << " -> " << s->edge_dst[e] << " [label=\"";
-            for (int32_t k = 0; k < s->n_vars; k++) os << (k ? ", " : "") << s->edge_label[e * s->n_vars + k];
-            os << "\"];\n";
+            line = std::to_string(v) + " -> " + std::to_string(s->edge_dst[e]) + " [label=\"";
+            for (int32_t k = 0; k < s->n_vars; k++) {
+                if (k) line += ", ";
+                line += std::to_string(s->edge_label[e * s->n_vars + k]);
+            }
+            line += "\"];\n";
+            sink(line);
         }
     }
-    os << "}\n";
-    return dup_string(os.str());
+    sink(std::string("}\n"));
+}
+
+template <class Sink>
+void emit_canonical(const stcsp_problem_t *p, const stcsp_solution_t *s, Sink &&sink) {
+    if (!s->root_valid) { sink(std::string("EMPTY")); return; }
+    const Impl *impl = (const Impl *)s->impl;
+    sink(header_line(p, s, false, nullptr, 0) + "\n");
+    sink(header_line(p, s, true, impl->sig_vars.data(), (int32_t)impl->sig_vars.size()) + "\n");
+    std::string line;
+    for (int64_t v = 0; v < s->n_states; v++) {
+        line = "V " + std::to_string(v) + " " + (s->state_final[v] ? "F" : "N") + " " + std::to_string(s->state_cset[v]) + " ";
+        if (v == 0) line += "S";
+        else
+            for (int32_t k = 0; k < s->sig_len; k++) {
+                if (k) line += " ";
+                line += std::to_string(s->state_sig[v * s->sig_len + k]);
+            }
+        line += "\n";
+        sink(line);
+    }
+    char buf[16];
+    for (int64_t e = 0; e < s->n_edges; e++) {
+        line = "E " + std::to_string(s->edge_src[e]) + " " + std::to_string(s->edge_dst[e]);
+        const int32_t *lab = s->edge_label + e * s->n_vars;
+        for (int32_t k = 0; k < s->n_vars; k++) {
+            snprintf(buf, sizeof buf, " %d", lab[k]);
+            line += buf;
+        }
+        line += "\n";
+        sink(line);
+    }
+}
+
+struct FileSink {
+    FILE *f;
+    bool ok = true;
+    void operator()(const std::string &l) { ok = ok && fwrite(l.data(), 1, l.size(), f) == l.size(); }
+};
+
+template <class Emit>
+int write_file(const char *path, Emit &&emit) {
+    FILE *f = fopen(path, "wb");
+    if (!f) { stcsp::set_error(std::string("cannot write ") + path); return STCSP_ERR_INVALID; }
+    std::vector<char> big(1 << 20);
+    setvbuf(f, big.data(), _IOFBF, big.size());
+    FileSink sink{f};
+    emit(sink);
+    const bool closed = fclose(f) == 0;
+    if (!sink.ok || !closed) { stcsp::set_error(std::string("short write to ") + path); return STCSP_ERR_INVALID; }
+    return STCSP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+char *stcsp_solution_dot(const stcsp_problem_t *p, const stcsp_solution_t *s) {
+    std::string out;
+    emit_dot(p, s, [&](const std::string &l) { out += l; });
+    return dup_string(out);
 }
 
 char *stcsp_solution_canonical(const stcsp_problem_t *p, const stcsp_solution_t *s) {
-    if (!s->root_valid) return dup_string("EMPTY");
-    const Impl *impl = (const Impl *)s->impl;
-    std::ostringstream os;
-    os << header_line(p, s, false, nullptr, 0) << "\n";
-    os << header_line(p, s, true, impl->sig_vars.data(), (int32_t)impl->sig_vars.size()) << "\n";
-    for (int64_t v = 0; v < s->n_states; v++) {
-        os << "V " << v << " " << (s->state_final[v] ? "F" : "N") << " " << s->state_cset[v] << " ";
-        if (v == 0) os << "S";
-        else
-            for (int32_t k = 0; k < s->sig_len; k++) os << (k ? " " : "") << s->state_sig[v * s->sig_len + k];
-        os << "\n";
-    }
-    for (int64_t e = 0; e < s->n_edges; e++) {
-        os << "E " << s->edge_src[e] << " " << s->edge_dst[e];
-        for (int32_t k = 0; k < s->n_vars; k++) os << " " << s->edge_label[e * s->n_vars + k];
-        os << "\n";
-    }
-    return dup_string(os.str());
+    std::string out;
+    emit_canonical(p, s, [&](const std::string &l) { out += l; });
+    return dup_string(out);
+}
+
+int stcsp_solution_write_dot(const stcsp_problem_t *p, const stcsp_solution_t *s, const char *path) {
+    if (!p || !s || !path) { stcsp::set_error("null argument"); return STCSP_ERR_INVALID; }
+    return write_file(path, [&](FileSink &sink) { emit_dot(p, s, sink); });
+}
+
+int stcsp_solution_write_canonical(const stcsp_problem_t *p, const stcsp_solution_t *s, const char *path) {
+    if (!p || !s || !path) { stcsp::set_error("null argument"); return STCSP_ERR_INVALID; }
+    return write_file(path, [&](FileSink &sink) { emit_canonical(p, s, sink); });
+}
+
+int stcsp_solution_canonical_sha256(const stcsp_problem_t *p, const stcsp_solution_t *s, char out_hex[65]) {
+    if (!p || !s || !out_hex) { stcsp::set_error("null argument"); return STCSP_ERR_INVALID; }
+    stcsp::Sha256 sha;
+    emit_canonical(p, s, [&](const std::string &l) { sha.update(l.data(), l.size()); });
+    const std::string hex = sha.hex();
+    memcpy(out_hex, hex.c_str(), 65);
+    return STCSP_OK;
 }
 
 void stcsp_string_free(char *s) { free(s); }

@@ -54,3 +54,46 @@ def sample(model: binding.Model, seconds: float):
     if rc not in (0, binding.ERR_TIMEOUT):
         raise RuntimeError("oracle: %s" % lib().stcsp_oracle_last_error().decode())
     return stats
+
+
+# ---- the independent semantic oracle (oracle/semantic_oracle.cpp): BFS over signatures from the definition ----
+SEMANTIC_PATH = os.path.join(ROOT, "oracle", "libsemantic.so")
+
+
+class SemanticResult(C.Structure):
+    _fields_ = [("n_states", C.c_int64), ("n_edges", C.c_int64), ("n_table_states", C.c_int64),
+                ("n_raw_edges", C.c_int64), ("n_point_nodes", C.c_int64), ("root_valid", C.c_int32),
+                ("adver1", C.c_int32), ("adver2", C.c_int32), ("n_constraint_sets", C.c_int32),
+                ("seconds", C.c_double), ("sha256", C.c_char * 72)]
+
+
+_sem = None
+
+
+def semantic_lib():
+    global _sem
+    if _sem is None:
+        L = C.CDLL(SEMANTIC_PATH)
+        L.stcsp_semantic_solve.argtypes = [C.POINTER(binding.Problem), C.c_int, C.c_int, C.POINTER(SemanticResult),
+                                           C.POINTER(C.c_void_p)]
+        L.stcsp_semantic_last_error.restype = C.c_char_p
+        L.stcsp_semantic_free_text.argtypes = [C.c_void_p]
+        _sem = L
+    return _sem
+
+
+def semantic(model: binding.Model, adversarial1: bool = False, adversarial2: bool = False, want_text: bool = False):
+    """Canonical automaton from the definition.  Returns a dict (states, edges, sha256, text or None, ...)."""
+    res = SemanticResult()
+    text = C.c_void_p()
+    rc = semantic_lib().stcsp_semantic_solve(model.problem, int(adversarial1), int(adversarial2), C.byref(res),
+                                             C.byref(text) if want_text else None)
+    if rc != 0:
+        raise RuntimeError("semantic oracle: %s" % semantic_lib().stcsp_semantic_last_error().decode())
+    out = {k: getattr(res, k) for k, _ in SemanticResult._fields_}
+    out["sha256"] = res.sha256.decode()
+    out["text"] = None
+    if want_text:
+        out["text"] = C.string_at(text).decode()
+        semantic_lib().stcsp_semantic_free_text(text)
+    return out

@@ -24,7 +24,8 @@ def pytest_configure(config):
 def _ensure_built():
     lib = os.path.join(ROOT, "stcsp_solver_b200", "libstcsp_b200.so")
     orc = os.path.join(ROOT, "oracle", "liboracle.so")
-    if not (os.path.exists(lib) and os.path.exists(orc)):
+    sem = os.path.join(ROOT, "oracle", "libsemantic.so")
+    if not (os.path.exists(lib) and os.path.exists(orc) and os.path.exists(sem)):
         subprocess.check_call(["make", "-C", ROOT, "-j8"], stdout=subprocess.DEVNULL)
 
 
