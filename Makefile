@@ -34,7 +34,7 @@ $(LIB): $(OBJ)
 bin/stcsp: stcsp_solver_b200/csrc/cli/main.cpp $(LIB) $(HDR)
 	$(CXX) $(CXXFLAGS) -o $@ $< -Lstcsp_solver_b200 -lstcsp_b200 -Wl,-rpath,'$$ORIGIN/../stcsp_solver_b200'
 
-oracle:
+oracle: $(LIB)
 	$(MAKE) -C oracle
 
 clean:

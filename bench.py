@@ -283,7 +283,7 @@ ctx = time.perf_counter() - t0
 out = {"context_ms": ctx * 1e3, "solves": []}
 for i in range(3):
     t0 = time.perf_counter()
-    a = binding.solve(model)
+    a = binding.solve(model, binding.default_options(verbosity=1 if i == 0 else 0))      # the first solve reports its phases on stderr
     w = time.perf_counter() - t0
     out["solves"].append({"e2e_ms": w * 1e3, "device_ms": a.c.solve_ms, "launches": a.c.n_kernel_launches})
 print(json.dumps(out))
@@ -297,7 +297,8 @@ def cold_numbers(name, text, ref_wall_s):
         p = subprocess.run([sys.executable, "-c", COLD_SNIPPET % {"root": ROOT, "name": name}], capture_output=True, text=True,
                            timeout=600)
         j = json.loads(p.stdout.strip().split("\n")[-1])
-        out = {"context_ms": j["context_ms"], "first_solve_e2e_ms": j["solves"][0]["e2e_ms"],
+        phases = [ln for ln in p.stderr.split("\n") if ln.startswith("[stcsp] wall:")]
+        out = {"context_ms": j["context_ms"], "first_solve_phases": phases[0][len("[stcsp] wall: "):] if phases else None, "first_solve_e2e_ms": j["solves"][0]["e2e_ms"],
                "first_solve_device_ms": j["solves"][0]["device_ms"], "first_solve_launches": j["solves"][0]["launches"],
                "second_solve_e2e_ms": j["solves"][1]["e2e_ms"], "third_solve_e2e_ms": j["solves"][2]["e2e_ms"],
                "first_over_third": j["solves"][0]["e2e_ms"] / max(j["solves"][2]["e2e_ms"], 1e-9)}

@@ -107,7 +107,10 @@ typedef struct stcsp_options {
                                         variable of the current point is bound).  Never changes the automaton. */
     int32_t wide_wave_nodes;         /* waves wider than this run as separate full-occupancy launches instead of inside the
                                         persistent search kernel: 0 = default (32768), < 0 = never */
-    int32_t reserved[3];
+    int32_t single_branch;           /* 1: a search node branches on ONE variable (the first unbound one), like the reference's
+                                        solverGetFirstUnboundVar; 0 (default): narrow waves branch on up to three variables at
+                                        once, which shortens the search tree.  Never changes the automaton. */
+    int32_t reserved[2];
 } stcsp_options_t;
 
 /* ---------------------------------------------------------------------------------------------

@@ -25,5 +25,26 @@ for s in "${srcs[@]}"; do
 done
 g++ -std=gnu++98 -O2 -w -I"$here/refshim" -I"$ref" -c "$here/ref_frontend.cpp" -o "$out/ref_frontend.o"
 g++ -O2 "${objs[@]}" "$out/ref_frontend.o" -Wl,--wrap=malloc -o "$out/stcsp_ref"
-rm -f "$out"/*.o
 echo "built $out/stcsp_ref"
+# stcsp_ref_gpu: the same reference objects (front end stand-in, normaliser, post-processing, DOT writer) with the ONE call
+# solverSolve(Solver*, bool) redirected by the linker to oracle/gpu_bridge.cpp, i.e. to stcsp_gpu_solve of the product
+# library (the compiled form of the binding shown in INTEGRATION.md).  Needs the product library to be built first.
+lib="$here/../stcsp_solver_b200"
+if [ -f "$lib/libstcsp_b200.so" ]; then
+    g++ -std=gnu++98 -O2 -w -I"$here/refshim" -I"$ref" -I"$here/../include" -c "$here/gpu_bridge.cpp" -o "$out/gpu_bridge.o"
+    g++ -O2 "${objs[@]}" "$out/ref_frontend.o" "$out/gpu_bridge.o" -Wl,--wrap=malloc -Wl,--wrap=_Z11solverSolveP6Solverb \
+        -L"$lib" -lstcsp_b200 -Wl,-rpath,'$ORIGIN/../../stcsp_solver_b200' -o "$out/stcsp_ref_gpu"
+    echo "built $out/stcsp_ref_gpu"
+else
+    echo "build_ref: $lib/libstcsp_b200.so not built yet - skipping stcsp_ref_gpu" >&2
+fi
+# stcsp_ref_bridge_cpu: the same bridge with the CPU oracle behind the three C-ABI symbols (bridge_cpu_shim.cpp), so the
+# bridge code itself is covered by the CPU test suite
+if [ -f "$here/liboracle.so" ]; then
+    g++ -std=gnu++98 -O2 -w -I"$here/refshim" -I"$ref" -I"$here/../include" -c "$here/gpu_bridge.cpp" -o "$out/gpu_bridge.o"
+    g++ -O2 -I"$here/../include" -c "$here/bridge_cpu_shim.cpp" -o "$out/bridge_cpu_shim.o"
+    g++ -O2 "${objs[@]}" "$out/ref_frontend.o" "$out/gpu_bridge.o" "$out/bridge_cpu_shim.o" -Wl,--wrap=malloc \
+        -Wl,--wrap=_Z11solverSolveP6Solverb -L"$here" -loracle -Wl,-rpath,'$ORIGIN/..' -o "$out/stcsp_ref_bridge_cpu"
+    echo "built $out/stcsp_ref_bridge_cpu"
+fi
+rm -f "$out"/*.o

@@ -41,7 +41,8 @@ class Options(C.Structure):
         ("verbosity", C.c_int32), ("enum_limit_now", C.c_int64), ("enum_limit_ahead", C.c_int64),
         ("max_frontier_nodes", C.c_int64), ("max_states", C.c_int64), ("max_edges", C.c_int64),
         ("expand_mode", C.c_int32), ("profile_kernels", C.c_int32), ("no_trim", C.c_int32),
-        ("lookahead", C.c_int32), ("wide_wave_nodes", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("lookahead", C.c_int32), ("wide_wave_nodes", C.c_int32), ("single_branch", C.c_int32),
+                ("reserved", C.c_int32 * 2),
     ]
 
 

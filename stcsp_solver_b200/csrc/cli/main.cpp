@@ -9,7 +9,7 @@
 // (:975-983), and with -s the automaton in `solutions.dot` of the working directory (:709-730).
 // The search itself runs on the GPU through the C ABI (include/stcsp_b200.h); there is no CPU solver.
 // Extensions: --canonical (print the canonical automaton text instead of writing DOT),
-// --stats (print the GPU path's own counters on stderr).
+// --stats (print the GPU path's own counters on stderr), --sha256 (SHA-256 of the canonical text on stderr).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -25,7 +25,7 @@ namespace {
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Cli {
-    bool print_solution = false, testing = false, adv1 = false, adv2 = false, canonical = false, stats = false;
+    bool print_solution = false, testing = false, adv1 = false, adv2 = false, canonical = false, stats = false, sha256 = false;
     int prefix_k = 2, time_limit = 0, log_level = 0;
     const char *file = nullptr;
 };
@@ -79,16 +79,12 @@ int run_once(const Cli &cli, bool print_stat, Run &r) {
     }
     if (cli.adv1) printf("adver1: %d; ", sol.adver1);
     if (cli.adv2) printf("adver2: %d\n", sol.adver2);
-    if (cli.print_solution) {
-        char *dot = stcsp_solution_dot(problem, &sol);
-        FILE *f = fopen("solutions.dot", "w");
-        if (f) {
-            fputs(dot, f);
-            fclose(f);
-        } else {
-            fprintf(stderr, "stcsp: cannot write solutions.dot\n");
-        }
-        stcsp_string_free(dot);
+    if (cli.print_solution && stcsp_solution_write_dot(problem, &sol, "solutions.dot") != STCSP_OK)      // streamed line by line
+        fprintf(stderr, "stcsp: %s\n", stcsp_last_error());
+    if (cli.sha256) {
+        char hex[65];
+        if (stcsp_solution_canonical_sha256(problem, &sol, hex) == STCSP_OK)
+            fprintf(stderr, "canonical sha256 %s states %lld edges %lld\n", hex, (long long)sol.n_states, (long long)sol.n_edges);
     }
     if (cli.canonical) {
         char *txt = stcsp_solution_canonical(problem, &sol);
@@ -127,6 +123,7 @@ int main(int argc, char **argv) {
         }
         if (!strcmp(a, "--canonical")) { cli.canonical = true; continue; }
         if (!strcmp(a, "--stats")) { cli.stats = true; continue; }
+        if (!strcmp(a, "--sha256")) { cli.sha256 = true; continue; }
         for (const char *p = a + 1; *p; p++) {
             const char c = *p;
             if (c == 's') cli.print_solution = true;
@@ -153,7 +150,7 @@ int main(int argc, char **argv) {
         }
     }
     if (!cli.file) {
-        fprintf(stderr, "usage: stcsp [-s] [-m<sec>] [-t] [-a] [-z] [-k<K>] [-l<level>] [--canonical] [--stats] file.csp\n");
+        fprintf(stderr, "usage: stcsp [-s] [-m<sec>] [-t] [-a] [-z] [-k<K>] [-l<level>] [--canonical] [--stats] [--sha256] file.csp\n");
         return 1;
     }
     Run r;

@@ -99,6 +99,35 @@ __device__ __forceinline__ u64 shift_bits(u64 v, int s) {
     return s >= 0 ? (v << s) : (v >> (-s));
 }
 
+// ---- branching header ------------------------------------------------------------------------------------------
+// Word [3] of a search node names the variables its parent branched on: -1 = first node of a new state (every propagator
+// runs), else up to three variable indices, ten bits each, the upper two stored + 1 (0 = none).  Narrow waves branch on
+// SEVERAL variables at once (the cartesian product of their domains): the depth of the search tree, not its width, is
+// what a narrow instance waits for, and the machine has idle warps for the extra children.
+constexpr int kBranchVarBits = 10;
+__device__ __forceinline__ int pack_branch(int v0, int v1, int v2) {
+    return v0 | ((v1 + 1) << kBranchVarBits) | ((v2 + 1) << (2 * kBranchVarBits));
+}
+// propagators to run first in a node whose header word is `hdr` (word w of the mask)
+__device__ __forceinline__ uint32_t initial_dirty(const DevModel &M, const DevSet &S, int hdr, int w) {
+    if (hdr < 0) {
+        const int left = S.n_prop - w * 32;
+        return left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+    }
+    const uint32_t *wk = M.wake + S.wake_off + w;
+    const int mask = (1 << kBranchVarBits) - 1;
+    uint32_t m = wk[((size_t)(hdr & mask) * M.k) * S.n_words];
+    const int v1 = ((hdr >> kBranchVarBits) & mask) - 1, v2 = ((hdr >> (2 * kBranchVarBits)) & mask) - 1;
+    if (v1 >= 0) m |= wk[((size_t)v1 * M.k) * S.n_words];
+    if (v2 >= 0) m |= wk[((size_t)v2 * M.k) * S.n_words];
+    return m;
+}
+// the n-th (0-based) set bit of d, as a one-bit mask
+__device__ __forceinline__ u64 nth_bit(u64 d, int n) {
+    for (int i = 0; i < n; i++) d &= d - 1;
+    return d & (~d + 1ull);
+}
+
 // ---- bytecode evaluator: one tuple per lane (reference solverValidateRe) --------------------------
 template <int LS>   // LS = distance between consecutive stack/scope slots of one lane (32: warp-interleaved, 1: private)
 __device__ __forceinline__ int eval_tuple(const Instr *__restrict__ code, const int32_t *cur, int32_t *stk, int lane,
@@ -673,6 +702,8 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                 if (!(wm.dirty[q >> 5] & bit)) continue;
                 if (held && (ahead[q >> 5] & bit)) continue;
                 atomicAnd(&wm.dirty[q >> 5], ~bit);
+                __threadfence_block();      // the domains are read AFTER the bit is cleared: a wake that lands in between re-arms
+                                            // this propagator instead of being erased while it still sees the old domain
                 const int r = scalar_revise(M, S, q, ctx.dom, wm.dirty, ctx.expire, my_tuples, CTA ? kScalarWalkCta : kScalarWalk);
                 st_rev++;
                 if (r == SR_FAIL) myfail = true;
@@ -864,16 +895,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
         for (int i = lane; i < V * k; i += 32) empty |= dom[i] == 0ull;
         bool fail = __any_sync(0xffffffffu, empty);
 
-        for (int w = gtid; w < S.n_words; w += gthreads) {
-            uint32_t m;
-            if (bvar < 0) {
-                const int left = S.n_prop - w * 32;
-                m = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
-            } else {
-                m = M.wake[S.wake_off + ((size_t)bvar * k) * S.n_words + w];
-            }
-            wm.dirty[w] = m;
-        }
+        for (int w = gtid; w < S.n_words; w += gthreads) wm.dirty[w] = initial_dirty(M, S, bvar, w);
         if (CTA) __syncthreads(); else __syncwarp();
 
         if (!fail) fail = propagate<CTA>(ctx, gw, gtid, gthreads, st_rev, my_tuples);   // `fail` is uniform over the group
@@ -903,8 +925,29 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
             if (lane < 4) rec[lane] = lane == 3 ? 0 : wm.nodew[lane];
             for (int v = lane; v < V; v += 32) rec[4 + v] = M.lb[v] + __ffsll((long long)dom[v * k]) - 1;
         } else {
+            // branch: on the first unbound variable, and -- while the wave is narrow enough that every child still gets a
+            // warp of its own (P.fan, set per wave) -- on the next one or two as well
+            int bv1 = -1, bv2 = -1;
+            u64 D1 = 1ull, D2 = 1ull;
             const u64 D = dom[bv * k];
-            const int d = __popcll(D);
+            int d = __popcll(D);
+            if (d < P.fan) {
+                for (int base = 0; base < V && bv2 < 0; base += 32) {
+                    const int v = base + lane;
+                    const bool unbound = v < V && v > bv && __popcll(dom[v * k]) > 1;
+                    unsigned b = __ballot_sync(0xffffffffu, unbound);
+                    while (b && bv2 < 0) {
+                        const int cand = base + __ffs(b) - 1;
+                        b &= b - 1;
+                        const u64 Dc = dom[cand * k];
+                        if ((long long)d * __popcll(Dc) > (long long)P.fan) { bv2 = -2; break; }       // would be too many: stop here
+                        if (bv1 < 0) { bv1 = cand; D1 = Dc; } else { bv2 = cand; D2 = Dc; }
+                        d *= __popcll(Dc);
+                    }
+                }
+                if (bv2 == -2) bv2 = -1;
+            }
+            const int d0 = __popcll(D), d1 = __popcll(D1);
             unsigned long long base = 0;
             if (CTA) {
                 if (threadIdx.x == 0) {
@@ -922,17 +965,22 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
                 if (gtid == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
                 continue;
             }
-            const int dw = 4 + 2 * (bv * k);
-            int j = 0;
-            for (u64 w = D; w; w &= w - 1, j++) {
-                if ((j % gwarps) != gw) continue;
-                const u64 one = w & (~w + 1ull);
+            const int hdr = pack_branch(bv, bv1, bv2);
+            const int dw = 4 + 2 * (bv * k), dw1 = bv1 >= 0 ? 4 + 2 * (bv1 * k) : -8, dw2 = bv2 >= 0 ? 4 + 2 * (bv2 * k) : -8;
+            for (int j = gw; j < d; j += gwarps) {
+                const u64 one = nth_bit(D, j % d0);
+                const u64 one1 = bv1 >= 0 ? nth_bit(D1, (j / d0) % d1) : 0ull;
+                const u64 one2 = bv2 >= 0 ? nth_bit(D2, j / (d0 * d1)) : 0ull;
                 int32_t *dst = P.out_nodes + (base + j) * NW;
                 for (int i = lane; i < NW; i += 32) {
                     int32_t val = wm.nodew[i];
-                    if (i == 3) val = bv;
+                    if (i == 3) val = hdr;
                     else if (i == dw) val = (int32_t)(uint32_t)(one & 0xffffffffull);
                     else if (i == dw + 1) val = (int32_t)(uint32_t)(one >> 32);
+                    else if (i == dw1) val = (int32_t)(uint32_t)(one1 & 0xffffffffull);
+                    else if (i == dw1 + 1) val = (int32_t)(uint32_t)(one1 >> 32);
+                    else if (i == dw2) val = (int32_t)(uint32_t)(one2 & 0xffffffffull);
+                    else if (i == dw2 + 1) val = (int32_t)(uint32_t)(one2 >> 32);
                     dst[i] = val;
                 }
             }
@@ -985,18 +1033,8 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
         if (have)
             for (int i = gl; i < V * k; i += 8) empty |= dom[i] == 0ull;
         bool fail = (__ballot_sync(0xffffffffu, empty) & gmask) != 0u;
-        if (have) {
-            for (int w = gl; w < S.n_words; w += 8) {
-                uint32_t m;
-                if (bvar < 0) {
-                    const int left = S.n_prop - w * 32;
-                    m = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
-                } else {
-                    m = M.wake[S.wake_off + ((size_t)bvar * k) * S.n_words + w];
-                }
-                wm.dirty[w] = m;
-            }
-        }
+        if (have)
+            for (int w = gl; w < S.n_words; w += 8) wm.dirty[w] = initial_dirty(M, S, bvar, w);
         __syncwarp();
 
         // ---- propagate the four nodes in lock step (the host never picks this mode with lazy look-ahead)
@@ -1009,6 +1047,7 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
                     const uint32_t bit = 1u << (q & 31);
                     if (!(wm.dirty[q >> 5] & bit)) continue;
                     atomicAnd(&wm.dirty[q >> 5], ~bit);
+                    __threadfence_block();  // as in propagate(): clear the bit, THEN read the domains
                     const int r = scalar_revise(M, S, q, dom, wm.dirty, expire, my_tuples, kScalarWalk);
                     st_rev++;
                     if (r == SR_FAIL) myfail = true;
@@ -1123,7 +1162,7 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
                     int32_t *dst = P.out_nodes + (slot + j) * NW;
                     for (int i = gl; i < NW; i += 8) {
                         int32_t val = wm.nodew[i];
-                        if (i == 3) val = bv;
+                        if (i == 3) val = pack_branch(bv, -1, -1);
                         else if (i == dw) val = (int32_t)(uint32_t)(one & 0xffffffffull);
                         else if (i == dw + 1) val = (int32_t)(uint32_t)(one >> 32);
                         dst[i] = val;
@@ -1622,7 +1661,10 @@ __global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const Ing
 // block 0 clears the set of wave w-1 after the barrier of wave w -- every block has finished reading it by then --
 // and no block touches that set again before it has passed the barrier of wave w+1, which block 0 reaches only after
 // the clearing.  C_STATES and C_EDGES (never reset) live in set 0.
-__global__ void __launch_bounds__(kExpandWarps * 32, kExpandCtasPerSm) search_kernel(const DevModel M, SearchArgs A) {
+// Two instantiations: CTAS = kExpandCtasPerSm for the full grid (80 registers per thread, the inlined expand bodies spill
+// a little), CTAS = 1 for the narrow grid of one CTA per SM, where ptxas may use 255 registers and nothing spills.
+template <int CTAS>
+__global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const DevModel M, SearchArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     volatile SearchCtl *ctl = A.ctl;
@@ -1728,6 +1770,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, kExpandCtasPerSm) search_ke
             ea.out_cap = A.out_cap;
             ea.leaves = A.leaves;
             ea.leaf_cap = A.leaf_cap;
+            ea.fan = branch_fan(M, c_n_in, A.out_cap);
             ea.counters = A.counters + set * kCounterStride;
             ea.dbg = A.trace ? A.trace + 5 * A.trace_cap : nullptr;     // block 0's timeline follows the per-wave stamps
             ea.dbg_cap = A.trace ? 4096 : 0;
@@ -1987,27 +2030,33 @@ int search_max_grid(const DevModel &m, int sm_count) {
     const size_t smem = expand_smem_bytes(m);
     static size_t configured = 0;
     if (smem > configured) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (smem > 48 * 1024) {
+            cudaFuncSetAttribute(search_kernel<kExpandCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        cudaFuncSetAttribute(search_kernel<kExpandCtasPerSm>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(search_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = smem;
     }
     static size_t cached_smem = ~(size_t)0;
     static int cached_per_sm = 0;
     if (smem == cached_smem) return cached_per_sm * sm_count;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel, kExpandWarps * 32, smem) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<kExpandCtasPerSm>, kExpandWarps * 32, smem) != cudaSuccess ||
+        per_sm < 1)
         per_sm = 0;
     cached_smem = smem;
     cached_per_sm = per_sm;
     return per_sm * sm_count;
 }
 
-cudaError_t launch_search(const DevModel &m, const SearchArgs &a, int grid, cudaStream_t stream) {
+cudaError_t launch_search(const DevModel &m, const SearchArgs &a, int grid, int sm_count, cudaStream_t stream) {
     const size_t smem = expand_smem_bytes(m);
     DevModel mm = m;
     SearchArgs aa = a;
     void *params[] = {&mm, &aa};
-    return cudaLaunchCooperativeKernel((const void *)search_kernel, dim3(grid), dim3(kExpandWarps * 32), params, smem, stream);
+    const void *fn = grid <= sm_count ? (const void *)search_kernel<1> : (const void *)search_kernel<kExpandCtasPerSm>;
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kExpandWarps * 32), params, smem, stream);
 }
 
 void launch_route(const DevModel &m, const RouteArgs &a, int grid, cudaStream_t stream) {

@@ -51,6 +51,8 @@ struct DevModel {
     int32_t node_slots;         // node blocks per CTA in shared memory: 8 (one per warp) or 32 (four per warp, quad mode)
     int32_t force_mode;         // 0 automatic, else ExpandMode + 1
     int32_t lazy_ahead;         // 1: pointwise propagators at look-ahead offsets run only once the current point is bound
+    int32_t multi_branch;       // 1: narrow waves branch on up to three variables at once (branch_fan)
+    int32_t fan_warps;          // warps of the narrow search grid (SM count x warps per CTA)
     long long enum_now, enum_ahead;
     const int32_t *lb, *width, *sig_vars;
     const DevSet *sets;
@@ -79,6 +81,8 @@ struct ExpandArgs {
     long long out_cap;
     int32_t *leaves;
     long long leaf_cap;
+    int fan;                    // most children one node may create this wave (branch_fan): > the first variable's domain
+                                // means the node branches on further variables too
     unsigned long long *counters;
     unsigned long long *dbg;    // optional timeline of block 0 (CTA mode): dbg[0] = entries used, then (tag, %globaltimer) pairs
     int dbg_cap;
@@ -181,9 +185,19 @@ __host__ __device__ inline int pick_expand_mode(const DevModel &m, long long n_i
     if (quad_ok && n_in >= 2ll * kExpandWarps * ctas) return EXPAND_QUAD;       // two nodes per resident warp or more
     return EXPAND_WARP;
 }
+// Children a node of a wave of n_in nodes may create: as long as the NEXT wave still has a resident warp per node
+// (m.fan_warps = warps of the narrow grid, one CTA per SM), branching on several variables at once saves whole waves and costs nothing but
+// idle lanes.  1 = never more than the first unbound variable's domain.  Off in lazy look-ahead mode and when a mapping of
+// nodes to threads is forced (tests compare the statistics of the paths).
+__host__ __device__ inline int branch_fan(const DevModel &m, long long n_in, long long out_cap) {
+    if (m.multi_branch == 0 || n_in <= 0) return 1;
+    const long long warps = m.fan_warps;        // the same on every path, so that their search statistics agree
+    const long long room = (warps < out_cap / 2 ? warps : out_cap / 2) / n_in;
+    return room < 1 ? 1 : (room > 4096 ? 4096 : (int)room);
+}
 // persistent wave loop (cooperative launch); search_max_grid = co-resident CTAs, 0 if unavailable
 int search_max_grid(const DevModel &m, int sm_count);
-cudaError_t launch_search(const DevModel &m, const SearchArgs &a, int grid, cudaStream_t stream);
+cudaError_t launch_search(const DevModel &m, const SearchArgs &a, int grid, int sm_count, cudaStream_t stream);
 void launch_route(const DevModel &m, const RouteArgs &a, int grid, cudaStream_t stream);
 void launch_ingest(const DevModel &m, const IngestArgs &a, int grid, cudaStream_t stream);
 // group the routed local leaves by owner rank into `outbox` (dev_offsets = exclusive prefix of the owner counts)

@@ -8,6 +8,7 @@
 // There is no CPU solver in this file: without a CUDA device every entry point fails with
 // STCSP_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <chrono>
@@ -18,6 +19,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../host/error.h"
@@ -41,52 +43,83 @@ struct Failure : std::runtime_error {
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// Process-wide cache of device blocks (power-of-two size classes, per device).  cudaMalloc / cudaFree cost
-// 0.3-0.6 ms each on B200 and the stream-ordered pool showed 5-350 ms stalls when it had to grow, so blocks
-// released by one solve are kept and handed to the next: in steady state a solve allocates nothing.
+// Process-wide cache of device blocks (power-of-two size classes, per device), carved out of a few large ARENAS.
+// cudaMalloc / cudaFree cost 0.3-0.6 ms each on B200 and the stream-ordered pool showed 5-350 ms stalls when it had to
+// grow, so (1) blocks released by one solve are kept and handed to the next -- in steady state a solve allocates nothing --
+// and (2) a block that is not cached is a bump allocation from an arena, so that the FIRST solve of a process pays for
+// one cudaMalloc instead of thirty (round 1: 10 ms of first-solve wall time on the headline instance were cudaMalloc).
 struct DeviceCache {
     std::mutex mu;
     std::map<std::pair<int, size_t>, std::vector<void *>> free_blocks;
+    struct Arena {
+        int device;
+        char *base;
+        size_t size, used;
+    };
+    std::vector<Arena> arenas;
+    std::map<int, long long> outstanding;           // blocks handed out per device
+    static constexpr size_t kFirstArena = (size_t)256 << 20;
     static size_t size_class(size_t bytes) {
         size_t c = 4096;
         while (c < bytes) c <<= 1;
         return c;
     }
     void *acquire(int device, size_t bytes) {       // bytes must be a size class
-        {
-            std::lock_guard<std::mutex> g(mu);
-            auto it = free_blocks.find({device, bytes});
-            if (it != free_blocks.end() && !it->second.empty()) {
-                void *p = it->second.back();
-                it->second.pop_back();
+        std::lock_guard<std::mutex> g(mu);
+        outstanding[device]++;
+        auto it = free_blocks.find({device, bytes});
+        if (it != free_blocks.end() && !it->second.empty()) {
+            void *p = it->second.back();
+            it->second.pop_back();
+            return p;
+        }
+        size_t biggest = 0;
+        for (Arena &a : arenas) {
+            if (a.device != device) continue;
+            biggest = std::max(biggest, a.size);
+            if (a.size - a.used >= bytes) {
+                void *p = a.base + a.used;
+                a.used += bytes;                    // size classes are multiples of 4096: every block stays 4 KiB-aligned
                 return p;
             }
         }
+        // a new arena: at least twice the largest so far (the pools of one solve double as they grow)
+        size_t want = std::max(bytes, biggest ? biggest * 2 : kFirstArena);
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) {                     // give the cached blocks back to the driver and retry once
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess && want > bytes) {     // not that much room left: just what is needed
             cudaGetLastError();
-            trim(device);
-            e = cudaMalloc(&p, bytes);
+            want = bytes;
+            e = cudaMalloc(&p, want);
         }
         if (e != cudaSuccess) {
             cudaGetLastError();
+            outstanding[device]--;
             throw Failure(STCSP_ERR_CAPACITY, "device allocation of " + std::to_string(bytes) + " bytes failed: " +
                                                   cudaGetErrorString(e));
         }
+        arenas.push_back(Arena{device, (char *)p, want, bytes});
         return p;
     }
     void give_back(int device, size_t bytes, void *p) {
         std::lock_guard<std::mutex> g(mu);
+        outstanding[device]--;
         free_blocks[{device, bytes}].push_back(p);
     }
+    // Give the memory back to the driver.  Blocks are slices of arenas, so this only happens when nothing is in use.
     void trim(int device) {
         std::lock_guard<std::mutex> g(mu);
+        if (outstanding[device] > 0) return;
         for (auto &kv : free_blocks)
-            if (kv.first.first == device) {
-                for (void *p : kv.second) cudaFree(p);
-                kv.second.clear();
+            if (kv.first.first == device) kv.second.clear();
+        for (size_t i = 0; i < arenas.size();) {
+            if (arenas[i].device == device) {
+                cudaFree(arenas[i].base);
+                arenas.erase(arenas.begin() + (long)i);
+            } else {
+                i++;
             }
+        }
     }
 };
 DeviceCache &device_cache() {
@@ -248,30 +281,133 @@ ExecPool &exec_pool() {
     return *p;
 }
 
-// Pinned host blocks for the counter read-back, cached per process (cudaMallocHost costs ~1 ms).
-struct PinnedCache {
+// Host memory the device writes into: always PINNED, but never through cudaMallocHost.
+//
+// Measured on this pool's B200 hosts (tools/micro/alloc_cost.cu): cudaMallocHost costs 2-3 ms even for 4 KiB and
+// 0.45 ms per MiB beyond (128 MiB: 60 ms); an anonymous mapping faulted in by four threads costs 0.035 ms per MiB and
+// cudaHostRegister of the populated range 0.03 ms per MiB (128 MiB: 4.5 + 4.2 ms).  Round 1 pinned the 89 MiB automaton of
+// partialorder_14 with cudaMallocHost: 80 ms of a 96 ms first solve.  So a block is mmap + parallel populate +
+// cudaHostRegister; small blocks (<= 256 KiB: counters, the automaton of a small instance) are slices of an arena made
+// the same way, so that the first solve of a process registers host memory once.  Released blocks are cached by size
+// class like the device blocks.  If registration fails the block stays pageable and is filled through two pinned
+// staging chunks (download()).
+struct HostCache {
+    enum Kind : int { PINNED = 0, PAGEABLE = 1 };
     std::mutex mu;
-    std::vector<unsigned long long *> free_blocks;
-    unsigned long long *acquire() {
+    std::map<size_t, std::vector<void *>> free_blocks;        // registered, by size class
+    struct Arena {
+        char *base;
+        size_t size, used;
+    };
+    std::vector<Arena> arenas;
+    static constexpr size_t kSmall = (size_t)256 << 10;
+    static constexpr size_t kFirstArena = (size_t)1 << 20;
+    void *acquire(size_t bytes, int &kind) {
+        kind = PINNED;
         {
             std::lock_guard<std::mutex> g(mu);
-            if (!free_blocks.empty()) {
-                unsigned long long *b = free_blocks.back();
-                free_blocks.pop_back();
-                return b;
+            auto it = free_blocks.find(bytes);
+            if (it != free_blocks.end() && !it->second.empty()) {
+                void *p = it->second.back();
+                it->second.pop_back();
+                return p;
+            }
+            if (bytes <= kSmall) {
+                for (Arena &a : arenas)
+                    if (a.size - a.used >= bytes) {
+                        void *p = a.base + a.used;
+                        a.used += bytes;
+                        return p;
+                    }
+                const size_t want = arenas.empty() ? kFirstArena : std::min<size_t>(arenas.back().size * 2, (size_t)64 << 20);
+                int k = PINNED;
+                void *p = map_and_register(want, k);
+                if (k == PINNED) {
+                    arenas.push_back(Arena{(char *)p, want, bytes});
+                    return p;
+                }
+                munmap(p, want);
             }
         }
-        unsigned long long *b = nullptr;
-        CK(cudaMallocHost(&b, C_COUNT * sizeof(unsigned long long) + 256));
-        return b;
+        return map_and_register(bytes, kind);
     }
-    void give_back(unsigned long long *b) {
+    void give_back(void *p, size_t bytes, int kind) {
+        if (kind == PAGEABLE) { munmap(p, bytes); return; }
         std::lock_guard<std::mutex> g(mu);
-        free_blocks.push_back(b);
+        free_blocks[bytes].push_back(p);
+    }
+    // Anonymous mapping (huge pages requested), faulted in by up to four threads, then registered with the driver.
+    static void *map_and_register(size_t bytes, int &kind) {
+        void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p == MAP_FAILED) throw std::bad_alloc();
+#ifdef MADV_HUGEPAGE
+        madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+        auto populate = [p](size_t lo, size_t hi) {
+#ifdef MADV_POPULATE_WRITE
+            if (madvise((char *)p + lo, hi - lo, MADV_POPULATE_WRITE) == 0) return;
+#endif
+            for (size_t o = lo; o < hi; o += 4096) ((volatile char *)p)[o] = 0;
+        };
+        const size_t slice = (size_t)4 << 20;
+        const size_t n_threads = std::min<size_t>(4, bytes / slice);
+        if (n_threads >= 2) {
+            std::vector<std::thread> pool;
+            const size_t per = ((bytes / n_threads) + 4095) & ~(size_t)4095;
+            for (size_t t = 1; t < n_threads; t++) {
+                const size_t lo = t * per, hi = t + 1 == n_threads ? bytes : std::min(bytes, lo + per);
+                if (lo < hi) pool.emplace_back(populate, lo, hi);
+            }
+            populate(0, std::min(bytes, per));
+            for (std::thread &t : pool) t.join();
+        } else {
+            populate(0, bytes);
+        }
+        kind = PINNED;
+        if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+            cudaGetLastError();
+            kind = PAGEABLE;
+        }
+        return p;
+    }
+    void release_all() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &kv : free_blocks) {
+            for (void *p : kv.second) {
+                bool in_arena = false;
+                for (const Arena &a : arenas) in_arena |= (char *)p >= a.base && (char *)p < a.base + a.size;
+                if (!in_arena) {
+                    cudaHostUnregister(p);
+                    munmap(p, kv.first);
+                }
+            }
+            kv.second.clear();
+        }
+        // (arena slices may still be referenced by live automata: the arenas stay)
     }
 };
+HostCache &host_cache() {
+    static HostCache *c = new HostCache();      // leaked on purpose: outlives the CUDA context teardown order
+    return *c;
+}
+
+// The counter read-back block of a session: a small pinned block like any other.
+struct PinnedCache {
+    static constexpr size_t kBytes = 4096;
+    unsigned long long *acquire() {
+        static_assert(C_COUNT * sizeof(unsigned long long) + 256 <= kBytes, "counter block");
+        int kind = 0;
+        void *p = host_cache().acquire(kBytes, kind);
+        if (kind != HostCache::PINNED) {
+            host_cache().give_back(p, kBytes, kind);
+            throw Failure(STCSP_ERR_CUDA, "cannot pin host memory for the counter read-back");
+        }
+        return (unsigned long long *)p;
+    }
+    void give_back(unsigned long long *b) { host_cache().give_back(b, kBytes, HostCache::PINNED); }
+};
 PinnedCache &pinned_cache() {
-    static PinnedCache *c = new PinnedCache();      // leaked on purpose: outlives the CUDA context teardown order
+    static PinnedCache *c = new PinnedCache();
     return *c;
 }
 
@@ -295,58 +431,32 @@ void bind_store(stcsp_automaton_t *a, AutoStore *st) {
     a->edge_label = st->edge_label.data();
 }
 
-// Pinned host blocks, cached per process by size class: the automaton is copied device -> host once, at PCIe speed,
-// into memory the caller reads in place (fresh pageable memory costs ~2.5 GB/s in page faults + staging).
-struct HostCache {
-    std::mutex mu;
-    std::map<size_t, std::vector<void *>> free_blocks;
-    static constexpr size_t kMaxPinned = (size_t)4 << 30;      // larger blocks are plain malloc, filled through pinned staging
-    void *acquire(size_t bytes, bool &pinned) {
-        pinned = bytes <= kMaxPinned;
-        if (!pinned) {
-            void *p = malloc(bytes);
-            if (!p) throw std::bad_alloc();
-            return p;
-        }
-        {
-            std::lock_guard<std::mutex> g(mu);
-            auto it = free_blocks.find(bytes);
-            if (it != free_blocks.end() && !it->second.empty()) {
-                void *p = it->second.back();
-                it->second.pop_back();
-                return p;
-            }
-        }
-        void *p = nullptr;
-        if (cudaMallocHost(&p, bytes) != cudaSuccess) {
-            cudaGetLastError();
-            pinned = false;
-            p = malloc(bytes);
-            if (!p) throw std::bad_alloc();
-        }
-        return p;
-    }
-    void give_back(void *p, size_t bytes, bool pinned) {
-        if (!pinned) { free(p); return; }
-        std::lock_guard<std::mutex> g(mu);
-        free_blocks[bytes].push_back(p);
-    }
-};
-HostCache &host_cache() {
-    static HostCache *c = new HostCache();
-    return *c;
-}
-
 struct HostBlock {
     void *p = nullptr;
     size_t bytes = 0;
-    bool pinned = false;
+    int kind = HostCache::PINNED;
+    bool pinned() const { return kind == HostCache::PINNED; }
     void alloc(size_t need) {
         bytes = DeviceCache::size_class(std::max<size_t>(need, 1));
-        p = host_cache().acquire(bytes, pinned);
+        p = host_cache().acquire(bytes, kind);
     }
-    ~HostBlock() { if (p) host_cache().give_back(p, bytes, pinned); }
+    ~HostBlock() { if (p) host_cache().give_back(p, bytes, kind); }
 };
+
+// dst <- src with up to four threads (one thread copies ~10 GB/s, a PCIe 5 link delivers ~50 GB/s)
+void parallel_copy(void *dst, const void *src, size_t n) {
+    const size_t piece = (size_t)8 << 20;
+    if (n < 2 * piece) { memcpy(dst, src, n); return; }
+    const size_t n_threads = std::min<size_t>(4, n / piece);
+    const size_t per = (n + n_threads - 1) / n_threads;
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < n_threads; t++) {
+        const size_t lo = t * per, hi = std::min(n, lo + per);
+        if (lo < hi) pool.emplace_back([=] { memcpy((char *)dst + lo, (const char *)src + lo, hi - lo); });
+    }
+    memcpy(dst, src, std::min(n, per));
+    for (std::thread &t : pool) t.join();
+}
 
 struct PinnedStore : Store {    // single-rank automata finished on the device
     HostBlock sig_vars, state_sig, state_cset, state_failed, edge_src, edge_dst, edge_label;
@@ -374,7 +484,11 @@ struct stcsp_session {
     bool time_expand = false;                               // expand launches of run_persistent's wide waves are timed
     static constexpr long long kWideWaveNodes = 32768;     // default of stcsp_options_t::wide_wave_nodes
     static constexpr long long kNarrowInstanceWave = 2048; // widest wave of an instance that runs on one CTA per SM
+    static constexpr long long kFirstFrontier = 32768, kFirstStates = 65536, kFirstEdges = 262144;    // pool sizes of a first solve
+    bool wide_grid = false;         // the narrow (one CTA per SM) grid was given up for this solve
     bool search_complete = false;                           // the wave loop ran to the end (max_wave is the instance's)
+    bool poisoned = false;          // a pool overflowed in mid-wave (table slots tombstoned, cursors past their capacity):
+                                    // unreachable as long as every path pre-reserves n_states + n, fatal for the session if not
     bool prefinished = false;       // the search kernel already grouped + trimmed (fb_* hold the result)
     long long prefinished_dead = 0;
     SearchCtl *h_ctl = nullptr;     // pinned, behind h_counters
@@ -400,8 +514,10 @@ struct stcsp_session {
     ~stcsp_session() {
         if (stream) cudaStreamSynchronize(stream);
         if (h_counters) pinned_cache().give_back(h_counters);
-        if (model && !cache_key.empty() && model->uploaded && !model->sets.dirty() && model->sets.table_jobs.empty() &&
-            model->tables_built == model->sets.table_words && dm.node_words > 0) {
+        // Only a solve that ran to the end hands its model back: after a failure (an exception between the host and the
+        // device update of the transition map, a timeout, a CUDA error) the host and device copies may disagree.
+        if (model && search_complete && !poisoned && !cache_key.empty() && model->uploaded && !model->sets.dirty() &&
+            model->sets.table_jobs.empty() && model->tables_built == model->sets.table_words && dm.node_words > 0) {
             model->hint_frontier = (long long)std::min(frontier[0].cap, frontier[1].cap) / dm.node_words;
             model->hint_states = (long long)state_key.cap / dm.key_words;
             model->hint_edges = (long long)edge_src.cap;
@@ -497,6 +613,9 @@ struct stcsp_session {
             dm.stage_bytes = sb <= 40 * 1024 ? (int32_t)sb : 0;     // larger model->sets stay in global memory / L1
         }
         dm.lazy_ahead = opt.lookahead == 2 ? 1 : 0;
+        dm.multi_branch = opt.single_branch ? 0 : 1;
+        dm.fan_warps = sm_count * kExpandWarps;
+        if (dm.V >= (1 << 10) - 1) dm.multi_branch = 0;        // the node header packs variable indices in ten bits
         // four node blocks per warp (quad mode for wide waves) when three CTAs still fit an SM
         dm.node_slots = 4 * kExpandWarps;
         if (expand_smem_bytes(dm) > (216 / kExpandCtasPerSm) * 1024) dm.node_slots = kExpandWarps;
@@ -599,8 +718,11 @@ struct stcsp_session {
         d_offsets.reserve(2 * kMaxWorld, 0, stream);
 
         const int NW = dm.node_words, KW = dm.key_words;
-        const size_t f0 = (size_t)std::max<long long>(4096, model->hint_frontier), s0 = (size_t)std::max<long long>(4096, model->hint_states),
-                     e0 = (size_t)std::max<long long>(8192, model->hint_edges);
+        // First solve of a model: pools that the shipped instances up to a few ten thousand states never outgrow (the blocks
+        // come from the arena, so their size costs nothing; growing them in mid-search costs a kernel relaunch each time).
+        const size_t f0 = (size_t)std::max<long long>(kFirstFrontier, model->hint_frontier),
+                     s0 = (size_t)std::max<long long>(kFirstStates, model->hint_states),
+                     e0 = (size_t)std::max<long long>(kFirstEdges, model->hint_edges);
         frontier[0].reserve(f0 * NW, 0, stream);
         frontier[1].reserve(f0 * NW, 0, stream);
         leaves.reserve(f0 * dm.rec_words, 0, stream);
@@ -682,9 +804,17 @@ struct stcsp_session {
             sa.edge_cap = (long long)std::min(edge_src.cap, edge_label.cap / (size_t)V);
             const long long wide = opt.wide_wave_nodes < 0 ? 0 : opt.wide_wave_nodes > 0 ? opt.wide_wave_nodes : kWideWaveNodes;
             sa.max_frontier = opt.max_frontier_nodes > 0 && (wide == 0 || opt.max_frontier_nodes < wide) ? opt.max_frontier_nodes : wide;
+            // An instance whose waves stay narrow gets one CTA per SM: with a third of the CTAs the grid barrier is cheaper
+            // and a node's CTA has the SM to itself (b6_nosym -7 %, b5_f6 -8 %); anything wider needs all resident warps
+            // (digitinvader7 with 148 CTAs: +22 %).  Every solve STARTS narrow unless the last solve of this model is known
+            // to have been wide; the kernel yields at the first wave wider than kNarrowInstanceWave and is relaunched on the
+            // full grid (one relaunch per solve, which a wide instance does not notice).
+            const bool narrow = !wide_grid && search_grid > sm_count &&
+                                !(model->hint_max_wave > kNarrowInstanceWave) && n_in <= kNarrowInstanceWave;
+            if (narrow && (sa.max_frontier == 0 || sa.max_frontier > kNarrowInstanceWave)) sa.max_frontier = kNarrowInstanceWave;
             // automata known (from the last solve of this model) to be small are finished inside the kernel
-            if (finish_in_kernel && model->hint_states > 0 && model->hint_edges <= (1ll << 18)) {
-                const long long cs = std::max<long long>(model->hint_states, 4096), ce = std::max<long long>(model->hint_edges, 8192);
+            if (finish_in_kernel && std::max<long long>(model->hint_edges, (long long)edge_src.cap) <= (1ll << 18)) {
+                const long long cs = std::max<long long>((long long)(state_key.cap / KW), 4096), ce = std::max<long long>((long long)edge_src.cap, 8192);
                 const int SLm = std::max(dm.sig_len, 1);
                 fb_deg.reserve((size_t)cs + 1, 0, stream);
                 fb_first.reserve((size_t)cs + 1, 0, stream);
@@ -719,13 +849,9 @@ struct stcsp_session {
             h_ctl->waves_left = deadline > 0 ? 256 : (1ll << 40);
             CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof *h_ctl, cudaMemcpyHostToDevice, stream));
             zero_wave_counters();
-            // An instance whose waves stay narrow (known from the last solve of this model) gets one CTA per SM: with a
-            // third of the CTAs the grid barrier is cheaper and a node's CTA has the SM to itself (b6_nosym -7 %,
-            // b5_f6 -8 %); anything wider needs all resident warps (digitinvader7 with 148 CTAs: +22 %).
-            const int grid = model->hint_max_wave > 0 && model->hint_max_wave <= kNarrowInstanceWave ? std::min(search_grid, sm_count)
-                                                                                                     : search_grid;
+            const int grid = narrow ? std::min(search_grid, sm_count) : search_grid;
             CK(cudaEventRecord(evk0, stream));
-            CK(launch_search(dm, sa, grid, stream));
+            CK(launch_search(dm, sa, grid, sm_count, stream));
             CK(cudaEventRecord(evk1, stream));
             CK(cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof *h_ctl, cudaMemcpyDeviceToHost, stream));
             read_counters();
@@ -776,7 +902,7 @@ struct stcsp_session {
                                 "out %llu leaves %llu overflow %d\n",
                         rank, (now_s() - t_create) * 1e3, h_ctl->status, h_ctl->t_waves, h_ctl->n_in, h_counters[C_STATES],
                         h_counters[C_EDGES], h_counters[C_OUT], h_counters[C_LEAVES], h_ctl->overflow);
-            if (h_ctl->overflow & ~1) throw Failure(STCSP_ERR_CAPACITY, "internal: a pool overflowed inside the search kernel");
+            if (h_ctl->overflow & ~1) { poisoned = true; throw Failure(STCSP_ERR_CAPACITY, "internal: a pool overflowed inside the search kernel"); }
             n_in = h_ctl->n_in;
             cur = h_ctl->cur;
             n_states = (long long)h_counters[C_STATES];
@@ -788,6 +914,7 @@ struct stcsp_session {
                     prefinished_dead = h_ctl->dead_edges;
                     break;
                 case SEARCH_YIELD:
+                    if (narrow && n_in > kNarrowInstanceWave) wide_grid = true;     // from here on: the full grid
                     // Waves this wide run faster as separate launches: the stand-alone expand kernels keep their inner
                     // loops in registers (inside search_kernel ptxas spills there) and route/ingest run at full occupancy;
                     // at this width the launches and the two host round trips per wave no longer matter.
@@ -885,6 +1012,7 @@ struct stcsp_session {
     }
 
     void expand(int64_t *out_leaves, int64_t *out_pending) {
+        if (poisoned) throw Failure(STCSP_ERR_CAPACITY, "session unusable: a pool overflowed in an earlier wave");
         begin_timing();
         pending.clear();
         n_leaves = n_unres = 0;
@@ -911,6 +1039,7 @@ struct stcsp_session {
                 ea.out_cap = (long long)(out.cap / NW);
                 ea.leaves = leaves.p;
                 ea.leaf_cap = (long long)(leaves.cap / RW);
+                ea.fan = branch_fan(dm, n_in, ea.out_cap);
                 ea.counters = counters.p;
                 // narrow wave: a whole CTA per node (intra-node parallelism); wide wave: a warp per node
                 const int mode = pick_expand_mode(dm, n_in, expand_grid_max);
@@ -955,7 +1084,7 @@ struct stcsp_session {
                     zero_wave_counters();
                     continue;
                 }
-                if (ov) throw Failure(STCSP_ERR_CAPACITY, "internal: leaf buffers overflowed");
+                if (ov) { poisoned = true; throw Failure(STCSP_ERR_CAPACITY, "internal: leaf buffers overflowed"); }
                 break;
             }
             n_out = (long long)(h_counters[C_OUT] + h_counters[C_NEW]);
@@ -1098,6 +1227,7 @@ struct stcsp_session {
     }
 
     void ingest(const int32_t *inbox, int64_t n, int64_t *frontier_next) {
+        if (poisoned) throw Failure(STCSP_ERR_CAPACITY, "session unusable: a pool overflowed in an earlier wave");
         if (n_unres > 0) throw Failure(STCSP_ERR_INVALID, "ingest called with unresolved leaves pending");
         const int NW = dm.node_words, KW = dm.key_words, V = dm.V;
         if (!inbox) n = world == 1 ? n_leaves : 0;       // single rank: this rank's own leaves, in place
@@ -1133,7 +1263,7 @@ struct stcsp_session {
             CK(cudaGetLastError());
             read_counters();
             t_launches++;
-            if (h_counters[C_OVERFLOW]) throw Failure(STCSP_ERR_CAPACITY, "internal: automaton pools overflowed during ingest");
+            if (h_counters[C_OVERFLOW]) { poisoned = true; throw Failure(STCSP_ERR_CAPACITY, "internal: automaton pools overflowed during ingest"); }
             n_out = (long long)(h_counters[C_OUT] + h_counters[C_NEW]);
             n_states = (long long)h_counters[C_STATES];
             n_edges = (long long)h_counters[C_EDGES];
@@ -1226,14 +1356,19 @@ struct stcsp_session {
     // gigabytes costs seconds, an unstaged pageable copy runs at ~2.5 GB/s).  Returns with the stream drained if staged.
     void download(const HostBlock &dst, const void *src, size_t bytes) {
         if (bytes == 0) return;
-        if (dst.pinned || bytes <= ((size_t)4 << 20)) {
+        if (dst.pinned()) {
             CK(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyDeviceToHost, stream));
             return;
         }
-        const size_t CH = (size_t)32 << 20;
+        const size_t CH = bytes > ((size_t)256 << 20) ? (size_t)32 << 20 : (size_t)4 << 20;
         HostBlock stage[2];
         stage[0].alloc(CH);
         stage[1].alloc(CH);
+        if (!stage[0].pinned() || !stage[1].pinned()) {        // nothing can be pinned: let the driver stage it
+            CK(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            return;
+        }
         cudaEvent_t done[2] = {evk0, evk1};
         size_t off[2] = {0, 0}, len[2] = {0, 0};
         size_t pos = 0;
@@ -1241,7 +1376,7 @@ struct stcsp_session {
             const int slot = i & 1;
             if (len[slot]) {                            // the chunk issued two steps ago has landed: move it out
                 CK(cudaEventSynchronize(done[slot]));
-                memcpy((char *)dst.p + off[slot], stage[slot].p, len[slot]);
+                parallel_copy((char *)dst.p + off[slot], stage[slot].p, len[slot]);
                 len[slot] = 0;
             }
             if (pos < bytes) {
@@ -1509,14 +1644,7 @@ void stcsp_gpu_release_caches(void) {
         return;
     }
     for (int d = 0; d < ndev; d++) device_cache().trim(d);
-    {
-        HostCache &hc = host_cache();
-        std::lock_guard<std::mutex> g(hc.mu);
-        for (auto &kv : hc.free_blocks) {
-            for (void *p : kv.second) cudaFreeHost(p);
-            kv.second.clear();
-        }
-    }
+    host_cache().release_all();
 }
 
 int stcsp_gpu_device_count(void) {

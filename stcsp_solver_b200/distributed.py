@@ -113,9 +113,10 @@ def solve_distributed(model: binding.Model, options: Optional[binding.Options] =
     ex = WaveExchange(group)
     opts = options if options is not None else binding.default_options()
     opts.use_current_device = 1
-    if adaptive and ex.world > 1:
+    if adaptive and trim and ex.world > 1:
         # Small instances stay on one GPU: rank 0 runs the persistent single-GPU search with a bound on the wave width;
         # only if a wave outgrows it do all ranks start the sharded search (the bounded attempt costs a few waves).
+        # Whatever happens on rank 0, the verdict is broadcast: the other ranks must never be left waiting.
         verdict = torch.zeros(1, dtype=torch.int64, device=ex.device)
         automaton = None
         failure = None
@@ -124,13 +125,14 @@ def solve_distributed(model: binding.Model, options: Optional[binding.Options] =
             opts.max_frontier_nodes = SINGLE_GPU_FRONTIER
             try:
                 automaton = binding.solve(model, opts)
-                if not trim:
-                    raise ValueError("adaptive single-GPU path always trims")
                 verdict[0] = 1
             except binding.StcspError as e:
                 if e.status != binding.ERR_CAPACITY:
                     failure = e
-                    verdict[0] = -1                     # tell the waiting ranks before raising
+                    verdict[0] = -1
+            except BaseException as e:                  # noqa: BLE001 -- re-raised below, after the broadcast
+                failure = e
+                verdict[0] = -1
             finally:
                 opts.max_frontier_nodes = saved
         dist.broadcast(verdict, src=0, group=ex.group)

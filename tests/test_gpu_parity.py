@@ -218,3 +218,39 @@ def test_no_device_option_errors_loudly():
     with pytest.raises(binding.StcspError) as e:
         binding.solve(model, binding.default_options(device=99))
     assert e.value.status == binding.ERR_CUDA
+
+
+CLI_CASES = [("juggling_b4_f4", ""), ("juggling_b5_f6_nosym", ""), ("digitinvader3", "-a"), ("digitinvader3", "-z"),
+             ("probe_adversarial_win", "-z"), ("probe_adversarial", "-a"), ("probe_k1", "-k1"), ("probe_until_two", ""),
+             ("partialorder_12", "")]
+
+
+@pytest.mark.parametrize("name,flag", CLI_CASES)
+def test_cli_on_gpu_writes_the_reference_output(name, flag, tmp_path):
+    """bin/stcsp (the C++ host: front end, flags, C-ABI solve, post-processing, DOT writer) as a user runs it:
+    `stcsp -s [flag] file.csp` -> the reference's stat line on stdout, solutions.dot in the working directory; the DOT
+    re-parsed by the independent Python canonicaliser gives the reference's golden hash."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    from stcsp_solver_b200 import canonical
+    key = name + ("_" + flag.strip("-") if flag else "")
+    g = GOLDENS[key]
+    p = tmp_path / (name + ".csp")
+    p.write_text(golden_text(g))
+    argv = [os.path.join(ROOT, "bin", "stcsp"), "-s"] + ([flag] if flag else []) + ["--sha256", str(p)]
+    r = subprocess.run(argv, cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    stat = r.stdout.strip().split("\n")[-1].split("\t")
+    assert len(stat) == 8                                                   # src/solveralgorithm.cpp:1000-1001
+    assert (int(stat[1]), int(stat[2])) == (g["stat"]["vars"], g["stat"]["cons"])
+    if flag == "-a":
+        assert r.stdout.startswith(g["stdout"].split(";")[0] + "; ")
+    if flag == "-z":
+        assert r.stdout.startswith(g["stdout"].split("\n")[0] + "\n")
+    dot = (tmp_path / "solutions.dot").read_text()
+    a = canonical.parse_dot(dot)
+    assert canonical.canonical_sha256(a) == g["sha256"]
+    assert canonical.counts(a) == (g["states"], g["edges"])
+    assert ("canonical sha256 " + g["sha256"]) in r.stderr                  # the library's streamed hash agrees
+    assert dot.split("\n")[1] == g["header_vars"] and dot.split("\n")[2].rstrip() == g["header_sig"].rstrip()
