@@ -12,7 +12,8 @@ B := build
 
 HOST_SRC := $(wildcard stcsp_solver_b200/csrc/host/*.cpp)
 GPU_CPP := stcsp_solver_b200/csrc/gpu/compile.cpp
-GPU_CU := stcsp_solver_b200/csrc/gpu/kernels.cu stcsp_solver_b200/csrc/gpu/solver.cu stcsp_solver_b200/csrc/gpu/automaton.cu
+GPU_CU := stcsp_solver_b200/csrc/gpu/kernels.cu stcsp_solver_b200/csrc/gpu/solver.cu stcsp_solver_b200/csrc/gpu/automaton.cu \
+          stcsp_solver_b200/csrc/gpu/exchange.cu
 OBJ := $(patsubst %.cpp,$(B)/%.o,$(notdir $(HOST_SRC) $(GPU_CPP))) $(patsubst %.cu,$(B)/%.o,$(notdir $(GPU_CU)))
 HDR := $(wildcard include/*.h stcsp_solver_b200/csrc/host/*.h stcsp_solver_b200/csrc/gpu/*.h stcsp_solver_b200/csrc/gpu/*.cuh)
 LIB := stcsp_solver_b200/libstcsp_b200.so

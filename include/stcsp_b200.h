@@ -110,7 +110,9 @@ typedef struct stcsp_options {
     int32_t single_branch;           /* 1: a search node branches on ONE variable (the first unbound one), like the reference's
                                         solverGetFirstUnboundVar; 0 (default): narrow waves branch on up to three variables at
                                         once, which shortens the search tree.  Never changes the automaton. */
-    int32_t reserved[2];
+    int32_t shard_mode;              /* group solves: 0 adaptive (instances whose waves fit one GPU stay on one GPU), 1 always shard
+                                        the search over the GPUs of the group */
+    int32_t reserved[1];
 } stcsp_options_t;
 
 /* ---------------------------------------------------------------------------------------------
@@ -253,6 +255,49 @@ int stcsp_session_export(stcsp_session_t *s, int32_t *keys, int32_t *src, int32_
 int stcsp_session_finish_merged(stcsp_session_t *s, int32_t world_size, const int64_t *n_states, const int64_t *n_edges,
                                 const int32_t *keys, int32_t *src, int32_t *dst, int32_t *label, const int64_t *extra_stats,
                                 int32_t trim, stcsp_automaton_t *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Groups: several GPUs of one NVLink domain on ONE automaton.
+ *
+ * States are owned by hash(state key) mod world_size.  Every rank expands the search nodes of its own
+ * states, groups the leaf records it found by owner in an OUTBOX in its own HBM, and meets the other
+ * ranks once per wave ON THE DEVICES: an all-gather of one small header row per rank plus a barrier,
+ * written straight into the peers' memory (peer access inside one process, CUDA IPC across processes).
+ * The owners' ingest kernels then read their records directly out of the producers' outboxes over
+ * NVLink -- the exchange and the merge are one kernel, nothing is staged, NCCL is not involved.  At the
+ * end rank 0 pulls the parts and groups / trims / downloads like a single GPU does.
+ *
+ * A group is a communicator: form it once (create on every rank, exchange the share blobs by any means
+ * -- torch.distributed, MPI, a file --, attach), then solve as often as needed.  One group per rank
+ * and process for the multi-process layout (torchrun: one process per GPU); stcsp_gpu_solve_multi runs
+ * one host thread per GPU inside a single process (the command-line tool's --gpus N).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct stcsp_group stcsp_group_t;
+
+typedef struct stcsp_exchange_stats {
+    int32_t sharded;                 /* 0: every wave fitted one GPU, rank 0 solved it alone (no exchange) */
+    int32_t pad;
+    int64_t waves, exchanges;        /* device-side exchanges (one per wave, two when constraint sets had to be resolved) */
+    int64_t records;                 /* leaf records this rank ingested */
+    int64_t bytes_pulled;            /* bytes this rank read out of its peers' memory over NVLink */
+    double exchange_ms;              /* host wall time spent in the exchanges (launch, wait for the slowest rank, read-back) */
+} stcsp_exchange_stats_t;
+
+/* device < 0: the current device */
+int stcsp_group_create(int32_t rank, int32_t world_size, int32_t device, stcsp_group_t **out);
+void stcsp_group_destroy(stcsp_group_t *g);
+int64_t stcsp_group_share_bytes(void);
+/* blob [share_bytes]: what this rank's peers need to map its exchange block */
+int stcsp_group_share(stcsp_group_t *g, void *blob);
+/* blobs [world_size * share_bytes]: every rank's blob, in rank order */
+int stcsp_group_attach(stcsp_group_t *g, const void *blobs);
+/* Collective: every rank of the group calls it with the same problem and options.  Rank 0 receives the automaton
+ * (as from stcsp_gpu_solve); on the other ranks *out stays empty. */
+int stcsp_group_solve(stcsp_group_t *g, const stcsp_problem_t *problem, const stcsp_options_t *options, stcsp_automaton_t *out,
+                      stcsp_exchange_stats_t *stats);
+/* The same from one process: n_gpus host threads, one per device (devices == NULL: 0 .. n_gpus - 1). */
+int stcsp_gpu_solve_multi(const stcsp_problem_t *problem, const stcsp_options_t *options, int32_t n_gpus, const int32_t *devices,
+                          stcsp_automaton_t *out, stcsp_exchange_stats_t *stats);
 
 /* Merge the per-rank parts (parts[r] = part of rank r; arrays may live in caller memory) into one
  * automaton with dense state ids (ascending global id, root = 0) and edges grouped by source;

@@ -42,8 +42,17 @@ class Options(C.Structure):
         ("max_frontier_nodes", C.c_int64), ("max_states", C.c_int64), ("max_edges", C.c_int64),
         ("expand_mode", C.c_int32), ("profile_kernels", C.c_int32), ("no_trim", C.c_int32),
         ("lookahead", C.c_int32), ("wide_wave_nodes", C.c_int32), ("single_branch", C.c_int32),
-                ("reserved", C.c_int32 * 2),
+                ("shard_mode", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
+
+
+class ExchangeStats(C.Structure):
+    """stcsp_exchange_stats_t"""
+    _fields_ = [("sharded", C.c_int32), ("pad", C.c_int32), ("waves", C.c_int64), ("exchanges", C.c_int64),
+                ("records", C.c_int64), ("bytes_pulled", C.c_int64), ("exchange_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad"}
 
 
 class AutomatonC(C.Structure):
@@ -138,6 +147,15 @@ def lib() -> C.CDLL:
                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32,
                                                   C.POINTER(AutomatonC)]
         L.stcsp_automaton_assemble.argtypes = [C.POINTER(AutomatonC), C.c_int32, C.POINTER(AutomatonC)]
+        L.stcsp_group_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.stcsp_group_destroy.argtypes = [C.c_void_p]
+        L.stcsp_group_share_bytes.restype = C.c_int64
+        L.stcsp_group_share.argtypes = [C.c_void_p, C.c_void_p]
+        L.stcsp_group_attach.argtypes = [C.c_void_p, C.c_void_p]
+        L.stcsp_group_solve.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Options), C.POINTER(AutomatonC),
+                                        C.POINTER(ExchangeStats)]
+        L.stcsp_gpu_solve_multi.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.c_int32, C.POINTER(C.c_int32),
+                                            C.POINTER(AutomatonC), C.POINTER(ExchangeStats)]
         _lib = L
     return _lib
 
@@ -421,3 +439,57 @@ def assemble(parts: Sequence[dict], trim: bool = True) -> Automaton:
     if trim:
         _check(lib().stcsp_automaton_trim(C.byref(out)))
     return Automaton(out, lib().stcsp_automaton_free)
+
+
+class Group:
+    """Several GPUs on one automaton (stcsp_group_*): one Group per rank.  Form it once, solve many times.
+
+    share() -> bytes for the peers; attach(list of every rank's bytes, rank order); solve(model) is collective and
+    returns (Automaton or None, exchange statistics) -- the automaton on rank 0 only."""
+
+    def __init__(self, rank: int, world_size: int, device: int = -1):
+        self.rank, self.world = rank, world_size
+        self._h = C.c_void_p()
+        _check(lib().stcsp_group_create(rank, world_size, device, C.byref(self._h)))
+
+    def share(self) -> bytes:
+        buf = C.create_string_buffer(lib().stcsp_group_share_bytes())
+        _check(lib().stcsp_group_share(self._h, buf))
+        return buf.raw
+
+    def attach(self, blobs: Sequence[bytes]) -> None:
+        joined = b"".join(blobs)
+        _check(lib().stcsp_group_attach(self._h, C.create_string_buffer(joined, len(joined))))
+
+    def solve(self, model: Model, options: Optional[Options] = None):
+        out, xs = AutomatonC(), ExchangeStats()
+        opts = options if options is not None else default_options()
+        _check(lib().stcsp_group_solve(self._h, model.problem, C.byref(opts), C.byref(out), C.byref(xs)))
+        stats = xs.as_dict()
+        if self.rank != 0:
+            return None, stats
+        a = Automaton(out, lib().stcsp_automaton_free)
+        a.exchange_stats = stats
+        return a, stats
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().stcsp_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def solve_multi(model: Model, n_gpus: int, options: Optional[Options] = None, devices: Optional[Sequence[int]] = None):
+    """One process, one host thread per GPU (stcsp_gpu_solve_multi).  Returns (Automaton, exchange statistics)."""
+    out, xs = AutomatonC(), ExchangeStats()
+    opts = options if options is not None else default_options()
+    dev = (C.c_int32 * n_gpus)(*devices) if devices is not None else None
+    _check(lib().stcsp_gpu_solve_multi(model.problem, C.byref(opts), n_gpus, dev, C.byref(out), C.byref(xs)))
+    a = Automaton(out, lib().stcsp_automaton_free)
+    a.exchange_stats = xs.as_dict()
+    return a, a.exchange_stats

@@ -9,7 +9,9 @@
 // (:975-983), and with -s the automaton in `solutions.dot` of the working directory (:709-730).
 // The search itself runs on the GPU through the C ABI (include/stcsp_b200.h); there is no CPU solver.
 // Extensions: --canonical (print the canonical automaton text instead of writing DOT),
-// --stats (print the GPU path's own counters on stderr), --sha256 (SHA-256 of the canonical text on stderr).
+// --stats (print the GPU path's own counters on stderr), --sha256 (SHA-256 of the canonical text on stderr),
+// --gpus N (shard the search over N GPUs of this box, one host thread per GPU; instances whose waves fit one GPU stay on
+// one unless --shard is given).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -26,7 +28,7 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 
 struct Cli {
     bool print_solution = false, testing = false, adv1 = false, adv2 = false, canonical = false, stats = false, sha256 = false;
-    int prefix_k = 2, time_limit = 0, log_level = 0;
+    int prefix_k = 2, time_limit = 0, log_level = 0, gpus = 1, shard = 0;
     const char *file = nullptr;
 };
 
@@ -55,7 +57,11 @@ int run_once(const Cli &cli, bool print_stat, Run &r) {
     opt.verbosity = cli.log_level;
     stcsp_automaton_t automaton;
     t = now_s();
-    rc = stcsp_gpu_solve(problem, &opt, &automaton);
+    opt.shard_mode = cli.shard;
+    stcsp_exchange_stats_t xs;
+    memset(&xs, 0, sizeof xs);
+    rc = cli.gpus > 1 ? stcsp_gpu_solve_multi(problem, &opt, cli.gpus, nullptr, &automaton, &xs)     // one host thread per GPU
+                      : stcsp_gpu_solve(problem, &opt, &automaton);
     r.solve_s = now_s() - t;
     if (rc == STCSP_ERR_TIMEOUT) {          // reference: SIGALRM handler exits 0 silently (src/solver.cpp:190-193)
         fprintf(stderr, "stcsp: time limit reached\n");
@@ -105,6 +111,10 @@ int run_once(const Cli &cli, bool print_stat, Run &r) {
                 (long long)automaton.n_search_nodes, (long long)automaton.n_fails, (long long)automaton.n_leaves,
                 (long long)automaton.n_waves, (long long)automaton.n_tuples, (long long)automaton.n_kernel_launches,
                 automaton.solve_ms, automaton.wall_ms);
+    if (cli.stats && cli.gpus > 1)
+        fprintf(stderr, "gpus %d: sharded %d waves %lld exchanges %lld records %lld bytes_over_nvlink %lld exchange_ms %.3f\n", cli.gpus,
+                xs.sharded, (long long)xs.waves, (long long)xs.exchanges, (long long)xs.records, (long long)xs.bytes_pulled,
+                xs.exchange_ms);
     stcsp_solution_free(&sol);
     stcsp_automaton_free(&automaton);
     stcsp_model_free(model);
@@ -124,6 +134,15 @@ int main(int argc, char **argv) {
         if (!strcmp(a, "--canonical")) { cli.canonical = true; continue; }
         if (!strcmp(a, "--stats")) { cli.stats = true; continue; }
         if (!strcmp(a, "--sha256")) { cli.sha256 = true; continue; }
+        if (!strcmp(a, "--shard")) { cli.shard = 1; continue; }
+        if (!strncmp(a, "--gpus", 6)) {          // --gpus N or --gpus=N (the one new flag)
+            const char *val = a[6] == '=' ? a + 7 : (i + 1 < argc ? argv[++i] : "");
+            if (sscanf(val, "%d", &cli.gpus) != 1 || cli.gpus < 1 || cli.gpus > 16) {
+                fprintf(stderr, "Invalid argument: %s\n", val);
+                return 1;
+            }
+            continue;
+        }
         for (const char *p = a + 1; *p; p++) {
             const char c = *p;
             if (c == 's') cli.print_solution = true;
@@ -150,7 +169,7 @@ int main(int argc, char **argv) {
         }
     }
     if (!cli.file) {
-        fprintf(stderr, "usage: stcsp [-s] [-m<sec>] [-t] [-a] [-z] [-k<K>] [-l<level>] [--canonical] [--stats] [--sha256] file.csp\n");
+        fprintf(stderr, "usage: stcsp [-s] [-m<sec>] [-t] [-a] [-z] [-k<K>] [-l<level>] [--canonical] [--stats] [--sha256] [--gpus N] [--shard] file.csp\n");
         return 1;
     }
     Run r;

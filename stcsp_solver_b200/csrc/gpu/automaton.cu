@@ -285,6 +285,30 @@ void launch_place_keys(const int32_t *keys_in, int32_t *keys_out, long long tota
                                                                                         make_counts(world, n_states));
 }
 
+void preload_automaton_kernels(cudaStream_t stream) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, edge_count_kernel);
+    cudaFuncGetAttributes(&fa, edge_scatter_kernel);
+    cudaFuncGetAttributes(&fa, trim_init_kernel);
+    cudaFuncGetAttributes(&fa, trim_step_kernel);
+    cudaFuncGetAttributes(&fa, alive_to_int_kernel);
+    cudaFuncGetAttributes(&fa, edge_compact_kernel);
+    cudaFuncGetAttributes(&fa, finish_small_kernel);
+    cudaFuncGetAttributes(&fa, place_keys_kernel);
+    cudaFuncGetAttributes(&fa, remap_ids_kernel);
+    cudaFuncGetAttributes(&fa, state_rows_kernel);
+    // the library kernels behind cub::DeviceScan: run one tiny scan
+    int32_t *buf = nullptr;
+    const size_t tmp = scan_temp_bytes(64);
+    if (cudaMalloc(&buf, 2 * 64 * sizeof(int32_t) + tmp + 256) == cudaSuccess) {
+        cudaMemsetAsync(buf, 0, 2 * 64 * sizeof(int32_t), stream);
+        launch_exclusive_scan(buf + 128, tmp, buf, buf + 64, 64, stream);
+        cudaStreamSynchronize(stream);
+        cudaFree(buf);
+    }
+    cudaGetLastError();
+}
+
 void launch_state_rows(const int32_t *keys, long long n_states, int KW, int32_t *cset, int32_t *sig, int sm_count,
                        cudaStream_t stream) {
     if (n_states > 0)

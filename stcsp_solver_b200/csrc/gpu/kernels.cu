@@ -1439,12 +1439,31 @@ __device__ __forceinline__ void ingest_leaf(const DevModel &M, const IngestArgs 
     for (int v = lane; v < V; v += 32) P.edge_label[e * V + v] = rec[4 + v];
 }
 
-__device__ __forceinline__ void ingest_body(const DevModel &M, const IngestArgs &P) {
-    const int lane = threadIdx.x & 31;
+// PULL mode: where record `it` of the concatenated segments lives (peer memory of the rank that produced it)
+__device__ __forceinline__ const int32_t *pull_source(const IngestArgs &P, long long it, int RW) {
+    int q = 0;
+    while (q + 1 < P.n_segs && it >= P.seg_count[q]) { it -= P.seg_count[q]; q++; }
+    return P.seg_base[q] + it * RW;
+}
+
+// pull_smem (PULL mode): one record slot per warp, the record is copied out of the producer's outbox once
+__device__ __forceinline__ void ingest_body(const DevModel &M, const IngestArgs &P, int32_t *pull_smem) {
+    const int lane = threadIdx.x & 31, RW = M.rec_words;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     unsigned long long st_dom = 0;
-    for (long long it = warp_id; it < P.count; it += total_warps) ingest_leaf(M, P, P.records + it * M.rec_words, lane, st_dom);
+    for (long long it = warp_id; it < P.count; it += total_warps) {
+        const int32_t *rec = P.records + it * RW;
+        if (P.n_segs > 0) {
+            const int32_t *src = pull_source(P, it, RW);
+            int32_t *slot = pull_smem + (threadIdx.x >> 5) * 4 * RW;
+            __syncwarp();
+            for (int w = lane; w < RW; w += 32) slot[w] = __ldcv(src + w);     // peer memory: never from a stale cache line
+            __syncwarp();
+            rec = slot;
+        }
+        ingest_leaf(M, P, rec, lane, st_dom);
+    }
     if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
 }
 
@@ -1467,7 +1486,8 @@ __device__ __forceinline__ void leaf_body(const DevModel &M, const RouteArgs &R,
 // chain's latency is all there is.  Four independent chains per warp overlap it.  Same results as leaf_body.
 // ROUTE without INGEST is the producing rank's half (multi-GPU), INGEST without ROUTE the owner's half over its inbox.
 template <bool ROUTE, bool INGEST>
-__device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArgs &R, const IngestArgs &P, long long n_leaves) {
+__device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArgs &R, const IngestArgs &P, long long n_leaves,
+                                               int32_t *pull_smem = nullptr) {
     const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7, lead = g * 8;
     const unsigned gmask = 0xffu << lead;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1480,6 +1500,17 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
         long long li = have ? it : 0;
         if (ROUTE && R.list) li = R.list[li];
         int32_t *rec = ROUTE ? R.leaves + li * M.rec_words : const_cast<int32_t *>(P.records) + li * M.rec_words;
+        if (!ROUTE && P.n_segs > 0) {
+            // PULL mode: the eight lanes of the group copy their record out of the producer's outbox (peer memory, NVLink)
+            int32_t *slot = pull_smem + ((threadIdx.x >> 5) * 4 + g) * M.rec_words;
+            __syncwarp();
+            if (have) {
+                const int32_t *src = pull_source(P, li, M.rec_words);
+                for (int w = gl; w < M.rec_words; w += 8) slot[w] = __ldcv(src + w);
+            }
+            __syncwarp();
+            rec = slot;
+        }
         // ---- route (reference src/solveralgorithm.cpp:755-837)
         int ncid = -1, nexp = 0;
         bool routed = false;
@@ -1645,8 +1676,10 @@ __global__ void __launch_bounds__(256) route_kernel(const DevModel M, const Rout
 }
 
 __global__ void __launch_bounds__(256) ingest_kernel(const DevModel M, const IngestArgs P) {
-    if (wide_leaf_list(M, P.count)) leaf_body_quad<false, true>(M, RouteArgs{}, P, P.count);
-    else ingest_body(M, P);
+    extern __shared__ __align__(16) unsigned char smem[];      // PULL mode: 32 record slots (four per warp)
+    int32_t *pull_smem = reinterpret_cast<int32_t *>(smem);
+    if (wide_leaf_list(M, P.count)) leaf_body_quad<false, true>(M, RouteArgs{}, P, P.count, pull_smem);
+    else ingest_body(M, P, pull_smem);
 }
 
 // ---- the whole wave loop in one cooperative launch -------------------------------------------------------
@@ -1913,6 +1946,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             ia.out_cap = A.out_cap;
             ia.counters = ea.counters;
             ia.totals = A.counters;
+            ia.n_segs = 0;
             if (n_leaves >= 4ll * kExpandWarps * gridDim.x || M.force_mode == EXPAND_QUAD + 1)
                 leaf_body_quad<true, true>(M, ra, ia, n_leaves);    // four leaves per warp
             else leaf_body(M, ra, ia, n_leaves);            // route + ingest in one pass
@@ -2065,7 +2099,8 @@ void launch_route(const DevModel &m, const RouteArgs &a, int grid, cudaStream_t 
 
 void launch_ingest(const DevModel &m, const IngestArgs &a, int grid, cudaStream_t stream) {
     if (a.count <= 0) return;
-    ingest_kernel<<<grid, 256, 0, stream>>>(m, a);
+    const size_t smem = a.n_segs > 0 ? (size_t)32 * m.rec_words * sizeof(int32_t) : 0;     // <= 48 KiB: checked by the caller
+    ingest_kernel<<<grid, 256, smem, stream>>>(m, a);
 }
 
 void launch_scatter(const DevModel &m, const int32_t *leaves, long long n_leaves, const long long *dev_offsets,
@@ -2091,6 +2126,25 @@ void launch_build_tables(const DevModel &m, const int32_t *dev_jobs, int n_jobs,
     if (n_jobs <= 0) return;
     dim3 grid((unsigned)std::min((max_entries + 127) / 128, 256), (unsigned)n_jobs);
     build_table_kernel<<<grid, 128, 0, stream>>>(m, dev_jobs, tables);
+}
+
+// CUDA loads kernels lazily, and loading one may have to wait for running kernels to finish.  A rank whose exchange
+// kernel is waiting for a peer must never be the reason that peer cannot launch: a group loads every kernel up front.
+void preload_search_kernels() {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, expand_kernel<false>);
+    cudaFuncGetAttributes(&fa, expand_kernel<true>);
+    cudaFuncGetAttributes(&fa, expand_quad_kernel);
+    cudaFuncGetAttributes(&fa, search_kernel<1>);
+    cudaFuncGetAttributes(&fa, search_kernel<kExpandCtasPerSm>);
+    cudaFuncGetAttributes(&fa, route_kernel);
+    cudaFuncGetAttributes(&fa, ingest_kernel);
+    cudaFuncGetAttributes(&fa, scatter_kernel);
+    cudaFuncGetAttributes(&fa, gather_kernel);
+    cudaFuncGetAttributes(&fa, rehash_kernel);
+    cudaFuncGetAttributes(&fa, build_table_kernel);
+    cudaFuncGetAttributes(&fa, fill_kernel);
+    cudaGetLastError();
 }
 
 void launch_fill(int32_t *ptr, long long n, int32_t value, cudaStream_t stream) {

@@ -114,6 +114,12 @@ struct IngestArgs {
     long long out_cap;
     unsigned long long *counters;   // the wave's counter set
     unsigned long long *totals;     // C_STATES, C_EDGES: never reset (set 0 of the session's counter block)
+    // PULL mode (multi-GPU, n_segs > 0): `records` is null; record number i is the i-th record of the concatenation of the
+    // segments, and segment q lies in the OUTBOX OF RANK q -- peer memory, read over NVLink by the ingesting warps themselves
+    // (the exchange and the merge are one kernel; nothing is staged in an inbox).
+    int32_t n_segs;
+    const int32_t *seg_base[kMaxWorld];
+    long long seg_count[kMaxWorld];
 };
 
 // Control block of the persistent search kernel (device memory, mirrored to the host when the kernel returns).
@@ -240,5 +246,33 @@ void launch_state_rows(const int32_t *keys, long long n_states, int KW, int32_t 
                        cudaStream_t stream);
 
 uint32_t capmap_hash(int cid, const int32_t *vals, int n);
+
+// ---- exchange.cu: the per-wave meeting point of the ranks of a sharded solve, entirely on the devices ----------------
+// Every rank owns one exchange block in device memory that all its peers have mapped (peer access in one process, CUDA
+// IPC across processes).  At an exchange every rank writes its header row (and its arena directory) into EVERY peer's
+// block, fences, raises its flag there, and waits until every peer's flag in its own block has reached the epoch: an
+// all-gather of a few hundred bytes plus a barrier, with no host and no NCCL call in it.
+constexpr int kHdrWords = 64;               // long long words per header row
+constexpr int kMaxArenas = 48;              // device arenas a rank can publish
+struct ArenaDir {                           // where a rank's device memory lives, for peers in other processes
+    long long n;
+    long long size[kMaxArenas];
+    unsigned char handle[kMaxArenas][64];   // cudaIpcMemHandle_t of each arena's base
+};
+struct XBlock {
+    unsigned long long flag[kMaxWorld];             // flag[q]: the last epoch rank q has reached
+    long long hdr[2][kMaxWorld][kHdrWords];         // header rows, double-buffered by epoch parity; row q is written by rank q
+    ArenaDir dir[kMaxWorld];                        // dir[q] is written by rank q
+};
+struct XPeers {
+    XBlock *block[kMaxWorld];                       // block[q]: rank q's exchange block as mapped into this process
+};
+// Load every kernel of the library now (see kernels.cu: lazy loading must not meet a waiting exchange kernel).
+void preload_search_kernels();
+void preload_automaton_kernels(cudaStream_t stream);
+void preload_exchange_kernels();
+// status (device int): 0 ok, 1 timed out waiting for a peer
+void launch_exchange(const XPeers &peers, const long long *my_row, const ArenaDir *my_dir, int rank, int world,
+                     unsigned long long epoch, double timeout_s, int *status, cudaStream_t stream);
 
 }  // namespace stcsp

@@ -9,6 +9,7 @@
 // STCSP_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <sys/mman.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -34,6 +35,13 @@ struct Failure : std::runtime_error {
     Failure(int c, const std::string &m) : std::runtime_error(m), code(c) {}
 };
 
+struct PeerFailure : Failure {      // learnt from a peer's header row: no need to tell the others
+    PeerFailure(int c, const std::string &m) : Failure(c, m) {}
+};
+struct ModelMismatch : Failure {    // the ranks of a group started from different resident copies of the model (seen by all of them)
+    ModelMismatch() : Failure(STCSP_ERR_INVALID, "the ranks of the group hold different resident copies of this model") {}
+};
+
 #define CK(expr)                                                                                     \
     do {                                                                                             \
         cudaError_t e_ = (expr);                                                                     \
@@ -42,6 +50,20 @@ struct Failure : std::runtime_error {
     } while (0)
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// STCSP_TRACE_GROUP=1: a timestamped line on stderr at every step of a sharded solve (who waits where)
+bool group_trace_on() {
+    static const bool on = getenv("STCSP_TRACE_GROUP") != nullptr;
+    return on;
+}
+#define GTRACE(...)                                                     \
+    do {                                                                \
+        if (group_trace_on()) {                                         \
+            fprintf(stderr, "[group %.6f] ", now_s());                  \
+            fprintf(stderr, __VA_ARGS__);                               \
+            fprintf(stderr, "\n");                                      \
+        }                                                               \
+    } while (0)
 
 // Process-wide cache of device blocks (power-of-two size classes, per device), carved out of a few large ARENAS.
 // cudaMalloc / cudaFree cost 0.3-0.6 ms each on B200 and the stream-ordered pool showed 5-350 ms stalls when it had to
@@ -55,9 +77,48 @@ struct DeviceCache {
         int device;
         char *base;
         size_t size, used;
+        bool has_handle = false;
+        cudaIpcMemHandle_t handle{};
+        Arena(int d, char *b, size_t s, size_t u) : device(d), base(b), size(s), used(u) {}
     };
     std::vector<Arena> arenas;
     std::map<int, long long> outstanding;           // blocks handed out per device
+    // Which arena of `device` (counting that device's arenas in creation order) holds p, and where in it.
+    bool locate(int device, const void *p, long long &index, long long &offset) {
+        std::lock_guard<std::mutex> g(mu);
+        long long i = 0;
+        for (const Arena &a : arenas) {
+            if (a.device != device) continue;
+            if ((const char *)p >= a.base && (const char *)p < a.base + a.size) {
+                index = i;
+                offset = (const char *)p - a.base;
+                return true;
+            }
+            i++;
+        }
+        return false;
+    }
+    // The arenas of `device` with their CUDA IPC handles (for peers in other processes).
+    void directory(int device, ArenaDir &d) {
+        std::lock_guard<std::mutex> g(mu);
+        d.n = 0;
+        for (Arena &a : arenas) {
+            if (a.device != device) continue;
+            if (d.n >= kMaxArenas) throw Failure(STCSP_ERR_CAPACITY, "more device arenas than a rank can publish to its peers");
+            if (!a.has_handle) {
+                cudaError_t e = cudaIpcGetMemHandle(&a.handle, a.base);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    memset(&a.handle, 0, sizeof a.handle);      // peers in this process never need it
+                }
+                a.has_handle = true;
+            }
+            d.size[d.n] = (long long)a.size;
+            static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+            memcpy(d.handle[d.n], &a.handle, 64);
+            d.n++;
+        }
+    }
     static constexpr size_t kFirstArena = (size_t)256 << 20;
     static size_t size_class(size_t bytes) {
         size_t c = 4096;
@@ -86,7 +147,9 @@ struct DeviceCache {
         // a new arena: at least twice the largest so far (the pools of one solve double as they grow)
         size_t want = std::max(bytes, biggest ? biggest * 2 : kFirstArena);
         void *p = nullptr;
+        GTRACE("device %d: cudaMalloc of a %zu MiB arena ...", device, want >> 20);
         cudaError_t e = cudaMalloc(&p, want);
+        GTRACE("device %d: ... arena allocated", device);
         if (e != cudaSuccess && want > bytes) {     // not that much room left: just what is needed
             cudaGetLastError();
             want = bytes;
@@ -98,7 +161,7 @@ struct DeviceCache {
             throw Failure(STCSP_ERR_CAPACITY, "device allocation of " + std::to_string(bytes) + " bytes failed: " +
                                                   cudaGetErrorString(e));
         }
-        arenas.push_back(Arena{device, (char *)p, want, bytes});
+        arenas.push_back(Arena(device, (char *)p, want, bytes));
         return p;
     }
     void give_back(int device, size_t bytes, void *p) {
@@ -196,6 +259,7 @@ struct ModelState {
 };
 
 struct ModelCache {
+    static constexpr size_t kCapacity = 24;
     std::mutex mu;
     std::map<std::string, std::unique_ptr<ModelState>> entries;
     std::vector<std::string> order;
@@ -213,9 +277,23 @@ struct ModelCache {
         if (entries.count(key)) return;
         entries[key] = std::move(e);
         order.push_back(key);
-        while (order.size() > 8) {          // oldest out (its blocks go back to the device cache)
-            entries.erase(order.front());
-            order.erase(order.begin());
+        while (order.size() > kCapacity) {  // oldest out (its blocks go back to the device cache) ...
+            // ... together with the copies the other ranks of its group keep in this process (stcsp_gpu_solve_multi): the
+            // ranks of a group must all have a resident copy of a model, or none
+            const std::string victim = order.front();
+            const size_t cut = victim.find("|group");
+            const std::string base = cut == std::string::npos ? victim : victim.substr(0, cut);
+            for (size_t i = 0; i < order.size();) {
+                const bool same = order[i] == victim ||
+                                  (cut != std::string::npos && order[i].compare(0, base.size(), base) == 0 &&
+                                   order[i].find("|group", base.size()) == base.size());
+                if (same) {
+                    entries.erase(order[i]);
+                    order.erase(order.begin() + (long)i);
+                } else {
+                    i++;
+                }
+            }
         }
     }
 };
@@ -475,7 +553,7 @@ struct stcsp_session {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     DevModel dm{};
     DBuf<int32_t> d_jobs;
-    std::string cache_key;
+    std::string cache_key, group_tag;
     DBuf<SearchCtl> d_ctl;
     // finishing scratch (also handed to the search kernel, which finishes small automata itself)
     DBuf<int32_t> fb_deg, fb_first, fb_fill, fb_outdeg, fb_src, fb_dst, fb_label, fb_cset, fb_sig, fb_flags;
@@ -697,8 +775,11 @@ struct stcsp_session {
             coop_launch = c.coop;
         }
         try {
-            if (w == 1) {           // multi-rank solves number constraint sets in lock-step: always from a fresh state
-                cache_key = model_key(*problem, device);
+            // Multi-rank solves number constraint sets in lock-step, so they start from a fresh state -- or from the state
+            // the SAME group of ranks left behind for this model (group_tag): every rank of a group has solved the same
+            // models in the same order, so their resident copies agree.
+            if (w == 1 || !group_tag.empty()) {
+                cache_key = model_key(*problem, device) + group_tag;
                 model = model_cache().take(cache_key);
             }
             if (!model) {
@@ -1226,12 +1307,24 @@ struct stcsp_session {
         t_launches++;
     }
 
-    void ingest(const int32_t *inbox, int64_t n, int64_t *frontier_next) {
+    struct PullSegs {               // the records of one wave where their producers left them (see IngestArgs)
+        int n = 0;
+        const int32_t *base[kMaxWorld];
+        long long count[kMaxWorld];
+    };
+    void ingest(const int32_t *inbox, int64_t n, int64_t *frontier_next, const PullSegs *segs = nullptr) {
         if (poisoned) throw Failure(STCSP_ERR_CAPACITY, "session unusable: a pool overflowed in an earlier wave");
         if (n_unres > 0) throw Failure(STCSP_ERR_INVALID, "ingest called with unresolved leaves pending");
         const int NW = dm.node_words, KW = dm.key_words, V = dm.V;
-        if (!inbox) n = world == 1 ? n_leaves : 0;       // single rank: this rank's own leaves, in place
-        const int32_t *records = inbox ? inbox : leaves.p;
+        if (segs) {
+            n = 0;
+            for (int q = 0; q < segs->n; q++) n += segs->count[q];
+            if ((size_t)32 * dm.rec_words * 4 > 48 * 1024)
+                throw Failure(STCSP_ERR_UNSUPPORTED, "models with more than 380 variables cannot be sharded (record staging)");
+        } else if (!inbox) {
+            n = world == 1 ? n_leaves : 0;               // single rank: this rank's own leaves, in place
+        }
+        const int32_t *records = segs ? nullptr : (inbox ? inbox : leaves.p);
         DBuf<int32_t> &out = frontier[cur ^ 1];
         const double tw0 = now_s();
         double tw1 = tw0, tw2 = tw0;
@@ -1259,6 +1352,10 @@ struct stcsp_session {
             ia.out_cap = (long long)(out.cap / NW);
             ia.counters = counters.p;
             ia.totals = counters.p;
+            if (segs) {
+                ia.n_segs = segs->n;
+                for (int q = 0; q < segs->n; q++) { ia.seg_base[q] = segs->base[q]; ia.seg_count[q] = segs->count[q]; }
+            }
             launch_ingest(dm, ia, (int)std::min<long long>((n + 7) / 8, sm_count * 8), stream);
             CK(cudaGetLastError());
             read_counters();
@@ -1603,6 +1700,417 @@ struct stcsp_session {
     }
 };
 
+namespace stcsp {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// A GROUP of ranks (one per GPU of one NVLink domain) that solve together: the persistent half of the multi-GPU path.
+// It owns this rank's exchange block, the mappings of the peers' blocks and arenas, and the epoch counter; it lives
+// across solves like a communicator does (mapping peer memory costs milliseconds, a solve of partialorder_18 fifty).
+//
+// Header row of an exchange (long long words):
+enum HdrWord : int {
+    H_N_IN = 0,          // search nodes this rank expanded in this wave
+    H_N_LEAVES,          // leaves it routed
+    H_N_PENDING,         // resolve requests it has (constraint-set transitions nobody has computed yet)
+    H_STATUS,            // != 0: this rank failed (stcsp_status); everybody gives up
+    H_OUTBOX_RAW, H_OUTBOX_ADDR,        // its outbox of this wave (records grouped by owner)
+    H_PENDING_RAW, H_PENDING_ADDR,      // its request list
+    H_COUNT0 = 8,        // + q: records for owner q
+    H_OFF0 = 24,         // + q: where they start in the outbox (in records)
+    H_N_STATES = 40, H_N_EDGES,
+    H_KEYS_RAW, H_KEYS_ADDR, H_ESRC_RAW, H_ESRC_ADDR, H_EDST_RAW, H_EDST_ADDR, H_ELAB_RAW, H_ELAB_ADDR,
+    H_STATS0 = 50,       // + 0..9: search statistics (same order as stcsp_session_counts)
+    H_MODEL_SETS = 60, H_MODEL_CAPS     // constraint sets / transitions this rank's resident copy of the model knows at wave 0
+};
+static_assert(H_STATS0 + 10 <= H_MODEL_SETS && H_MODEL_CAPS < kHdrWords && H_OFF0 + kMaxWorld <= H_N_STATES, "header row layout");
+
+struct ShareBlob {          // what a rank tells its peers once, when the group forms
+    long long magic, pid, boot;
+    int32_t rank, device;
+    XBlock *block_raw;
+    cudaIpcMemHandle_t block_handle;
+};
+
+}  // namespace
+}  // namespace stcsp
+
+struct stcsp_group {
+    int rank = 0, world = 1, device = 0;
+    bool attached = false;
+    XBlock *block = nullptr;
+    XPeers peers{};
+    bool same_process[kMaxWorld] = {false};
+    unsigned long long epoch = 0;
+    long long *d_row = nullptr;
+    ArenaDir *d_dir = nullptr;
+    int *d_status = nullptr;
+    long long *h_rows = nullptr;            // pinned: [world][kHdrWords] + a status word + my row
+    ArenaDir h_dir{};                       // what the peers know of my arenas
+    ArenaDir peer_dir[kMaxWorld];
+    std::vector<void *> peer_arena[kMaxWorld];       // arenas of rank q mapped into this process (IPC)
+    std::vector<std::string> wide_models;   // models known not to fit one GPU's wave limit: no single-GPU attempt
+    cudaStream_t stream = nullptr;
+    // statistics of the last sharded solve
+    long long x_waves = 0, x_exchanges = 0, x_records = 0, x_bytes = 0;
+    double x_exchange_ms = 0;
+
+    ~stcsp_group() {
+        if (device >= 0) cudaSetDevice(device);
+        for (int q = 0; q < world; q++) {
+            for (void *p : peer_arena[q])
+                if (p) cudaIpcCloseMemHandle(p);
+            if (attached && q != rank && !same_process[q] && peers.block[q]) cudaIpcCloseMemHandle(peers.block[q]);
+        }
+        if (stream) cudaStreamDestroy(stream);
+        if (h_rows) cudaFreeHost(h_rows);
+        if (d_status) cudaFree(d_status);
+        if (d_dir) cudaFree(d_dir);
+        if (d_row) cudaFree(d_row);
+        if (block) cudaFree(block);
+    }
+
+    static long long boot_id() {            // distinguishes hosts / containers that happen to share pids
+        long long h = 1469598103934665603ll;
+        FILE *f = fopen("/proc/sys/kernel/random/boot_id", "r");
+        if (f) {
+            int c;
+            while ((c = fgetc(f)) != EOF) h = (h ^ c) * 1099511628211ll;
+            fclose(f);
+        }
+        return h;
+    }
+
+    void create(int r, int w, int dev) {
+        if (w < 1 || w > kMaxWorld || r < 0 || r >= w) throw Failure(STCSP_ERR_INVALID, "bad rank / world size");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw Failure(STCSP_ERR_CUDA, "no usable CUDA device; this library has no CPU fallback");
+        if (dev < 0) CK(cudaGetDevice(&dev));
+        if (dev >= ndev) throw Failure(STCSP_ERR_CUDA, "CUDA device ordinal out of range");
+        rank = r; world = w; device = dev;
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaMalloc(&block, sizeof(XBlock)));
+        CK(cudaMemset(block, 0, sizeof(XBlock)));
+        CK(cudaMalloc(&d_row, kHdrWords * sizeof(long long)));
+        CK(cudaMalloc(&d_dir, sizeof(ArenaDir)));
+        CK(cudaMemset(d_dir, 0, sizeof(ArenaDir)));
+        CK(cudaMalloc(&d_status, sizeof(int)));
+        CK(cudaMemset(d_status, 0, sizeof(int)));
+        CK(cudaMallocHost(&h_rows, ((size_t)kMaxWorld + 2) * kHdrWords * sizeof(long long)));
+        preload_search_kernels();
+        preload_automaton_kernels(stream);
+        preload_exchange_kernels();
+        CK(cudaDeviceSynchronize());
+        for (int q = 0; q < kMaxWorld; q++) peers.block[q] = nullptr;
+        peers.block[rank] = block;
+        same_process[rank] = true;
+        memset(&h_dir, 0, sizeof h_dir);
+        memset(peer_dir, 0, sizeof peer_dir);
+    }
+
+    void share(ShareBlob *b) {
+        memset(b, 0, sizeof *b);
+        b->magic = 0x53544353504752ll;
+        b->pid = (long long)getpid();
+        b->boot = boot_id();
+        b->rank = rank;
+        b->device = device;
+        b->block_raw = block;
+        if (cudaIpcGetMemHandle(&b->block_handle, block) != cudaSuccess) cudaGetLastError();    // (single-process groups do not need it)
+    }
+
+    void attach(const ShareBlob *blobs) {
+        CK(cudaSetDevice(device));
+        ShareBlob mine;
+        share(&mine);
+        for (int q = 0; q < world; q++) {
+            const ShareBlob &b = blobs[q];
+            if (b.magic != mine.magic || b.rank != q) throw Failure(STCSP_ERR_INVALID, "group attach: blobs are not in rank order");
+            if (q == rank) continue;
+            same_process[q] = b.pid == mine.pid && b.boot == mine.boot;
+            if (same_process[q]) {
+                if (b.device != device) {
+                    int can = 0;
+                    CK(cudaDeviceCanAccessPeer(&can, device, b.device));
+                    if (!can) throw Failure(STCSP_ERR_CUDA, "GPUs of the group cannot access each other's memory (no NVLink / P2P)");
+                    cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+                    cudaGetLastError();
+                }
+                peers.block[q] = b.block_raw;
+            } else {
+                void *p = nullptr;
+                cudaError_t e = cudaIpcOpenMemHandle(&p, b.block_handle, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    throw Failure(STCSP_ERR_CUDA, std::string("cannot map the exchange block of rank ") + std::to_string(q) +
+                                                      " (CUDA IPC): " + cudaGetErrorString(e));
+                }
+                peers.block[q] = (XBlock *)p;
+            }
+        }
+        attached = true;
+    }
+
+    // A device pointer of rank q as this process can use it.
+    const void *peer_ptr(int q, long long raw, long long addr) {
+        if (same_process[q]) return (const void *)(uintptr_t)raw;
+        const long long idx = addr >> 40, off = addr & ((1ll << 40) - 1);
+        if (idx < 0 || idx >= kMaxArenas) throw Failure(STCSP_ERR_INVALID, "peer address names an unknown arena");
+        if ((long long)peer_arena[q].size() <= idx) peer_arena[q].resize((size_t)idx + 1, nullptr);
+        if (!peer_arena[q][idx]) {
+            // the directory rank q published with (or before) the row that carries this address
+            CK(cudaMemcpyAsync(&peer_dir[q], &block->dir[q], sizeof(ArenaDir), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            if (idx >= peer_dir[q].n) throw Failure(STCSP_ERR_INVALID, "peer address names an arena its rank has not published");
+            cudaIpcMemHandle_t h;
+            memcpy(&h, peer_dir[q].handle[idx], 64);
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                throw Failure(STCSP_ERR_CUDA, std::string("cannot map device memory of rank ") + std::to_string(q) + " (CUDA IPC): " +
+                                                  cudaGetErrorString(e));
+            }
+            peer_arena[q][idx] = p;
+        }
+        return (const char *)peer_arena[q][idx] + off;
+    }
+
+    // my pointer p as (raw, arena << 40 | offset) for a header row
+    void publish_ptr(const void *p, long long *row, int raw_word) {
+        row[raw_word] = (long long)(uintptr_t)p;
+        long long idx = 0, off = 0;
+        if (p && device_cache().locate(device, p, idx, off)) row[raw_word + 1] = (idx << 40) | off;
+        else row[raw_word + 1] = -1;
+    }
+
+    // All-gather of one header row per rank + barrier, on the devices.  rows: [world][kHdrWords] (pinned, valid until the
+    // next exchange).  Throws if a peer reports failure or does not show up.
+    const long long *exchange(const long long *row, cudaStream_t stream) {
+        // (on the calling session's stream: a rank then needs ONE hardware queue to make progress; with every rank of a
+        //  group on the same device -- the test layout -- more streams than CUDA_DEVICE_MAX_CONNECTIONS alias onto the same
+        //  queue, and a kernel queued behind a peer's waiting exchange kernel would never start)
+        const double t0 = now_s();
+        epoch++;
+        GTRACE("rank %d: exchange %llu begins (n_in %lld leaves %lld pending %lld status %lld)", rank, epoch, row[H_N_IN], row[H_N_LEAVES],
+               row[H_N_PENDING], row[H_STATUS]);
+        long long *stage = h_rows + (size_t)(kMaxWorld + 1) * kHdrWords;
+        memcpy(stage, row, kHdrWords * sizeof(long long));
+        CK(cudaMemcpyAsync(d_row, stage, kHdrWords * sizeof(long long), cudaMemcpyHostToDevice, stream));
+        ArenaDir now_dir;
+        memset(&now_dir, 0, sizeof now_dir);
+        device_cache().directory(device, now_dir);
+        if (now_dir.n != h_dir.n) {
+            h_dir = now_dir;
+            CK(cudaMemcpy(d_dir, &h_dir, sizeof(ArenaDir), cudaMemcpyHostToDevice));
+        }
+        launch_exchange(peers, d_row, d_dir, rank, world, epoch, 30.0, d_status, stream);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_rows, &block->hdr[epoch & 1ull][0][0], (size_t)world * kHdrWords * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        int *h_status = reinterpret_cast<int *>(h_rows + (size_t)kMaxWorld * kHdrWords);
+        CK(cudaMemcpyAsync(h_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        GTRACE("rank %d: exchange %llu done after %.3f ms", rank, epoch, (now_s() - t0) * 1e3);
+        x_exchanges++;
+        x_exchange_ms += (now_s() - t0) * 1e3;
+        if (*h_status != 0) throw Failure(STCSP_ERR_CUDA, "a rank of the group did not reach the exchange (timeout)");
+        for (int q = 0; q < world; q++)
+            if (h_rows[(size_t)q * kHdrWords + H_STATUS] != 0)
+                throw PeerFailure((int)h_rows[(size_t)q * kHdrWords + H_STATUS], "rank " + std::to_string(q) + " of the group failed");
+        return h_rows;
+    }
+};
+
+namespace stcsp {
+namespace {
+
+// The sharded wave loop of one rank.  out: the merged automaton (rank 0 only).
+void run_sharded(stcsp_session &s, stcsp_group &g, bool trim, stcsp_automaton_t *out) {
+    const int W = g.world, R = g.rank, V = s.dm.V, RW = s.dm.rec_words, KW = s.dm.key_words;
+    DBuf<int32_t> outbox[2], d_pending, m_keys, m_src, m_dst, m_label;
+    g.x_waves = g.x_exchanges = g.x_records = g.x_bytes = 0;
+    g.x_exchange_ms = 0;
+    long long row[kHdrWords];
+    const long long start_sets = s.model->sets.n_sets(), start_caps = s.model->capmap_used;
+    bool local_failure = true;          // an exception raised here (not learnt from a peer) is announced to the peers
+    try {
+        for (long long wave = 0;; wave++) {
+            if (s.n_states * (long long)W + R >= (1ll << 31) - (long long)W * 2)
+                throw Failure(STCSP_ERR_CAPACITY, "more states than 32-bit global state ids can name at this world size");
+            if (s.opt.time_limit_s > 0 && now_s() - s.t_create > s.opt.time_limit_s) throw Failure(STCSP_ERR_TIMEOUT, "time limit reached");
+            memset(row, 0, sizeof row);
+            row[H_N_IN] = s.n_in;
+            int64_t nl = 0, np = 0;
+            GTRACE("rank %d: wave %lld expand of %lld nodes", R, wave, s.n_in);
+            s.expand(&nl, &np);
+            GTRACE("rank %d: wave %lld expanded: %lld leaves, %lld requests", R, wave, (long long)nl, (long long)np);
+            auto publish_outbox = [&]() {
+                row[H_N_LEAVES] = s.n_leaves;
+                row[H_N_PENDING] = (long long)(s.pending.size() / (size_t)(1 + V));
+                for (int q = 0; q < W; q++) row[H_COUNT0 + q] = row[H_OFF0 + q] = 0;
+                if (row[H_N_PENDING] == 0 && s.n_leaves > 0) {
+                    DBuf<int32_t> &ob = outbox[wave & 1];
+                    ob.reserve((size_t)s.n_leaves * RW, 0, s.stream);
+                    int64_t counts[kMaxWorld] = {0};
+                    s.outbox(ob.p, (int64_t)(ob.cap / RW), counts);
+                    long long off = 0;
+                    for (int q = 0; q < W; q++) {
+                        row[H_COUNT0 + q] = counts[q];
+                        row[H_OFF0 + q] = off;
+                        off += counts[q];
+                    }
+                    g.publish_ptr(ob.p, row, H_OUTBOX_RAW);
+                }
+            };
+            if (np > 0) {
+                d_pending.reserve(s.pending.size(), 0, s.stream);
+                CK(cudaMemcpyAsync(d_pending.p, s.pending.data(), s.pending.size() * 4, cudaMemcpyHostToDevice, s.stream));
+                g.publish_ptr(d_pending.p, row, H_PENDING_RAW);
+            }
+            publish_outbox();
+            if (wave == 0) {
+                row[H_MODEL_SETS] = start_sets;
+                row[H_MODEL_CAPS] = start_caps;
+            }
+            CK(cudaStreamSynchronize(s.stream));            // the outbox is complete before anybody is told about it
+            const long long *rows = g.exchange(row, s.stream);
+            if (wave == 0)          // set ids travel in the records: every rank must have started from the same numbering
+                for (int q = 0; q < W; q++)
+                    if (rows[(size_t)q * kHdrWords + H_MODEL_SETS] != start_sets || rows[(size_t)q * kHdrWords + H_MODEL_CAPS] != start_caps)
+                        throw ModelMismatch();      // every rank sees the same rows: all of them start over without their copies
+            long long total_in = 0, total_pending = 0;
+            for (int q = 0; q < W; q++) {
+                total_in += rows[(size_t)q * kHdrWords + H_N_IN];
+                total_pending += rows[(size_t)q * kHdrWords + H_N_PENDING];
+            }
+            if (total_in == 0) break;                       // no rank had anything to expand: the search is over
+            if (total_pending > 0) {
+                // some rank met a constraint-set transition nobody has computed yet: every rank resolves the union of all
+                // requests in one sorted order (so that set ids agree), then the outboxes are published again
+                std::vector<std::vector<int32_t>> reqs;
+                for (int q = 0; q < W; q++) {
+                    const long long cnt = rows[(size_t)q * kHdrWords + H_N_PENDING];
+                    if (cnt == 0) continue;
+                    std::vector<int32_t> buf((size_t)cnt * (1 + V));
+                    const void *src = g.peer_ptr(q, rows[(size_t)q * kHdrWords + H_PENDING_RAW], rows[(size_t)q * kHdrWords + H_PENDING_ADDR]);
+                    CK(cudaMemcpyAsync(buf.data(), src, buf.size() * 4, cudaMemcpyDefault, s.stream));
+                    CK(cudaStreamSynchronize(s.stream));
+                    for (long long i = 0; i < cnt; i++) reqs.emplace_back(buf.begin() + i * (1 + V), buf.begin() + (i + 1) * (1 + V));
+                }
+                std::sort(reqs.begin(), reqs.end());
+                reqs.erase(std::unique(reqs.begin(), reqs.end()), reqs.end());
+                std::vector<int32_t> flat;
+                for (const auto &r : reqs) flat.insert(flat.end(), r.begin(), r.end());
+                s.resolve(flat.data(), (int64_t)reqs.size());
+                memset(row, 0, sizeof row);
+                row[H_N_IN] = 1;                            // (only the sum matters, and it was not zero)
+                publish_outbox();
+                CK(cudaStreamSynchronize(s.stream));
+                rows = g.exchange(row, s.stream);
+            }
+            stcsp_session::PullSegs segs;
+            segs.n = W;
+            long long incoming = 0;
+            for (int q = 0; q < W; q++) {
+                const long long *rq = rows + (size_t)q * kHdrWords;
+                segs.count[q] = rq[H_COUNT0 + R];
+                segs.base[q] = nullptr;
+                if (segs.count[q] > 0)
+                    segs.base[q] = (const int32_t *)g.peer_ptr(q, rq[H_OUTBOX_RAW], rq[H_OUTBOX_ADDR]) + rq[H_OFF0 + R] * RW;
+                incoming += segs.count[q];
+                if (q != R) g.x_bytes += segs.count[q] * RW * 4;
+            }
+            g.x_records += incoming;
+            int64_t next = 0;
+            GTRACE("rank %d: wave %lld ingest of %lld records", R, wave, incoming);
+            s.ingest(nullptr, 0, &next, &segs);
+            GTRACE("rank %d: wave %lld ingested, next frontier %lld", R, wave, (long long)next);
+            g.x_waves++;
+        }
+        // ---- merge: every rank publishes its part, rank 0 pulls them over NVLink and finishes on its GPU
+        memset(row, 0, sizeof row);
+        row[H_N_STATES] = s.n_states;
+        row[H_N_EDGES] = s.n_edges;
+        g.publish_ptr(s.state_key.p, row, H_KEYS_RAW);
+        g.publish_ptr(s.edge_src.p, row, H_ESRC_RAW);
+        g.publish_ptr(s.edge_dst.p, row, H_EDST_RAW);
+        g.publish_ptr(s.edge_label.p, row, H_ELAB_RAW);
+        {
+            const long long v[10] = {s.t_nodes, s.t_fails, s.t_leaves, s.t_dominance, s.t_tuples, s.t_revisions, s.t_launches,
+                                     s.t_expand_launches, s.h2d, s.d2h};
+            for (int i = 0; i < 10; i++) row[H_STATS0 + i] = v[i];
+        }
+        CK(cudaStreamSynchronize(s.stream));
+        const long long *rows = g.exchange(row, s.stream);
+        if (R == 0) {
+            int64_t ns[kMaxWorld], ne[kMaxWorld], extra[10] = {0};
+            long long tot_s = 0, tot_e = 0;
+            for (int q = 0; q < W; q++) {
+                ns[q] = rows[(size_t)q * kHdrWords + H_N_STATES];
+                ne[q] = rows[(size_t)q * kHdrWords + H_N_EDGES];
+                tot_s += ns[q];
+                tot_e += ne[q];
+                if (q > 0)
+                    for (int i = 0; i < 10; i++) extra[i] += rows[(size_t)q * kHdrWords + H_STATS0 + i];
+            }
+            if (tot_s >= (1ll << 31) || tot_e >= (1ll << 31)) throw Failure(STCSP_ERR_CAPACITY, "merged automaton exceeds 32-bit ids");
+            m_keys.reserve((size_t)std::max<long long>(tot_s, 1) * KW, 0, s.stream);
+            m_src.reserve((size_t)std::max<long long>(tot_e, 1), 0, s.stream);
+            m_dst.reserve((size_t)std::max<long long>(tot_e, 1), 0, s.stream);
+            m_label.reserve((size_t)std::max<long long>(tot_e, 1) * V, 0, s.stream);
+            long long so = 0, eo = 0;
+            // (copy the rows out first: the done-exchange below reuses the pinned table)
+            std::vector<long long> keep(rows, rows + (size_t)W * kHdrWords);
+            for (int q = 0; q < W; q++) {
+                const long long *rq = keep.data() + (size_t)q * kHdrWords;
+                if (ns[q])
+                    CK(cudaMemcpyAsync(m_keys.p + so * KW, g.peer_ptr(q, rq[H_KEYS_RAW], rq[H_KEYS_ADDR]), (size_t)ns[q] * KW * 4,
+                                       cudaMemcpyDefault, s.stream));
+                if (ne[q]) {
+                    CK(cudaMemcpyAsync(m_src.p + eo, g.peer_ptr(q, rq[H_ESRC_RAW], rq[H_ESRC_ADDR]), (size_t)ne[q] * 4, cudaMemcpyDefault, s.stream));
+                    CK(cudaMemcpyAsync(m_dst.p + eo, g.peer_ptr(q, rq[H_EDST_RAW], rq[H_EDST_ADDR]), (size_t)ne[q] * 4, cudaMemcpyDefault, s.stream));
+                    CK(cudaMemcpyAsync(m_label.p + eo * V, g.peer_ptr(q, rq[H_ELAB_RAW], rq[H_ELAB_ADDR]), (size_t)ne[q] * V * 4,
+                                       cudaMemcpyDefault, s.stream));
+                    if (q != 0) g.x_bytes += ne[q] * (2 + V) * 4 + ns[q] * KW * 4;
+                }
+                so += ns[q];
+                eo += ne[q];
+            }
+            CK(cudaStreamSynchronize(s.stream));            // the parts are here: the peers may release theirs
+            memset(row, 0, sizeof row);
+            g.exchange(row, s.stream);
+            s.search_complete = true;
+            s.finish_merged(W, ns, ne, m_keys.p, m_src.p, m_dst.p, m_label.p, extra, trim, out);
+        } else {
+            memset(row, 0, sizeof row);
+            g.exchange(row, s.stream);                      // rank 0 has copied this rank's part
+            s.search_complete = true;
+        }
+        CK(cudaStreamSynchronize(s.stream));
+    } catch (const PeerFailure &) {
+        throw;                                              // everybody already knows
+    } catch (const ModelMismatch &) {
+        throw;                                              // everybody has seen it in the same exchange
+    } catch (const Failure &f) {
+        if (local_failure && f.code != STCSP_ERR_CUDA) {
+            // tell the peers at the exchange they are (or will be) waiting at, so that nobody waits for the timeout
+            try {
+                memset(row, 0, sizeof row);
+                row[H_STATUS] = f.code;
+                g.exchange(row, s.stream);
+            } catch (...) {
+            }
+        }
+        throw;
+    }
+}
+
+}  // namespace
+}  // namespace stcsp
+
 namespace {
 
 int fail_with(const Failure &f) {
@@ -1849,6 +2357,160 @@ int stcsp_automaton_trim(stcsp_automaton_t *a) {
         }
         a->n_edges = w;
     });
+}
+
+// ---- groups: several GPUs on one automaton --------------------------------------------------------------------------
+int stcsp_group_create(int32_t rank, int32_t world_size, int32_t device, stcsp_group_t **out) {
+    if (!out) { set_error("null argument"); return STCSP_ERR_INVALID; }
+    *out = nullptr;
+    stcsp_group *g = nullptr;
+    int rc = guarded([&] {
+        g = new stcsp_group();
+        g->create(rank, world_size, device);
+    });
+    if (rc != STCSP_OK) {
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return STCSP_OK;
+}
+
+void stcsp_group_destroy(stcsp_group_t *g) { delete g; }
+
+int64_t stcsp_group_share_bytes(void) { return (int64_t)sizeof(ShareBlob); }
+
+int stcsp_group_share(stcsp_group_t *g, void *blob) {
+    if (!g || !blob) { set_error("null argument"); return STCSP_ERR_INVALID; }
+    return guarded([&] { g->share((ShareBlob *)blob); });
+}
+
+int stcsp_group_attach(stcsp_group_t *g, const void *blobs) {
+    if (!g || !blobs) { set_error("null argument"); return STCSP_ERR_INVALID; }
+    return guarded([&] { g->attach((const ShareBlob *)blobs); });
+}
+
+int stcsp_group_solve(stcsp_group_t *g, const stcsp_problem_t *problem, const stcsp_options_t *options, stcsp_automaton_t *out,
+                      stcsp_exchange_stats_t *xs) {
+    if (!g || !problem || !out) { set_error("null argument"); return STCSP_ERR_INVALID; }
+    memset(out, 0, sizeof *out);
+    if (xs) memset(xs, 0, sizeof *xs);
+    if (!g->attached && g->world > 1) { set_error("group solve before stcsp_group_attach"); return STCSP_ERR_INVALID; }
+    stcsp_options_t opt;
+    memset(&opt, 0, sizeof opt);
+    if (options) opt = *options;
+    opt.device = g->device;
+    opt.use_current_device = 0;
+    const double t0 = now_s();
+    const std::string key = model_key(*problem, g->device);
+    const bool known_wide = std::find(g->wide_models.begin(), g->wide_models.end(), key) != g->wide_models.end();
+    if (g->world == 1 || (opt.shard_mode == 0 && !known_wide)) {
+        // Instances whose waves fit one GPU are fastest on one GPU.  EVERY rank runs the same bounded single-GPU search on its
+        // own device -- the verdict is a deterministic function of the model, so the ranks agree without exchanging a byte --
+        // and rank 0 returns its result.  Only a wave wider than the bound makes the group shard the search.
+        stcsp_options_t o1 = opt;
+        const long long bound = 1ll << 20;
+        if (g->world > 1 && (o1.max_frontier_nodes <= 0 || o1.max_frontier_nodes > bound)) o1.max_frontier_nodes = bound;
+        stcsp_automaton_t tmp;
+        const int rc = stcsp_gpu_solve(problem, &o1, &tmp);
+        if (rc == STCSP_OK) {
+            if (g->rank == 0) *out = tmp;
+            else stcsp_automaton_free(&tmp);
+            return STCSP_OK;
+        }
+        if (rc != STCSP_ERR_CAPACITY || g->world == 1) return rc;
+        g->wide_models.push_back(key);
+    }
+    stcsp_session *s = nullptr;
+    int rc = STCSP_OK;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        bool mismatch = false;
+        rc = guarded([&] {
+            CK(cudaSetDevice(g->device));
+            s = new stcsp_session();
+            // (per rank: ranks that share a process -- stcsp_gpu_solve_multi -- must not swap their resident copies)
+            s->group_tag = "|group" + std::to_string(g->world) + "r" + std::to_string(g->rank);
+            GTRACE("rank %d: session init ...", g->rank);
+            s->init(problem, &opt, g->rank, g->world);
+            GTRACE("rank %d: ... session ready", g->rank);
+            try {
+                run_sharded(*s, *g, !opt.no_trim, out);
+            } catch (const ModelMismatch &) {
+                mismatch = true;            // the session dies without handing its copy back: the second attempt compiles afresh
+                throw;
+            }
+        });
+        delete s;
+        s = nullptr;
+        if (!mismatch) break;
+    }
+    if (xs) {
+        xs->sharded = 1;
+        xs->waves = g->x_waves;
+        xs->exchanges = g->x_exchanges;
+        xs->records = g->x_records;
+        xs->bytes_pulled = g->x_bytes;
+        xs->exchange_ms = g->x_exchange_ms;
+    }
+    if (rc == STCSP_OK && g->rank == 0) out->wall_ms = (now_s() - t0) * 1e3;
+    if (rc != STCSP_OK) stcsp_automaton_free(out);
+    return rc;
+}
+
+// One process, one host thread per GPU: the groups are formed once per device list and kept.
+int stcsp_gpu_solve_multi(const stcsp_problem_t *problem, const stcsp_options_t *options, int32_t n_gpus, const int32_t *devices,
+                          stcsp_automaton_t *out, stcsp_exchange_stats_t *xs) {
+    if (!problem || !out) { set_error("null argument"); return STCSP_ERR_INVALID; }
+    if (n_gpus < 1 || n_gpus > kMaxWorld) { set_error("bad GPU count"); return STCSP_ERR_INVALID; }
+    static std::mutex mu;
+    static std::map<std::vector<int>, std::vector<stcsp_group *>> teams;
+    std::lock_guard<std::mutex> lock(mu);                   // one multi-GPU solve at a time per process
+    std::vector<int> devs;
+    for (int i = 0; i < n_gpus; i++) devs.push_back(devices ? devices[i] : i);
+    std::vector<stcsp_group *> &team = teams[devs];
+    if (team.empty()) {
+        std::vector<ShareBlob> blobs((size_t)n_gpus);
+        int rc = STCSP_OK;
+        for (int r = 0; r < n_gpus && rc == STCSP_OK; r++) {
+            stcsp_group *g = nullptr;
+            rc = stcsp_group_create(r, n_gpus, devs[r], &g);
+            if (rc == STCSP_OK) {
+                team.push_back(g);
+                rc = stcsp_group_share(g, &blobs[r]);
+            }
+        }
+        for (int r = 0; r < n_gpus && rc == STCSP_OK; r++) rc = stcsp_group_attach(team[r], blobs.data());
+        if (rc != STCSP_OK) {
+            const std::string why = stcsp_last_error();
+            for (stcsp_group *g : team) delete g;
+            team.clear();
+            set_error(why);
+            return rc;
+        }
+    }
+    std::vector<int> rcs((size_t)n_gpus, STCSP_OK);
+    std::vector<std::string> errs((size_t)n_gpus);
+    std::vector<stcsp_automaton_t> outs((size_t)n_gpus);
+    std::vector<stcsp_exchange_stats_t> xss((size_t)n_gpus);
+    std::vector<std::thread> pool;
+    for (int r = 1; r < n_gpus; r++)
+        pool.emplace_back([&, r] {
+            rcs[r] = stcsp_group_solve(team[r], problem, options, &outs[r], &xss[r]);
+            if (rcs[r] != STCSP_OK) errs[r] = stcsp_last_error();
+        });
+    rcs[0] = stcsp_group_solve(team[0], problem, options, &outs[0], &xss[0]);
+    if (rcs[0] != STCSP_OK) errs[0] = stcsp_last_error();
+    for (std::thread &t : pool) t.join();
+    for (int r = 1; r < n_gpus; r++) stcsp_automaton_free(&outs[r]);
+    for (int r = 0; r < n_gpus; r++)
+        if (rcs[r] != STCSP_OK) {
+            stcsp_automaton_free(&outs[0]);
+            set_error(errs[r]);
+            return rcs[r];
+        }
+    *out = outs[0];
+    if (xs) *xs = xss[0];
+    return STCSP_OK;
 }
 
 int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *options, stcsp_automaton_t *out) {

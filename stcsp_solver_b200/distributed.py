@@ -1,14 +1,15 @@
-"""Multi-GPU solve: one process per GPU, states sharded by the hash of their signature.
+"""Multi-GPU solve: one process per GPU (torchrun), states sharded by the hash of their signature.
 
-Each rank runs the same C-ABI session (include/stcsp_b200.h) on its own GPU.  Per frontier wave:
-local expand -> leaves grouped by owner rank (device) -> counts all-to-all -> payload all-to-all
-(NCCL over NVLink when the backend is nccl) -> owners dedup/insert -> all-reduce of the frontier
-sizes for termination.  Constraint-set ids are kept identical on every rank by resolving the
-union of all ranks' requests in one sorted order.  Rank 0 gathers the per-rank parts and
-assembles + trims the automaton (reference fail rule, src/solveralgorithm.cpp:904-910).
+The data path is the library's own (include/stcsp_b200.h, ``stcsp_group_*``): every rank expands the search
+nodes of its states, groups the leaf records by owner in an outbox in its own HBM, meets the other ranks
+once per wave ON THE DEVICES (a header all-gather + barrier written straight into the peers' memory,
+mapped through CUDA IPC) and the owners' ingest kernels read their records out of the producers' outboxes
+over NVLink.  ``torch.distributed`` is plumbing only: it carries the 100-byte share blobs once, when the
+group forms (``solve_distributed`` / ``group_for``).
 
-The collective plumbing (``WaveExchange``) is device-agnostic so that it is covered by
-world_size-2 gloo tests on CPU; the sessions themselves need CUDA.
+``solve_distributed_nccl`` is the round-1 driver (two host-synchronised NCCL collectives per wave, driven
+from Python); it is kept as the baseline the device-side exchange is measured against, and its collective
+plumbing (``WaveExchange``) is device-agnostic so that world_size-2 gloo tests cover it on CPU.
 """
 from __future__ import annotations
 
@@ -94,14 +95,59 @@ class WaveExchange:
         return out
 
 
+_GROUPS = {}
+
+
+def group_for(pg=None) -> binding.Group:
+    """The stcsp group of this rank for a torch.distributed process group (formed once, then cached)."""
+    key = id(pg) if pg is not None else 0
+    if key in _GROUPS:
+        return _GROUPS[key]
+    rank, world = dist.get_rank(pg), dist.get_world_size(pg)
+    g = binding.Group(rank, world, torch.cuda.current_device())
+    mine = g.share()
+    on_gpu = dist.get_backend(pg) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    allb = torch.empty(world * t.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allb, t, group=pg)
+    raw = allb.cpu().numpy().tobytes()
+    n = len(mine)
+    g.attach([raw[i * n:(i + 1) * n] for i in range(world)])
+    dist.barrier(group=pg)                      # every rank has mapped every block before anybody uses one
+    _GROUPS[key] = g
+    return g
+
+
+def solve_distributed(model: binding.Model, options: Optional[binding.Options] = None, group=None,
+                      trim: bool = True, adaptive: bool = True):
+    """Solve on all ranks of `group` (default: the world).  Returns the merged Automaton on rank 0, None elsewhere.
+
+    The caller has initialised torch.distributed and set the CUDA device of this process.  adaptive: instances whose
+    waves never exceed 2**20 nodes are solved on one GPU -- every rank runs the same bounded search on its own device and
+    comes to the same verdict without any communication, rank 0 keeps the result; wider instances are sharded.
+    adaptive=False shards always."""
+    g = group_for(group)
+    opts = options if options is not None else binding.default_options()
+    opts.shard_mode = 0 if adaptive else 1
+    opts.no_trim = 0 if trim else 1
+    automaton, stats = g.solve(model, opts)
+    if automaton is not None:
+        stats = dict(stats)
+        stats["single_gpu"] = not stats["sharded"]
+        stats["records_sent"] = stats["records"]
+        automaton.exchange_stats = stats
+    return automaton
+
+
 # Below this wave width one B200 is faster than several: sharding adds two host-synchronised collectives per wave
 # (measured: partialorder_16, widest wave 0.5 M nodes, 14.7 ms on one GPU and 20-23 ms sharded over 2 or 4;
 # partialorder_18, 2.4 M nodes, 58.7 ms on one, 55.6 on two, 40.3 on four).
 SINGLE_GPU_FRONTIER = 1 << 20
 
 
-def solve_distributed(model: binding.Model, options: Optional[binding.Options] = None, group=None,
-                      trim: bool = True, adaptive: bool = True):
+def solve_distributed_nccl(model: binding.Model, options: Optional[binding.Options] = None, group=None,
+                           trim: bool = True, adaptive: bool = True):
     """Solve on all ranks of `group` (default: the world).  Returns the merged Automaton on rank 0, None elsewhere.
 
     The caller has initialised torch.distributed (backend nccl) and set the CUDA device of this process.

@@ -11,6 +11,11 @@ import sys
 
 import pytest
 
+# The group tests run up to eight ranks of a sharded solve on ONE device, and their exchange kernels wait for each other:
+# every rank's stream needs a hardware queue of its own (the default of 8 connections lets streams alias).  Read by the
+# driver when the CUDA context is created, i.e. after this line.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
