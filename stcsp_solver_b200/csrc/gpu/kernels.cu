@@ -2022,8 +2022,17 @@ size_t expand_smem_bytes(const DevModel &m) {
     return node_bytes(m) * m.node_slots + scratch_bytes(m) * kExpandWarps + align8(sizeof(DevModel)) + align8((size_t)m.stage_bytes);
 }
 
+// Function attributes (dynamic shared memory above 48 KiB, carve-out) belong to the CONTEXT: one record per device.
+constexpr int kMaxDevices = 64;
+static int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d >= 0 && d < kMaxDevices ? d : 0;
+}
+
 static void configure_expand(size_t smem) {
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {0};
+    size_t &configured = configured_dev[current_device()];
     if (smem > configured) {
         if (smem > 48 * 1024) {
             cudaFuncSetAttribute(expand_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -2040,8 +2049,15 @@ static void configure_expand(size_t smem) {
 int expand_max_grid(const DevModel &m, int sm_count) {
     const size_t smem = expand_smem_bytes(m);
     configure_expand(smem);
-    static size_t cached_smem = ~(size_t)0;
-    static int cached_per_sm = 0;
+    static size_t cached_smem_dev[kMaxDevices];
+    static int cached_per_sm_dev[kMaxDevices] = {0};
+    static bool init_done = false;
+    if (!init_done) {
+        for (int i = 0; i < kMaxDevices; i++) cached_smem_dev[i] = ~(size_t)0;
+        init_done = true;
+    }
+    size_t &cached_smem = cached_smem_dev[current_device()];
+    int &cached_per_sm = cached_per_sm_dev[current_device()];
     if (smem == cached_smem) return cached_per_sm * sm_count;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_kernel<false>, kExpandWarps * 32, smem) != cudaSuccess ||
@@ -2062,7 +2078,8 @@ void launch_expand(const DevModel &m, const ExpandArgs &a, int grid, int mode, c
 
 int search_max_grid(const DevModel &m, int sm_count) {
     const size_t smem = expand_smem_bytes(m);
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {0};
+    size_t &configured = configured_dev[current_device()];
     if (smem > configured) {
         if (smem > 48 * 1024) {
             cudaFuncSetAttribute(search_kernel<kExpandCtasPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -2072,8 +2089,15 @@ int search_max_grid(const DevModel &m, int sm_count) {
         cudaFuncSetAttribute(search_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = smem;
     }
-    static size_t cached_smem = ~(size_t)0;
-    static int cached_per_sm = 0;
+    static size_t cached_smem_dev[kMaxDevices];
+    static int cached_per_sm_dev[kMaxDevices] = {0};
+    static bool init_done = false;
+    if (!init_done) {
+        for (int i = 0; i < kMaxDevices; i++) cached_smem_dev[i] = ~(size_t)0;
+        init_done = true;
+    }
+    size_t &cached_smem = cached_smem_dev[current_device()];
+    int &cached_per_sm = cached_per_sm_dev[current_device()];
     if (smem == cached_smem) return cached_per_sm * sm_count;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<kExpandCtasPerSm>, kExpandWarps * 32, smem) != cudaSuccess ||

@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -1725,10 +1726,20 @@ enum HdrWord : int {
 };
 static_assert(H_STATS0 + 10 <= H_MODEL_SETS && H_MODEL_CAPS < kHdrWords && H_OFF0 + kMaxWorld <= H_N_STATES, "header row layout");
 
+// Meeting point of ranks that are threads of ONE process (stcsp_gpu_solve_multi): the same all-gather + barrier in host
+// memory.  A waiting exchange KERNEL is no option there: with peer access enabled, a cudaMalloc or cudaHostRegister issued
+// by one rank's thread maps memory into every peer context and waits for the peers' devices to drain -- which a kernel
+// that is itself waiting for that rank never lets happen (measured: 30 s timeout on two B200s).
+struct HostShared {
+    std::atomic<long long> arrived{0}, generation{0};
+    long long rows[2][kMaxWorld][kHdrWords];
+};
+
 struct ShareBlob {          // what a rank tells its peers once, when the group forms
     long long magic, pid, boot;
     int32_t rank, device;
     XBlock *block_raw;
+    HostShared *shared_raw;
     cudaIpcMemHandle_t block_handle;
 };
 
@@ -1749,6 +1760,8 @@ struct stcsp_group {
     ArenaDir h_dir{};                       // what the peers know of my arenas
     ArenaDir peer_dir[kMaxWorld];
     std::vector<void *> peer_arena[kMaxWorld];       // arenas of rank q mapped into this process (IPC)
+    HostShared *my_shared = nullptr, *shared = nullptr;     // shared: rank 0's, when every rank lives in this process
+    bool host_exchange = false;
     std::vector<std::string> wide_models;   // models known not to fit one GPU's wave limit: no single-GPU attempt
     cudaStream_t stream = nullptr;
     // statistics of the last sharded solve
@@ -1768,6 +1781,7 @@ struct stcsp_group {
         if (d_dir) cudaFree(d_dir);
         if (d_row) cudaFree(d_row);
         if (block) cudaFree(block);
+        delete my_shared;
     }
 
     static long long boot_id() {            // distinguishes hosts / containers that happen to share pids
@@ -1799,6 +1813,8 @@ struct stcsp_group {
         CK(cudaMalloc(&d_status, sizeof(int)));
         CK(cudaMemset(d_status, 0, sizeof(int)));
         CK(cudaMallocHost(&h_rows, ((size_t)kMaxWorld + 2) * kHdrWords * sizeof(long long)));
+        my_shared = new HostShared();
+        memset(my_shared->rows, 0, sizeof my_shared->rows);
         preload_search_kernels();
         preload_automaton_kernels(stream);
         preload_exchange_kernels();
@@ -1818,6 +1834,7 @@ struct stcsp_group {
         b->rank = rank;
         b->device = device;
         b->block_raw = block;
+        b->shared_raw = my_shared;
         if (cudaIpcGetMemHandle(&b->block_handle, block) != cudaSuccess) cudaGetLastError();    // (single-process groups do not need it)
     }
 
@@ -1851,7 +1868,41 @@ struct stcsp_group {
                 peers.block[q] = (XBlock *)p;
             }
         }
+        // every rank a thread of this process: meet in host memory (STCSP_GROUP_EXCHANGE=device keeps the device-side
+        // exchange, for tests that run all ranks on one GPU)
+        bool all_local = true;
+        for (int q = 0; q < world; q++) all_local = all_local && same_process[q];
+        const char *force = getenv("STCSP_GROUP_EXCHANGE");
+        host_exchange = all_local && !(force && !strcmp(force, "device"));
+        shared = blobs[0].shared_raw;
         attached = true;
+    }
+
+    const long long *exchange_host(const long long *row) {
+        const double t0 = now_s();
+        epoch++;
+        GTRACE("rank %d: host exchange %llu begins (n_in %lld leaves %lld pending %lld status %lld)", rank, epoch, row[H_N_IN],
+               row[H_N_LEAVES], row[H_N_PENDING], row[H_STATUS]);
+        memcpy(shared->rows[epoch & 1ull][rank], row, kHdrWords * sizeof(long long));
+        const long long gen = shared->generation.load();
+        if (shared->arrived.fetch_add(1) + 1 == world) {
+            shared->arrived.store(0);
+            shared->generation.store(gen + 1);
+        } else {
+            long spins = 0;
+            while (shared->generation.load() == gen) {
+                if (++spins > 2000) std::this_thread::yield();
+                if ((spins & 0xfffff) == 0 && now_s() - t0 > 60.0)
+                    throw Failure(STCSP_ERR_CUDA, "a rank of the group did not reach the exchange (timeout)");
+            }
+        }
+        memcpy(h_rows, shared->rows[epoch & 1ull], (size_t)world * kHdrWords * sizeof(long long));
+        x_exchanges++;
+        x_exchange_ms += (now_s() - t0) * 1e3;
+        for (int q = 0; q < world; q++)
+            if (h_rows[(size_t)q * kHdrWords + H_STATUS] != 0)
+                throw PeerFailure((int)h_rows[(size_t)q * kHdrWords + H_STATUS], "rank " + std::to_string(q) + " of the group failed");
+        return h_rows;
     }
 
     // A device pointer of rank q as this process can use it.
@@ -1893,6 +1944,7 @@ struct stcsp_group {
         // (on the calling session's stream: a rank then needs ONE hardware queue to make progress; with every rank of a
         //  group on the same device -- the test layout -- more streams than CUDA_DEVICE_MAX_CONNECTIONS alias onto the same
         //  queue, and a kernel queued behind a peer's waiting exchange kernel would never start)
+        if (host_exchange) return exchange_host(row);
         const double t0 = now_s();
         epoch++;
         GTRACE("rank %d: exchange %llu begins (n_in %lld leaves %lld pending %lld status %lld)", rank, epoch, row[H_N_IN], row[H_N_LEAVES],
@@ -2467,7 +2519,12 @@ int stcsp_gpu_solve_multi(const stcsp_problem_t *problem, const stcsp_options_t 
     std::lock_guard<std::mutex> lock(mu);                   // one multi-GPU solve at a time per process
     std::vector<int> devs;
     for (int i = 0; i < n_gpus; i++) devs.push_back(devices ? devices[i] : i);
-    std::vector<stcsp_group *> &team = teams[devs];
+    std::vector<int> team_key = devs;
+    {
+        const char *force = getenv("STCSP_GROUP_EXCHANGE");       // (part of the key: read when a team forms)
+        team_key.push_back(force && !strcmp(force, "device") ? -2 : -1);
+    }
+    std::vector<stcsp_group *> &team = teams[team_key];
     if (team.empty()) {
         std::vector<ShareBlob> blobs((size_t)n_gpus);
         int rc = STCSP_OK;
@@ -2502,12 +2559,22 @@ int stcsp_gpu_solve_multi(const stcsp_problem_t *problem, const stcsp_options_t 
     if (rcs[0] != STCSP_OK) errs[0] = stcsp_last_error();
     for (std::thread &t : pool) t.join();
     for (int r = 1; r < n_gpus; r++) stcsp_automaton_free(&outs[r]);
-    for (int r = 0; r < n_gpus; r++)
-        if (rcs[r] != STCSP_OK) {
+    {
+        // a rank that failed on its own explains more than the ranks that then waited for it in vain
+        int first = -1;
+        for (int r = 0; r < n_gpus; r++)
+            if (rcs[r] != STCSP_OK && (first < 0 || errs[first].find("did not reach the exchange") != std::string::npos ||
+                                       errs[first].find("of the group failed") != std::string::npos))
+                first = first < 0 || errs[r].find("did not reach the exchange") == std::string::npos ? r : first;
+        if (first >= 0) {
+            std::string all = "rank " + std::to_string(first) + ": " + errs[first];
+            for (int r = 0; r < n_gpus; r++)
+                if (r != first && rcs[r] != STCSP_OK) all += " | rank " + std::to_string(r) + ": " + errs[r];
             stcsp_automaton_free(&outs[0]);
-            set_error(errs[r]);
-            return rcs[r];
+            set_error(all);
+            return rcs[first];
         }
+    }
     *out = outs[0];
     if (xs) *xs = xss[0];
     return STCSP_OK;

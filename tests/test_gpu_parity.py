@@ -19,7 +19,8 @@ import _oracle
 
 pytestmark = pytest.mark.gpu
 
-CASES = sorted(k for k, g in GOLDENS.items() if "sha256" in g)
+# (partialorder_19 / _20 -- 30 M and 63 M edges, 12 GB of automaton -- are checked by bench.py's `also` leg, not here)
+CASES = sorted(k for k, g in GOLDENS.items() if "sha256" in g and g.get("edges", 0) <= 20_000_000)
 
 
 def run_gpu(text, flags=(), **opts):

@@ -124,9 +124,14 @@ GROUP_CASES = ["juggling_b4_f5_nosym", "juggling_b5_f6", "digitinvader3", "parti
                "probe_first_expr", "partialorder_13"]
 
 
+@pytest.mark.parametrize("exchange", ["host", "device"])
 @pytest.mark.parametrize("world", [2, 3, 8])
 @pytest.mark.parametrize("name", GROUP_CASES)
-def test_group_solve_sharded_matches_reference(name, world):
+def test_group_solve_sharded_matches_reference(name, world, exchange, monkeypatch):
+    """exchange: ranks that are threads of one process meet in host memory by default; "device" forces the exchange kernel
+    (header rows and flags written into the peers' device memory, a waiting kernel as the barrier) -- what ranks in
+    different processes use."""
+    monkeypatch.setenv("STCSP_GROUP_EXCHANGE", exchange)
     g = GOLDENS[name]
     model = binding.Model(golden_text(g))
     automaton, xs = binding.solve_multi(model, world, binding.default_options(shard_mode=1), devices=[0] * world)
@@ -173,7 +178,8 @@ def test_group_solve_on_random_models(seed):
     assert binding.Solution(model, automaton).canonical_text() == want
 
 
-def test_group_solve_semantic_golden_po15():
+def test_group_solve_semantic_golden_po15(monkeypatch):
+    monkeypatch.setenv("STCSP_GROUP_EXCHANGE", "device")
     g = GOLDENS["semantic_partialorder_15"]
     model = binding.Model(golden_text(g))
     automaton, xs = binding.solve_multi(model, 4, binding.default_options(shard_mode=1), devices=[0] * 4)
