@@ -965,25 +965,50 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
                 if (gtid == 0) atomicOr(&P.counters[C_OVERFLOW], 1ull);
                 continue;
             }
+            dbg_stamp(dbg, P.dbg_cap, 3);               // branching variables chosen, room reserved
             const int hdr = pack_branch(bv, bv1, bv2);
-            const int dw = 4 + 2 * (bv * k), dw1 = bv1 >= 0 ? 4 + 2 * (bv1 * k) : -8, dw2 = bv2 >= 0 ? 4 + 2 * (bv2 * k) : -8;
-            for (int j = gw; j < d; j += gwarps) {
-                const u64 one = nth_bit(D, j % d0);
-                const u64 one1 = bv1 >= 0 ? nth_bit(D1, (j / d0) % d1) : 0ull;
-                const u64 one2 = bv2 >= 0 ? nth_bit(D2, j / (d0 * d1)) : 0ull;
-                int32_t *dst = P.out_nodes + (base + j) * NW;
-                for (int i = lane; i < NW; i += 32) {
-                    int32_t val = wm.nodew[i];
-                    if (i == 3) val = hdr;
-                    else if (i == dw) val = (int32_t)(uint32_t)(one & 0xffffffffull);
-                    else if (i == dw + 1) val = (int32_t)(uint32_t)(one >> 32);
-                    else if (i == dw1) val = (int32_t)(uint32_t)(one1 & 0xffffffffull);
-                    else if (i == dw1 + 1) val = (int32_t)(uint32_t)(one1 >> 32);
-                    else if (i == dw2) val = (int32_t)(uint32_t)(one2 & 0xffffffffull);
-                    else if (i == dw2 + 1) val = (int32_t)(uint32_t)(one2 >> 32);
-                    dst[i] = val;
+            const int dw = 4 + 2 * (bv * k), dw1 = bv1 >= 0 ? 4 + 2 * (bv1 * k) : -1, dw2 = bv2 >= 0 ? 4 + 2 * (bv2 * k) : -1;
+            // Writing a child takes ~130 dependent instructions if a warp does it word by word with selects (0.6 us per
+            // child: 25 us for the 343 children of the root of juggling_b6_f6_nosym).  Two passes instead:
+            //   copy   every lane OWNS word indices lane, lane + 32, ... : it reads them from the parent once and stores them
+            //          into one child after the other (address arithmetic and stores only);
+            //   patch  every lane owns a CHILD: it works out that child's one-bit domains and overwrites the seven words
+            //          that differ from the parent.
+            const int my_children = (d - gw + gwarps - 1) / gwarps;        // children gw, gw + gwarps, ...
+            for (int c0 = 0; c0 < NW; c0 += 128) {
+                const int i0 = c0 + lane, i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
+                const int32_t w0 = i0 < NW ? wm.nodew[i0] : 0, w1 = i1 < NW ? wm.nodew[i1] : 0, w2 = i2 < NW ? wm.nodew[i2] : 0,
+                              w3 = i3 < NW ? wm.nodew[i3] : 0;
+                int32_t *dst = P.out_nodes + (base + gw) * NW;
+                const long long stride = (long long)gwarps * NW;
+                for (int t = 0; t < my_children; t++, dst += stride) {
+                    if (i0 < NW) dst[i0] = w0;
+                    if (i1 < NW) dst[i1] = w1;
+                    if (i2 < NW) dst[i2] = w2;
+                    if (i3 < NW) dst[i3] = w3;
                 }
             }
+            __syncwarp();                               // the patches below overwrite words other lanes have just stored
+            for (int r0 = 0; r0 < my_children; r0 += 32) {
+                if (r0 + lane >= my_children) continue;
+                const int j = gw + (r0 + lane) * gwarps;
+                int32_t *dst = P.out_nodes + (base + j) * NW;
+                const u64 m0 = nth_bit(D, j % d0);
+                dst[3] = hdr;
+                dst[dw] = (int32_t)(uint32_t)(m0 & 0xffffffffull);
+                dst[dw + 1] = (int32_t)(uint32_t)(m0 >> 32);
+                if (bv1 >= 0) {
+                    const u64 m1 = nth_bit(D1, (j / d0) % d1);
+                    dst[dw1] = (int32_t)(uint32_t)(m1 & 0xffffffffull);
+                    dst[dw1 + 1] = (int32_t)(uint32_t)(m1 >> 32);
+                }
+                if (bv2 >= 0) {
+                    const u64 m2 = nth_bit(D2, j / (d0 * d1));
+                    dst[dw2] = (int32_t)(uint32_t)(m2 & 0xffffffffull);
+                    dst[dw2 + 1] = (int32_t)(uint32_t)(m2 >> 32);
+                }
+            }
+            dbg_stamp(dbg, P.dbg_cap, 4);               // children written (this warp's share)
         }
     }
     // st_rev / my_tuples are per thread (scalar revisions), st_tuples is warp-uniform (cooperative revisions)

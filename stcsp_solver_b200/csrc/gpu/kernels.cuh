@@ -53,6 +53,7 @@ struct DevModel {
     int32_t lazy_ahead;         // 1: pointwise propagators at look-ahead offsets run only once the current point is bound
     int32_t multi_branch;       // 1: narrow waves branch on up to three variables at once (branch_fan)
     int32_t fan_warps;          // warps of the narrow search grid (SM count x warps per CTA)
+    int32_t dbg_flags;          // experiments (environment STCSP_DBG_FLAGS); 0 in production
     long long enum_now, enum_ahead;
     const int32_t *lb, *width, *sig_vars;
     const DevSet *sets;
@@ -256,6 +257,7 @@ constexpr int kHdrWords = 64;               // long long words per header row
 constexpr int kMaxArenas = 48;              // device arenas a rank can publish
 struct ArenaDir {                           // where a rank's device memory lives, for peers in other processes
     long long n;
+    long long serial[kMaxArenas];           // process-wide unique id of the arena (indices shift when arenas are freed)
     long long size[kMaxArenas];
     unsigned char handle[kMaxArenas][64];   // cudaIpcMemHandle_t of each arena's base
 };

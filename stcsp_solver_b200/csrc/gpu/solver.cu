@@ -78,24 +78,27 @@ struct DeviceCache {
         int device;
         char *base;
         size_t size, used;
-        bool has_handle = false;
+        bool has_handle = false;            // exported to peers (CUDA IPC): never freed again -- freeing memory that another
+                                            // process still has mapped is undefined
         cudaIpcMemHandle_t handle{};
-        Arena(int d, char *b, size_t s, size_t u) : device(d), base(b), size(s), used(u) {}
+        long long serial;
+        Arena(int d, char *b, size_t s, size_t u) : device(d), base(b), size(s), used(u) {
+            static std::atomic<long long> next{1};
+            serial = next.fetch_add(1);
+        }
     };
     std::vector<Arena> arenas;
     std::map<int, long long> outstanding;           // blocks handed out per device
-    // Which arena of `device` (counting that device's arenas in creation order) holds p, and where in it.
-    bool locate(int device, const void *p, long long &index, long long &offset) {
+    // Which arena of `device` holds p (by its serial number), and where in it.
+    bool locate(int device, const void *p, long long &serial, long long &offset) {
         std::lock_guard<std::mutex> g(mu);
-        long long i = 0;
         for (const Arena &a : arenas) {
             if (a.device != device) continue;
             if ((const char *)p >= a.base && (const char *)p < a.base + a.size) {
-                index = i;
+                serial = a.serial;
                 offset = (const char *)p - a.base;
                 return true;
             }
-            i++;
         }
         return false;
     }
@@ -114,6 +117,7 @@ struct DeviceCache {
                 }
                 a.has_handle = true;
             }
+            d.serial[d.n] = a.serial;
             d.size[d.n] = (long long)a.size;
             static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
             memcpy(d.handle[d.n], &a.handle, 64);
@@ -174,10 +178,16 @@ struct DeviceCache {
     void trim(int device) {
         std::lock_guard<std::mutex> g(mu);
         if (outstanding[device] > 0) return;
-        for (auto &kv : free_blocks)
-            if (kv.first.first == device) kv.second.clear();
+        for (auto &kv : free_blocks) {
+            if (kv.first.first != device) continue;
+            std::vector<void *> keep;               // blocks inside exported arenas stay usable
+            for (void *p : kv.second)
+                for (const Arena &a : arenas)
+                    if (a.device == device && a.has_handle && (char *)p >= a.base && (char *)p < a.base + a.size) keep.push_back(p);
+            kv.second.swap(keep);
+        }
         for (size_t i = 0; i < arenas.size();) {
-            if (arenas[i].device == device) {
+            if (arenas[i].device == device && !arenas[i].has_handle) {
                 cudaFree(arenas[i].base);
                 arenas.erase(arenas.begin() + (long)i);
             } else {
@@ -694,6 +704,10 @@ struct stcsp_session {
         dm.lazy_ahead = opt.lookahead == 2 ? 1 : 0;
         dm.multi_branch = opt.single_branch ? 0 : 1;
         dm.fan_warps = sm_count * kExpandWarps;
+        {
+            static const int flags = getenv("STCSP_DBG_FLAGS") ? atoi(getenv("STCSP_DBG_FLAGS")) : 0;
+            dm.dbg_flags = flags;
+        }
         if (dm.V >= (1 << 10) - 1) dm.multi_branch = 0;        // the node header packs variable indices in ten bits
         // four node blocks per warp (quad mode for wide waves) when three CTAs still fit an SM
         dm.node_slots = 4 * kExpandWarps;
@@ -1759,7 +1773,7 @@ struct stcsp_group {
     long long *h_rows = nullptr;            // pinned: [world][kHdrWords] + a status word + my row
     ArenaDir h_dir{};                       // what the peers know of my arenas
     ArenaDir peer_dir[kMaxWorld];
-    std::vector<void *> peer_arena[kMaxWorld];       // arenas of rank q mapped into this process (IPC)
+    std::map<long long, void *> peer_arena[kMaxWorld];      // arenas of rank q mapped into this process (CUDA IPC), by serial
     HostShared *my_shared = nullptr, *shared = nullptr;     // shared: rank 0's, when every rank lives in this process
     bool host_exchange = false;
     std::vector<std::string> wide_models;   // models known not to fit one GPU's wave limit: no single-GPU attempt
@@ -1771,8 +1785,8 @@ struct stcsp_group {
     ~stcsp_group() {
         if (device >= 0) cudaSetDevice(device);
         for (int q = 0; q < world; q++) {
-            for (void *p : peer_arena[q])
-                if (p) cudaIpcCloseMemHandle(p);
+            for (auto &kv : peer_arena[q])
+                if (kv.second) cudaIpcCloseMemHandle(kv.second);
             if (attached && q != rank && !same_process[q] && peers.block[q]) cudaIpcCloseMemHandle(peers.block[q]);
         }
         if (stream) cudaStreamDestroy(stream);
@@ -1908,14 +1922,17 @@ struct stcsp_group {
     // A device pointer of rank q as this process can use it.
     const void *peer_ptr(int q, long long raw, long long addr) {
         if (same_process[q]) return (const void *)(uintptr_t)raw;
-        const long long idx = addr >> 40, off = addr & ((1ll << 40) - 1);
-        if (idx < 0 || idx >= kMaxArenas) throw Failure(STCSP_ERR_INVALID, "peer address names an unknown arena");
-        if ((long long)peer_arena[q].size() <= idx) peer_arena[q].resize((size_t)idx + 1, nullptr);
-        if (!peer_arena[q][idx]) {
+        const long long serial = addr >> 40, off = addr & ((1ll << 40) - 1);
+        if (addr < 0) throw Failure(STCSP_ERR_INVALID, "peer address outside the arenas of its rank");
+        auto it = peer_arena[q].find(serial);
+        if (it == peer_arena[q].end()) {
             // the directory rank q published with (or before) the row that carries this address
             CK(cudaMemcpyAsync(&peer_dir[q], &block->dir[q], sizeof(ArenaDir), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
-            if (idx >= peer_dir[q].n) throw Failure(STCSP_ERR_INVALID, "peer address names an arena its rank has not published");
+            long long idx = -1;
+            for (long long i = 0; i < peer_dir[q].n && i < kMaxArenas; i++)
+                if (peer_dir[q].serial[i] == serial) idx = i;
+            if (idx < 0) throw Failure(STCSP_ERR_INVALID, "peer address names an arena its rank has not published");
             cudaIpcMemHandle_t h;
             memcpy(&h, peer_dir[q].handle[idx], 64);
             void *p = nullptr;
@@ -1925,9 +1942,9 @@ struct stcsp_group {
                 throw Failure(STCSP_ERR_CUDA, std::string("cannot map device memory of rank ") + std::to_string(q) + " (CUDA IPC): " +
                                                   cudaGetErrorString(e));
             }
-            peer_arena[q][idx] = p;
+            it = peer_arena[q].emplace(serial, p).first;
         }
-        return (const char *)peer_arena[q][idx] + off;
+        return (const char *)it->second + off;
     }
 
     // my pointer p as (raw, arena << 40 | offset) for a header row
@@ -1955,7 +1972,7 @@ struct stcsp_group {
         ArenaDir now_dir;
         memset(&now_dir, 0, sizeof now_dir);
         device_cache().directory(device, now_dir);
-        if (now_dir.n != h_dir.n) {
+        if (memcmp(&now_dir, &h_dir, sizeof now_dir) != 0) {
             h_dir = now_dir;
             CK(cudaMemcpy(d_dir, &h_dir, sizeof(ArenaDir), cudaMemcpyHostToDevice));
         }
