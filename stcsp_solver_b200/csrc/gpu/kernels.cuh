@@ -52,7 +52,7 @@ struct DevModel {
     int32_t force_mode;         // 0 automatic, else ExpandMode + 1
     int32_t lazy_ahead;         // 1: pointwise propagators at look-ahead offsets run only once the current point is bound
     int32_t multi_branch;       // 1: narrow waves branch on up to three variables at once (branch_fan)
-    int32_t fan_warps;          // warps of the narrow search grid (SM count x warps per CTA)
+    int32_t fan_warps;          // children a narrow wave may create in total (2 x SM count), see branch_fan
     int32_t dbg_flags;          // experiments (environment STCSP_DBG_FLAGS); 0 in production
     long long enum_now, enum_ahead;
     const int32_t *lb, *width, *sig_vars;
@@ -193,7 +193,7 @@ __host__ __device__ inline int pick_expand_mode(const DevModel &m, long long n_i
     return EXPAND_WARP;
 }
 // Children a node of a wave of n_in nodes may create: as long as the NEXT wave still has a resident warp per node
-// (m.fan_warps = warps of the narrow grid, one CTA per SM), branching on several variables at once saves whole waves and costs nothing but
+// (m.fan_warps, two per SM), branching on several variables at once saves whole waves and costs nothing but
 // idle lanes.  1 = never more than the first unbound variable's domain.  Off in lazy look-ahead mode and when a mapping of
 // nodes to threads is forced (tests compare the statistics of the paths).
 __host__ __device__ inline int branch_fan(const DevModel &m, long long n_in, long long out_cap) {

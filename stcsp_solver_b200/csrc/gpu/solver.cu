@@ -703,7 +703,14 @@ struct stcsp_session {
         }
         dm.lazy_ahead = opt.lookahead == 2 ? 1 : 0;
         dm.multi_branch = opt.single_branch ? 0 : 1;
-        dm.fan_warps = sm_count * kExpandWarps;
+        // Measured (tools/fan_sweep.py, device ms): b6_f6_nosym 0.318 with one variable per node, 0.302 / 0.271 / 0.273 / 0.274 / 0.269
+        // with room for 148 / 296 / 592 / 1184 / 3552 children per wave; the symmetric instances and digitinvader lose a few
+        // per cent beyond 296 (children that fail at once still cost a node each).
+        dm.fan_warps = sm_count * 2;
+        {
+            static const int fan_override = getenv("STCSP_FAN_WARPS") ? atoi(getenv("STCSP_FAN_WARPS")) : 0;   // tuning experiments
+            if (fan_override > 0) dm.fan_warps = fan_override;
+        }
         {
             static const int flags = getenv("STCSP_DBG_FLAGS") ? atoi(getenv("STCSP_DBG_FLAGS")) : 0;
             dm.dbg_flags = flags;

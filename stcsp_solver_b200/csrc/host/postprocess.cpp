@@ -168,8 +168,12 @@ int stcsp_postprocess(const stcsp_problem_t *problem, const stcsp_automaton_t *a
         w.fin[s] = w.valid[s] = f;
     }
     if (w.n > 0) w.fin[0] = w.valid[0] = a->root_final != 0;
-    w.build_parents(false);
-    {
+    bool all_valid = true;
+    for (int64_t s = 0; s < w.n && all_valid; s++) all_valid = w.valid[s] != 0;
+    // (a model without `until` -- every shipped and generated benchmark instance -- makes every state final: nothing to
+    //  propagate, and at partialorder_20 size the parent lists alone would be 63 M entries)
+    if (!all_valid) {
+        w.build_parents(false);
         std::vector<int32_t> stack;
         for (int64_t s = 1; s < w.n; s++)
             if (w.valid[s]) stack.push_back((int32_t)s);
@@ -179,8 +183,8 @@ int stcsp_postprocess(const stcsp_problem_t *problem, const stcsp_automaton_t *a
             for (int32_t p : w.parents[s])
                 if (!w.valid[p]) { w.valid[p] = 1; stack.push_back(p); }
         }
+        w.drop_edges_into_invalid(true);
     }
-    w.drop_edges_into_invalid(true);
 
     out->adver1 = out->adver2 = -1;
     if (adversarial1 || adversarial2) {
