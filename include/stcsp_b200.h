@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define STCSP_ABI_VERSION 1
+#define STCSP_ABI_VERSION 2
 
 /* ---------------------------------------------------------------------------------------------
  * Constraint expressions: one postfix (post-order) token list per constraint.
@@ -112,7 +112,10 @@ typedef struct stcsp_options {
                                         once, which shortens the search tree.  Never changes the automaton. */
     int32_t shard_mode;              /* group solves: 0 adaptive (instances whose waves fit one GPU stay on one GPU), 1 always shard
                                         the search over the GPUs of the group */
-    int32_t reserved[1];
+    int32_t adversarial;             /* post-processing fixpoints to run ON THE DEVICE before the download: bit 0 = flag -a
+                                        (reference adversarialTraverse, src/graph.cpp:304-355), bit 1 = flag -z
+                                        (adversarialTraverse2, :247-302).  The automaton then carries state_valid / edge_alive /
+                                        adver1 / adver2 and stcsp_postprocess, called with the same flags, only numbers it. */
 } stcsp_options_t;
 
 /* ---------------------------------------------------------------------------------------------
@@ -161,8 +164,21 @@ typedef struct stcsp_automaton {
     int64_t n_expand_launches;       /* launches of that kernel */
     int64_t algorithmic_bytes;       /* SURVEY.md section 8(d) formula with this run's counts */
     int64_t h2d_bytes, d2h_bytes;
+    /* Post-processing done on the device.  Liveness of reference graphTraverse
+     * (src/graph.cpp:357-418) is computed for every model with `until`: final = all until flags set, valid = a final state can
+     * be reached; the adversarial fixpoints when stcsp_options_t::adversarial asks for them.  post_applied says which ran
+     * (0: none -- models without `until`, automata assembled on the host -- the three pointers are NULL and
+     * stcsp_postprocess derives everything itself). */
+    uint8_t *state_final;            /* [n_states] or NULL */
+    uint8_t *state_valid;            /* [n_states] or NULL: valid after every fixpoint that ran */
+    uint8_t *edge_alive;             /* [n_edges] or NULL: 0 = removed by the fixpoints that ran (an end is invalid, or -z dropped it) */
+    int32_t post_applied;            /* STCSP_POST_* bits */
+    int32_t adver1, adver2;          /* root valid after -a / after -z (what the reference prints, src/solver.cpp:300-321); -1 = not run */
+    int32_t pad0;
     void *impl;                      /* private */
 } stcsp_automaton_t;
+
+enum stcsp_post { STCSP_POST_LIVENESS = 1, STCSP_POST_ADVERSARIAL1 = 2, STCSP_POST_ADVERSARIAL2 = 4 };
 
 enum stcsp_status {
     STCSP_OK = 0,

@@ -42,7 +42,7 @@ class Options(C.Structure):
         ("max_frontier_nodes", C.c_int64), ("max_states", C.c_int64), ("max_edges", C.c_int64),
         ("expand_mode", C.c_int32), ("profile_kernels", C.c_int32), ("no_trim", C.c_int32),
         ("lookahead", C.c_int32), ("wide_wave_nodes", C.c_int32), ("single_branch", C.c_int32),
-                ("shard_mode", C.c_int32), ("reserved", C.c_int32 * 1),
+        ("shard_mode", C.c_int32), ("adversarial", C.c_int32),
     ]
 
 
@@ -69,6 +69,8 @@ class AutomatonC(C.Structure):
         ("solve_ms", C.c_double), ("wall_ms", C.c_double), ("expand_ms", C.c_double),
         ("n_expand_launches", C.c_int64),
         ("algorithmic_bytes", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("state_final", C.POINTER(C.c_uint8)), ("state_valid", C.POINTER(C.c_uint8)), ("edge_alive", C.POINTER(C.c_uint8)),
+        ("post_applied", C.c_int32), ("adver1", C.c_int32), ("adver2", C.c_int32), ("pad0", C.c_int32),
         ("impl", C.c_void_p),
     ]
 
@@ -233,6 +235,11 @@ class Automaton:
         self.edge_src = _np(a.edge_src, a.n_edges, np.int32, copy)
         self.edge_dst = _np(a.edge_dst, a.n_edges, np.int32, copy)
         self.edge_label = _np(a.edge_label, a.n_edges * a.n_vars, np.int32, copy).reshape(a.n_edges, a.n_vars)
+        # post-processing done on the device (None when it did not run)
+        self.post_applied = a.post_applied
+        self.state_final = _np(a.state_final, a.n_states, np.uint8, copy) if a.state_final else None
+        self.state_valid = _np(a.state_valid, a.n_states, np.uint8, copy) if a.state_valid else None
+        self.edge_alive = _np(a.edge_alive, a.n_edges, np.uint8, copy) if a.edge_alive else None
 
     def stats(self) -> dict:
         a = self.c

@@ -58,6 +58,7 @@ int run_once(const Cli &cli, bool print_stat, Run &r) {
     stcsp_automaton_t automaton;
     t = now_s();
     opt.shard_mode = cli.shard;
+    opt.adversarial = (cli.adv1 ? 1 : 0) | (cli.adv2 ? 2 : 0);      // -a / -z fixpoints run on the device, before the download
     stcsp_exchange_stats_t xs;
     memset(&xs, 0, sizeof xs);
     rc = cli.gpus > 1 ? stcsp_gpu_solve_multi(problem, &opt, cli.gpus, nullptr, &automaton, &xs)     // one host thread per GPU

@@ -285,6 +285,137 @@ void launch_place_keys(const int32_t *keys_in, int32_t *keys_out, long long tota
                                                                                         make_counts(world, n_states));
 }
 
+// ---- post-processing fixpoints on the device ---------------------------------------------------
+// liveness        reference graphTraverse        src/graph.cpp:357-418  least fixpoint: valid = a final state can be reached
+// adversarial -a  reference adversarialTraverse  src/graph.cpp:304-355  greatest fixpoint: every value of variable #5 has an edge
+// adversarial -z  reference adversarialTraverse2 src/graph.cpp:247-302  greatest fixpoint: some value of #6 answers every value of #5
+// All three run over the edge list that survived the fail rule, one thread per edge / per state, without a CSR (the value sets of
+// a state are 64-bit masks collected with atomicOr: domains have at most 64 values); the host iterates each until *changed stays 0.
+// `valid` only grows (liveness) or only shrinks (-a, -z), so stale reads inside a sweep only delay the fixpoint by a sweep.
+// final = every until flag the reference looks at is set (it looks at numUntil = DISTINCT right-hand variables, :372-374).
+__global__ void __launch_bounds__(256) liveness_init_kernel(const int32_t *keys, long long ns, int KW, int n_sig, int n_flags,
+                                                            int root_final, uint8_t *fin, uint8_t *valid) {
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += (long long)gridDim.x * blockDim.x) {
+        bool f = true;
+        if (s == 0) f = root_final != 0;
+        else
+            for (int c = 0; f && c < n_flags; c++) f = keys[s * KW + 1 + n_sig + c] == 1;
+        fin[s] = f;
+        valid[s] = f;
+    }
+}
+
+__global__ void __launch_bounds__(256) liveness_step_kernel(const int32_t *src, const int32_t *dst, long long ne, uint8_t *valid,
+                                                            int32_t *changed) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (long long)gridDim.x * blockDim.x) {
+        const int s = src[e], d = dst[e];
+        if (s != d && valid[d] && !valid[s]) {
+            valid[s] = 1;
+            *changed = 1;
+        }
+    }
+}
+
+// -a sweep, edge half: have[src] |= bit(value of the opponent's variable) for every edge into a valid state
+__global__ void __launch_bounds__(256) adv1_edge_kernel(const int32_t *src, const int32_t *dst, const int32_t *label, long long ne,
+                                                        int V, int var, int lb, const uint8_t *valid,
+                                                        unsigned long long *have) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (long long)gridDim.x * blockDim.x) {
+        const int s = src[e];
+        if (!valid[s] || !valid[dst[e]]) continue;
+        const int b = label[e * V + var] - lb;
+        if (b >= 0 && b < 64) atomicOr(have + s, 1ull << b);
+    }
+}
+
+// -a sweep, state half: a valid state stays valid iff every value lb..ub was seen (reference checkVertexOutEdge, :304-326)
+__global__ void __launch_bounds__(256) adv1_state_kernel(long long ns, unsigned long long full, unsigned long long *have,
+                                                         uint8_t *valid, int32_t *changed) {
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long h = have[s];
+        have[s] = 0;                                 // ready for the next sweep
+        if (valid[s] && h != full) {
+            valid[s] = 0;
+            *changed = 1;
+        }
+    }
+}
+
+// -z sweep, edge half: cover[src][avatar value] |= bit(opponent value) for every edge into a valid state
+__global__ void __launch_bounds__(256) adv2_edge_kernel(const int32_t *src, const int32_t *dst, const int32_t *label, long long ne,
+                                                        int V, int op, int op_lb, int ava, int ava_lb, int A,
+                                                        const uint8_t *valid, unsigned long long *cover) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (long long)gridDim.x * blockDim.x) {
+        const int s = src[e];
+        if (!valid[s] || !valid[dst[e]]) continue;
+        const int a = label[e * V + ava] - ava_lb, b = label[e * V + op] - op_lb;
+        if (a >= 0 && a < A && b >= 0 && b < 64) atomicOr(cover + (long long)s * A + a, 1ull << b);
+    }
+}
+
+// -z sweep, state half: valid iff some avatar value saw every opponent value (reference checkVertexOutEdge2, :247-273).
+// `clear` = 0 on the last sweep keeps the masks for adv2_kill_kernel.
+__global__ void __launch_bounds__(256) adv2_state_kernel(long long ns, int A, unsigned long long full,
+                                                         const unsigned long long *cover, uint8_t *valid, int32_t *changed) {
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += (long long)gridDim.x * blockDim.x) {
+        if (!valid[s]) continue;
+        bool ok = false;
+        for (int a = 0; a < A && !ok; a++) ok = cover[s * A + a] == full;
+        if (!ok) {
+            valid[s] = 0;
+            *changed = 1;
+        }
+    }
+}
+
+// What survives: both ends valid, and (after -z, cover != NULL) the avatar value of the edge answers every opponent value
+// (the reference deletes the other edges of a valid vertex, :262-271, and every edge into an invalid vertex, :290-300 / :343-353).
+__global__ void __launch_bounds__(256) post_alive_kernel(const int32_t *src, const int32_t *dst, const int32_t *label, long long ne,
+                                                         int V, int ava, int ava_lb, int A, unsigned long long full,
+                                                         const unsigned long long *cover, const uint8_t *valid, uint8_t *alive) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (long long)gridDim.x * blockDim.x) {
+        const int s = src[e];
+        bool ok = valid[s] && valid[dst[e]];
+        if (ok && cover) {
+            const int a = label[e * V + ava] - ava_lb;
+            ok = a >= 0 && a < A && cover[(long long)s * A + a] == full;
+        }
+        alive[e] = ok;
+    }
+}
+
+void launch_liveness_init(const int32_t *keys, long long ns, int KW, int n_sig, int n_flags, int root_final, uint8_t *fin,
+                          uint8_t *valid, int sm_count, cudaStream_t stream) {
+    if (ns > 0) liveness_init_kernel<<<grid_for(ns, 256, sm_count), 256, 0, stream>>>(keys, ns, KW, n_sig, n_flags, root_final, fin, valid);
+}
+
+void launch_liveness_step(const int32_t *src, const int32_t *dst, long long ne, uint8_t *valid, int32_t *changed, int sm_count,
+                          cudaStream_t stream) {
+    if (ne > 0) liveness_step_kernel<<<grid_for(ne, 256, sm_count), 256, 0, stream>>>(src, dst, ne, valid, changed);
+}
+
+void launch_adv1_sweep(const int32_t *src, const int32_t *dst, const int32_t *label, long long ne, int V, int var, int lb,
+                       unsigned long long full, long long ns, unsigned long long *have, uint8_t *valid, int32_t *changed,
+                       int sm_count, cudaStream_t stream) {
+    if (ne > 0) adv1_edge_kernel<<<grid_for(ne, 256, sm_count), 256, 0, stream>>>(src, dst, label, ne, V, var, lb, valid, have);
+    if (ns > 0) adv1_state_kernel<<<grid_for(ns, 256, sm_count), 256, 0, stream>>>(ns, full, have, valid, changed);
+}
+
+void launch_adv2_sweep(const int32_t *src, const int32_t *dst, const int32_t *label, long long ne, int V, int op, int op_lb, int ava,
+                       int ava_lb, int A, unsigned long long full, long long ns, unsigned long long *cover, uint8_t *valid,
+                       int32_t *changed, int sm_count, cudaStream_t stream) {
+    if (ne > 0)
+        adv2_edge_kernel<<<grid_for(ne, 256, sm_count), 256, 0, stream>>>(src, dst, label, ne, V, op, op_lb, ava, ava_lb, A, valid, cover);
+    if (ns > 0) adv2_state_kernel<<<grid_for(ns, 256, sm_count), 256, 0, stream>>>(ns, A, full, cover, valid, changed);
+}
+
+void launch_post_alive(const int32_t *src, const int32_t *dst, const int32_t *label, long long ne, int V, int ava, int ava_lb, int A,
+                       unsigned long long full, const unsigned long long *cover, const uint8_t *valid, uint8_t *alive, int sm_count,
+                       cudaStream_t stream) {
+    if (ne > 0)
+        post_alive_kernel<<<grid_for(ne, 256, sm_count), 256, 0, stream>>>(src, dst, label, ne, V, ava, ava_lb, A, full, cover, valid, alive);
+}
+
 void preload_automaton_kernels(cudaStream_t stream) {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, edge_count_kernel);
@@ -297,6 +428,13 @@ void preload_automaton_kernels(cudaStream_t stream) {
     cudaFuncGetAttributes(&fa, place_keys_kernel);
     cudaFuncGetAttributes(&fa, remap_ids_kernel);
     cudaFuncGetAttributes(&fa, state_rows_kernel);
+    cudaFuncGetAttributes(&fa, liveness_init_kernel);
+    cudaFuncGetAttributes(&fa, liveness_step_kernel);
+    cudaFuncGetAttributes(&fa, adv1_edge_kernel);
+    cudaFuncGetAttributes(&fa, adv1_state_kernel);
+    cudaFuncGetAttributes(&fa, adv2_edge_kernel);
+    cudaFuncGetAttributes(&fa, adv2_state_kernel);
+    cudaFuncGetAttributes(&fa, post_alive_kernel);
     // the library kernels behind cub::DeviceScan: run one tiny scan
     int32_t *buf = nullptr;
     const size_t tmp = scan_temp_bytes(64);

@@ -246,6 +246,22 @@ void launch_place_keys(const int32_t *keys_in, int32_t *keys_out, long long tota
 void launch_state_rows(const int32_t *keys, long long n_states, int KW, int32_t *cset, int32_t *sig, int sm_count,
                        cudaStream_t stream);
 
+// post-processing fixpoints on the device (reference graphTraverse / adversarialTraverse / adversarialTraverse2): the host
+// iterates a step / sweep until *changed stays 0
+void launch_liveness_init(const int32_t *keys, long long ns, int KW, int n_sig, int n_flags, int root_final, uint8_t *fin,
+                          uint8_t *valid, int sm_count, cudaStream_t stream);
+void launch_liveness_step(const int32_t *src, const int32_t *dst, long long ne, uint8_t *valid, int32_t *changed, int sm_count,
+                          cudaStream_t stream);
+void launch_adv1_sweep(const int32_t *src, const int32_t *dst, const int32_t *label, long long ne, int V, int var, int lb,
+                       unsigned long long full, long long ns, unsigned long long *have, uint8_t *valid, int32_t *changed,
+                       int sm_count, cudaStream_t stream);
+void launch_adv2_sweep(const int32_t *src, const int32_t *dst, const int32_t *label, long long ne, int V, int op, int op_lb, int ava,
+                       int ava_lb, int A, unsigned long long full, long long ns, unsigned long long *cover, uint8_t *valid,
+                       int32_t *changed, int sm_count, cudaStream_t stream);
+void launch_post_alive(const int32_t *src, const int32_t *dst, const int32_t *label, long long ne, int V, int ava, int ava_lb, int A,
+                       unsigned long long full, const unsigned long long *cover, const uint8_t *valid, uint8_t *alive, int sm_count,
+                       cudaStream_t stream);
+
 uint32_t capmap_hash(int cid, const int32_t *vals, int n);
 
 // ---- exchange.cu: the per-wave meeting point of the ranks of a sharded solve, entirely on the devices ----------------

@@ -548,7 +548,7 @@ void parallel_copy(void *dst, const void *src, size_t n) {
 }
 
 struct PinnedStore : Store {    // single-rank automata finished on the device
-    HostBlock sig_vars, state_sig, state_cset, state_failed, edge_src, edge_dst, edge_label;
+    HostBlock sig_vars, state_sig, state_cset, state_failed, edge_src, edge_dst, edge_label, state_final, state_valid, edge_alive;
 };
 
 }  // namespace
@@ -568,7 +568,8 @@ struct stcsp_session {
     DBuf<SearchCtl> d_ctl;
     // finishing scratch (also handed to the search kernel, which finishes small automata itself)
     DBuf<int32_t> fb_deg, fb_first, fb_fill, fb_outdeg, fb_src, fb_dst, fb_label, fb_cset, fb_sig, fb_flags;
-    DBuf<uint8_t> fb_failed, fb_alive, fb_scan;
+    DBuf<uint8_t> fb_failed, fb_alive, fb_scan, fb_fin, fb_valid, fb_palive;
+    DBuf<unsigned long long> fb_cover;
     bool finish_in_kernel = false, finish_trim = true;     // set by stcsp_gpu_solve (single rank)
     bool time_expand = false;                               // expand launches of run_persistent's wide waves are timed
     static constexpr long long kWideWaveNodes = 32768;     // default of stcsp_options_t::wide_wave_nodes
@@ -630,7 +631,7 @@ struct stcsp_session {
         model.reset();     // (if it was not handed to the cache) its device blocks go back to the block cache
         fb_deg.release(); fb_first.release(); fb_fill.release(); fb_outdeg.release(); fb_src.release(); fb_dst.release();
         fb_label.release(); fb_cset.release(); fb_sig.release(); fb_flags.release(); fb_failed.release(); fb_alive.release();
-        fb_scan.release();
+        fb_scan.release(); fb_fin.release(); fb_valid.release(); fb_palive.release(); fb_cover.release();
         d_jobs.release(); d_ctl.release(); frontier[0].release(); frontier[1].release();
         leaves.release(); unresolved.release(); gathered.release(); table.release(); state_key.release();
         edge_src.release(); edge_dst.release(); edge_label.release(); counters.release(); d_offsets.release();
@@ -1654,6 +1655,100 @@ struct stcsp_session {
             t_launches++;
             CK(cudaGetLastError());
         }
+        // ---- post-processing fixpoints on the device, before anything is downloaded:
+        // liveness (reference graphTraverse, src/graph.cpp:357-418) for models with `until` -- models without make every state
+        // final, which the host knows without looking -- and the adversarial fixpoints -a / -z (src/graph.cpp:304-355, :247-302)
+        // when the caller asked for them (stcsp_options_t::adversarial).  They need the live edges alone, so an automaton
+        // finished by one CTA / inside the search kernel is compacted first if the fail rule killed edges.
+        const bool pre = prefinished && keys_p == state_key.p;
+        const bool liveness = model->sets.n_until() > 0 && ns > 0;
+        const int adv = ns > 0 ? (opt.adversarial & 3) : 0;
+        bool compacted_early = false;
+        int adver1 = -1, adver2 = -1;
+        if (adv && V < ((adv & 2) ? 7 : 6))
+            throw Failure(STCSP_ERR_INVALID, "adversarial modes use variables #5 and #6 (reference src/graph.cpp:275,329); the model has too few");
+        if (liveness || adv) {
+            if (pre || small) {
+                long long dead = prefinished_dead;
+                if (!pre) {
+                    CK(cudaMemcpyAsync(h_counters, counters.p + C_OUT, 8, cudaMemcpyDeviceToHost, stream));
+                    CK(cudaStreamSynchronize(stream));
+                    dead = (long long)(int32_t)h_counters[0];
+                }
+                if (dead > 0) {
+                    flags.reserve((size_t)ne + 1, 0, stream);
+                    launch_alive_to_int(alive.p, ne, flags.p, sm_count, stream);
+                    const size_t tmp2 = scan_temp_bytes(ne + 1);
+                    scan_tmp.reserve(tmp2 + 16, 0, stream);
+                    launch_exclusive_scan(scan_tmp.p, tmp2, flags.p, flags.p, ne, stream);
+                    launch_edge_compact(f_src, f_dst, f_label, alive.p, flags.p, ne, V, esrc_p, edst_p, elabel_p, sm_count, stream);
+                    f_src = esrc_p; f_dst = edst_p; f_label = elabel_p;
+                    n_final = ne - dead;
+                    t_launches += 3;
+                }
+                compacted_early = true;
+            }
+            fb_fin.reserve((size_t)ns + 1, 0, stream);
+            fb_valid.reserve((size_t)ns + 1, 0, stream);
+            fb_palive.reserve((size_t)n_final + 1, 0, stream);
+            unsigned long long *ctl = counters.p + C_OUT + 2;          // a scratch word the finishing kernels above do not use
+            auto converge = [&](auto &&sweep) {
+                for (;;) {
+                    CK(cudaMemsetAsync(ctl, 0, 8, stream));
+                    sweep();
+                    CK(cudaMemcpyAsync(h_counters + 2, ctl, 8, cudaMemcpyDeviceToHost, stream));
+                    CK(cudaStreamSynchronize(stream));
+                    if ((int32_t)h_counters[2] == 0) break;
+                }
+            };
+            auto root_valid = [&]() {
+                uint8_t v = 0;
+                CK(cudaMemcpyAsync(h_counters + 3, fb_valid.p, 1, cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                memcpy(&v, h_counters + 3, 1);
+                return (int)v;
+            };
+            // final = all until flags set; without `until` every state is final and valid to begin with
+            launch_liveness_init(keys_p, ns, KW, dm.n_sig, liveness ? model->sets.n_until_vars() : 0, liveness ? 0 : 1, fb_fin.p,
+                                 fb_valid.p, sm_count, stream);
+            t_launches++;
+            if (liveness)
+                converge([&] {
+                    launch_liveness_step(f_src, f_dst, n_final, fb_valid.p, (int32_t *)ctl, sm_count, stream);
+                    t_launches++;
+                });
+            const int32_t op_lb = adv ? model->sets.lb()[5] : 0, op_n = adv ? model->sets.width()[5] : 0;
+            const unsigned long long full = op_n >= 64 ? ~0ull : ((1ull << op_n) - 1);
+            if (adv & 1) {
+                fb_cover.reserve((size_t)ns + 1, 0, stream);
+                CK(cudaMemsetAsync(fb_cover.p, 0, ((size_t)ns + 1) * 8, stream));
+                converge([&] {
+                    launch_adv1_sweep(f_src, f_dst, f_label, n_final, V, 5, op_lb, full, ns, fb_cover.p, fb_valid.p, (int32_t *)ctl,
+                                      sm_count, stream);
+                    t_launches += 2;
+                });
+                adver1 = root_valid();
+            }
+            int ava_lb = 0, A = 0;
+            if (adv & 2) {
+                ava_lb = model->sets.lb()[6];
+                A = model->sets.width()[6];
+                fb_cover.reserve((size_t)ns * A + 1, 0, stream);
+                converge([&] {
+                    CK(cudaMemsetAsync(fb_cover.p, 0, (size_t)ns * A * 8, stream));
+                    launch_adv2_sweep(f_src, f_dst, f_label, n_final, V, 5, op_lb, 6, ava_lb, A, full, ns, fb_cover.p, fb_valid.p,
+                                      (int32_t *)ctl, sm_count, stream);
+                    t_launches += 2;
+                });
+                adver2 = root_valid();
+            }
+            // the reference keeps the vertex's edges when -z leaves the root invalid (src/graph.cpp:288: only `if (root valid)`)
+            const bool kill_by_cover = (adv & 2) && adver2 == 1;
+            launch_post_alive(f_src, f_dst, f_label, n_final, V, 6, ava_lb, A, full, kill_by_cover ? fb_cover.p : nullptr, fb_valid.p,
+                              fb_palive.p, sm_count, stream);
+            t_launches++;
+            CK(cudaGetLastError());
+        }
         float ms = 0;
         if (timing_open) {
             CK(cudaEventRecord(ev1, stream));
@@ -1668,6 +1763,14 @@ struct stcsp_session {
             st->edge_src.alloc((size_t)n_final * 4);
             st->edge_dst.alloc((size_t)n_final * 4);
             st->edge_label.alloc((size_t)n_final * V * 4);
+            if (liveness || adv) {
+                st->state_final.alloc((size_t)ns);
+                st->state_valid.alloc((size_t)ns);
+                st->edge_alive.alloc((size_t)n_final);
+                download(st->state_final, fb_fin.p, (size_t)ns);
+                download(st->state_valid, fb_valid.p, (size_t)ns);
+                if (n_final) download(st->edge_alive, fb_palive.p, (size_t)n_final);
+            }
             if (!model->sets.sig_vars().empty()) memcpy(st->sig_vars.p, model->sets.sig_vars().data(), model->sets.sig_vars().size() * 4);
             if (ns) {
                 if (SL) download(st->state_sig, rows_sig.p, (size_t)ns * SL * 4);
@@ -1679,10 +1782,10 @@ struct stcsp_session {
                 download(st->edge_dst, f_dst, (size_t)n_final * 4);
                 download(st->edge_label, f_label, (size_t)n_final * V * 4);
             }
-            if (small && !prefinished) CK(cudaMemcpyAsync(h_counters, counters.p + C_OUT, 8, cudaMemcpyDeviceToHost, stream));
+            if (small && !pre && !compacted_early) CK(cudaMemcpyAsync(h_counters, counters.p + C_OUT, 8, cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             if (timing_open) CK(cudaEventElapsedTime(&ms, ev0, ev1));
-            const long long dead = prefinished ? prefinished_dead : (small ? (long long)(int32_t)h_counters[0] : 0);
+            const long long dead = compacted_early ? 0 : pre ? prefinished_dead : (small ? (long long)(int32_t)h_counters[0] : 0);
             if (dead > 0) {
                 // rare (models with dead ends): compact the live edges into the append-order buffers and copy them again
                 flags.reserve((size_t)ne + 1, 0, stream);
@@ -1719,6 +1822,15 @@ struct stcsp_session {
         out->edge_src = (int32_t *)st->edge_src.p;
         out->edge_dst = (int32_t *)st->edge_dst.p;
         out->edge_label = (int32_t *)st->edge_label.p;
+        if (liveness || adv) {
+            out->state_final = (uint8_t *)st->state_final.p;
+            out->state_valid = (uint8_t *)st->state_valid.p;
+            out->edge_alive = (uint8_t *)st->edge_alive.p;
+            out->post_applied = STCSP_POST_LIVENESS | (adv & 1 ? STCSP_POST_ADVERSARIAL1 : 0) | (adv & 2 ? STCSP_POST_ADVERSARIAL2 : 0);
+            d2h += 2 * ns + n_final;
+        }
+        out->adver1 = adver1;
+        out->adver2 = adver2;
     }
 };
 

@@ -159,33 +159,7 @@ int stcsp_postprocess(const stcsp_problem_t *problem, const stcsp_automaton_t *a
     }
     for (int64_t s = 0; s < w.n; s++) w.first_edge[s + 1] += w.first_edge[s];
 
-    // ---- graphTraverse: final = all until flags set (the reference looks at numUntil flags, which
-    // counts distinct right-hand variables), valid = can reach a final state.
-    for (int64_t s = 1; s < w.n; s++) {
-        bool f = true;
-        for (int32_t c = a->n_sig_vars; f && c < a->n_sig_vars + a->n_until_vars; c++)
-            f = a->state_sig[s * a->sig_len + c] == 1;
-        w.fin[s] = w.valid[s] = f;
-    }
-    if (w.n > 0) w.fin[0] = w.valid[0] = a->root_final != 0;
-    bool all_valid = true;
-    for (int64_t s = 0; s < w.n && all_valid; s++) all_valid = w.valid[s] != 0;
-    // (a model without `until` -- every shipped and generated benchmark instance -- makes every state final: nothing to
-    //  propagate, and at partialorder_20 size the parent lists alone would be 63 M entries)
-    if (!all_valid) {
-        w.build_parents(false);
-        std::vector<int32_t> stack;
-        for (int64_t s = 1; s < w.n; s++)
-            if (w.valid[s]) stack.push_back((int32_t)s);
-        while (!stack.empty()) {
-            int32_t s = stack.back();
-            stack.pop_back();
-            for (int32_t p : w.parents[s])
-                if (!w.valid[p]) { w.valid[p] = 1; stack.push_back(p); }
-        }
-        w.drop_edges_into_invalid(true);
-    }
-
+    const int32_t want = STCSP_POST_LIVENESS | (adversarial1 ? STCSP_POST_ADVERSARIAL1 : 0) | (adversarial2 ? STCSP_POST_ADVERSARIAL2 : 0);
     out->adver1 = out->adver2 = -1;
     if (adversarial1 || adversarial2) {
         if (problem->n_vars < (adversarial2 ? 7 : 6)) {
@@ -193,14 +167,59 @@ int stcsp_postprocess(const stcsp_problem_t *problem, const stcsp_automaton_t *a
             return STCSP_ERR_INVALID;
         }
     }
-    if (adversarial1) {
+    const bool have_flags = a->post_applied && a->state_valid && a->state_final && (a->edge_alive || w.m == 0);
+    const int32_t applied = have_flags ? a->post_applied : 0;
+    if (applied & ~want) {
+        stcsp::set_error("the automaton was post-processed on the device with -a / -z flags this call does not ask for");
+        return STCSP_ERR_INVALID;
+    }
+    if ((applied & STCSP_POST_ADVERSARIAL2) && adversarial1 && !(applied & STCSP_POST_ADVERSARIAL1)) {
+        stcsp::set_error("the device ran -z without -a; -a cannot follow it (the reference runs -a first, src/solver.cpp:300-321)");
+        return STCSP_ERR_INVALID;
+    }
+    if (applied) {
+        // ---- the device ran these fixpoints (automaton.cu: liveness / -a / -z sweeps): take its flags; what it did not run
+        // (the caller asked stcsp_gpu_solve for less than it asks for here) follows on the host below
+        for (int64_t s = 0; s < w.n; s++) { w.valid[s] = a->state_valid[s]; w.fin[s] = a->state_final[s]; }
+        for (int64_t e = 0; e < w.m; e++) w.alive[e] = a->edge_alive[e];
+        if (applied & STCSP_POST_ADVERSARIAL1) out->adver1 = a->adver1;
+        if (applied & STCSP_POST_ADVERSARIAL2) out->adver2 = a->adver2;
+    } else {
+        // ---- graphTraverse: final = all until flags set (the reference looks at numUntil flags, which
+        // counts distinct right-hand variables), valid = can reach a final state.
+        for (int64_t s = 1; s < w.n; s++) {
+            bool f = true;
+            for (int32_t c = a->n_sig_vars; f && c < a->n_sig_vars + a->n_until_vars; c++)
+                f = a->state_sig[s * a->sig_len + c] == 1;
+            w.fin[s] = w.valid[s] = f;
+        }
+        if (w.n > 0) w.fin[0] = w.valid[0] = a->root_final != 0;
+        bool all_valid = true;
+        for (int64_t s = 0; s < w.n && all_valid; s++) all_valid = w.valid[s] != 0;
+        // (a model without `until` -- every shipped and generated benchmark instance -- makes every state final: nothing to
+        //  propagate, and at partialorder_20 size the parent lists alone would be 63 M entries)
+        if (!all_valid) {
+            w.build_parents(false);
+            std::vector<int32_t> stack;
+            for (int64_t s = 1; s < w.n; s++)
+                if (w.valid[s]) stack.push_back((int32_t)s);
+            while (!stack.empty()) {
+                int32_t s = stack.back();
+                stack.pop_back();
+                for (int32_t p : w.parents[s])
+                    if (!w.valid[p]) { w.valid[p] = 1; stack.push_back(p); }
+            }
+            w.drop_edges_into_invalid(true);
+        }
+    }
+    if (adversarial1 && !(applied & STCSP_POST_ADVERSARIAL1)) {
         w.build_parents(false);
         int32_t lb = problem->var_lb[5], ub = problem->var_ub[5];
         greatest_fixpoint(w, [&](int32_t s) { return check_all_values(w, s, 5, lb, ub); });
         w.drop_edges_into_invalid(false);
         out->adver1 = w.valid[0];
     }
-    if (adversarial2) {
+    if (adversarial2 && !(applied & STCSP_POST_ADVERSARIAL2)) {
         w.build_parents(true);
         int32_t alb = problem->var_lb[6], aub = problem->var_ub[6];
         int64_t opn = (int64_t)problem->var_ub[5] - problem->var_lb[5] + 1;

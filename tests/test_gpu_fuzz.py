@@ -41,6 +41,28 @@ def test_random_model_matches_oracle(seed):
     TALLY["compared"] += 1
 
 
+@pytest.mark.parametrize("seed", list(range(300, 700, 3)))
+def test_random_model_device_postprocessing(seed):
+    """-a / -z / both on the device (stcsp_options_t::adversarial) against the host fixpoints over the oracle's automaton."""
+    text = random_model(seed)
+    try:
+        model = binding.Model(text)
+    except binding.StcspError:
+        pytest.skip("rejected by the front end")
+    if model.problem.contents.n_vars < 7:
+        pytest.skip("adversarial modes need variables #5 and #6")
+    oracle_automaton, _ = _oracle.solve(model, 2.0)
+    if oracle_automaton is None:
+        pytest.skip("oracle needs more than 2 s")
+    for a, z in ((1, 0), (0, 1), (1, 1)):
+        want = binding.Solution(model, oracle_automaton, a, z)
+        automaton = binding.solve(model, binding.default_options(adversarial=a | (z << 1)))
+        assert automaton.post_applied == 1 | (a << 1) | (z << 2)
+        got = binding.Solution(model, automaton, a, z)
+        assert (got.adver1, got.adver2) == (want.adver1, want.adver2), (seed, a, z)
+        assert got.canonical_text() == want.canonical_text(), "seed %d -a %d -z %d\n%s" % (seed, a, z, text)
+
+
 def test_zz_fuzz_skips_are_counted():
     """Runs after the seeds (file order): how many models were really compared.  A model the GPU path rejects as
     unsupported is a gap against the reference (which accepts any int domain), so it is counted, printed and bounded."""

@@ -24,10 +24,37 @@ CASES = sorted(k for k, g in GOLDENS.items() if "sha256" in g and g.get("edges",
 
 
 def run_gpu(text, flags=(), **opts):
+    """Like `bin/stcsp`: the -a / -z fixpoints (and liveness, for models with `until`) run on the device."""
     k = next((int(f[2:]) for f in flags if f.startswith("-k")), 2)
     model = binding.Model(text, k)
+    adversarial = ("-a" in flags) | (("-z" in flags) << 1)
+    if adversarial:
+        opts = dict(opts, adversarial=adversarial)
     automaton = binding.solve(model, binding.default_options(**opts) if opts else None)
+    if adversarial:
+        assert automaton.post_applied == 1 | (adversarial << 1)
     return model, automaton, binding.Solution(model, automaton, "-a" in flags, "-z" in flags)
+
+
+POST_CASES = [k for k in CASES if {"-a", "-z"} & set(golden_flags(GOLDENS[k])) or "until" in golden_text(GOLDENS[k])]
+
+
+@pytest.mark.parametrize("key", POST_CASES)
+def test_device_postprocessing_equals_host_postprocessing(key):
+    """Liveness and the -a / -z fixpoints as device sweeps (automaton.cu) against the host restatement of reference
+    src/graph.cpp:247-418 (postprocess.cpp) on the same automaton: same flags, same surviving edges, same canonical text."""
+    g = GOLDENS[key]
+    flags = golden_flags(g)
+    model, automaton, sol = run_gpu(golden_text(g), flags)
+    plain = binding.solve(model)                         # liveness alone on the device (until) or nothing: the rest on the host
+    layered = binding.Solution(model, plain, "-a" in flags, "-z" in flags)
+    had = plain.post_applied
+    plain.c.post_applied = 0                             # nothing taken from the device
+    host = binding.Solution(model, plain, "-a" in flags, "-z" in flags)
+    assert "until" not in golden_text(g) or had == 1
+    assert sol.canonical_text() == host.canonical_text() == layered.canonical_text()
+    assert (sol.adver1, sol.adver2) == (host.adver1, host.adver2) == (layered.adver1, layered.adver2)
+    assert sol.canonical_sha256() == g["sha256"]
 
 
 @pytest.mark.parametrize("key", CASES)
