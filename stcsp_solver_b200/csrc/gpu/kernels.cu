@@ -704,7 +704,7 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                 atomicAnd(&wm.dirty[q >> 5], ~bit);
                 __threadfence_block();      // the domains are read AFTER the bit is cleared: a wake that lands in between re-arms
                                             // this propagator instead of being erased while it still sees the old domain
-                const int r = scalar_revise(M, S, q, ctx.dom, wm.dirty, ctx.expire, my_tuples, CTA ? kScalarWalkCta : kScalarWalk);
+                const int r = scalar_revise(M, S, q, ctx.dom, wm.dirty, ctx.expire, my_tuples, CTA ? kScalarWalkCta : M.scalar_walk);
                 st_rev++;
                 if (r == SR_FAIL) myfail = true;
                 else if (r == SR_HEAVY) atomicOr(&wm.hvy[q >> 5], bit);
@@ -754,6 +754,7 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
             __syncwarp();
             if (lane == 0) wm.dirty[q >> 5] &= ~(1u << (q & 31));       // idempotent: its own wake is void
             __syncwarp();
+            dbg_stamp(ctx.dbg, ctx.dbg_cap, 30);           // one 32-lane revision done (warp per node)
             st_rev += lane == 0;
             if (!ok) return true;
         } else {
@@ -858,6 +859,11 @@ __device__ int stage_set(const DevModel &M, unsigned char *smem, int cid, int *r
 // CTA = true : one CTA per search node, its warps revise different dirty propagators of the node concurrently
 //              (narrow waves: fewer nodes than resident CTAs, the latency of one node is the wave's duration).
 // CTA = false: one warp per search node (wide waves: throughput).
+// Leaf found inside expand (search_kernel on narrow waves): route it and merge it into the automaton right here.  Out of line:
+// it is off the propagation path and must not cost the expand bodies registers.  Defined behind route_leaf / ingest_leaf.
+__device__ __noinline__ void fused_leaf(const DevModel &M, const RouteArgs &R, const IngestArgs &I, int32_t *rec, long long li,
+                                        int lane, unsigned long long *st_dom);
+
 template <bool CTA>
 __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs &P, unsigned char *smem, int *resident = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -870,11 +876,12 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
     const int gw = CTA ? warp : 0;                      // this warp's index among them
     const int gtid = CTA ? threadIdx.x : lane, gthreads = gwarps * 32;
     unsigned st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;    // per launch and thread
+    unsigned long long st_dom = 0;                      // fused leaves that hit an existing state
     // stage the constraint set of this CTA's first node (waves are almost always homogeneous)
     const long long probe = CTA ? (long long)blockIdx.x : (long long)blockIdx.x * kExpandWarps;
     const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1, resident);
     const DevModel &Ms = *reinterpret_cast<const DevModel *>(stage_base(smem, Mg));
-    if (CTA && blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(P.dbg, P.dbg_cap, 0);     // wave entered, set staged
+    if (blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(P.dbg, P.dbg_cap, 0);     // wave entered, set staged
 
     for (long long ni = first; ni < n_in; ni += step) {
         const int32_t *src = P.in_nodes + ni * NW;
@@ -886,7 +893,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
         const int cid = wm.nodew[1], bvar = wm.nodew[3];
         const DevModel &M = cid == staged ? Ms : Mg;    // metadata from shared memory when this node's set is the staged one
         const DevSet S = Mg.sets[cid];
-        unsigned long long *dbg = (CTA && blockIdx.x == 0 && threadIdx.x == 0) ? P.dbg : nullptr;
+        unsigned long long *dbg = (blockIdx.x == 0 && threadIdx.x == 0) ? P.dbg : nullptr;    // (warp mode: warp 0's nodes)
         NodeCtx ctx{M, S, wm, reinterpret_cast<u64 *>(wm.nodew + 4), lane, wm.nodew[2], 0ull, dbg, P.dbg_cap};
         dbg_stamp(dbg, P.dbg_cap, 1);                   // node loaded
         u64 *dom = ctx.dom;
@@ -924,6 +931,11 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
             int32_t *rec = P.leaves + li * M.rec_words;
             if (lane < 4) rec[lane] = lane == 3 ? 0 : wm.nodew[lane];
             for (int v = lane; v < V; v += 32) rec[4 + v] = M.lb[v] + __ffsll((long long)dom[v * k]) - 1;
+            if (P.fuse_route) {
+                __syncwarp();                           // the record is complete for every lane of this warp
+                fused_leaf(Mg, *P.fuse_route, *P.fuse_ingest, rec, (long long)li, lane, &st_dom);
+                dbg_stamp(dbg, P.dbg_cap, 5);           // leaf routed and merged
+            }
         } else {
             // branch: on the first unbound variable, and -- while the wave is narrow enough that every child still gets a
             // warp of its own (P.fan, set per wave) -- on the next one or two as well
@@ -1020,6 +1032,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
         if (st_tuples) atomicAdd(&P.counters[C_TUPLES], (unsigned long long)st_tuples);
         if (st_rev) atomicAdd(&P.counters[C_REVISIONS], (unsigned long long)st_rev);
     }
+    if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
 }
 
 // ---- wide waves: FOUR search nodes per warp, eight lanes each ----------------------------------------------------
@@ -1426,7 +1439,7 @@ __device__ __forceinline__ void ingest_leaf(const DevModel &M, const IngestArgs 
     // both cursors at once: two atomics in flight instead of two round trips one after the other
     unsigned long long o = 0, e = 0;
     if (lane == 0) {
-        if (is_new) o = (unsigned long long)P.out_base + atomicAdd(&P.counters[C_NEW], 1ull);
+        if (is_new) o = (unsigned long long)P.out_base + atomicAdd(&P.counters[P.fused ? C_OUT : C_NEW], 1ull);
         e = atomicAdd(&P.totals[C_EDGES], 1ull);
     }
     o = __shfl_sync(0xffffffffu, o, 0);
@@ -1505,6 +1518,11 @@ __device__ __forceinline__ void leaf_body(const DevModel &M, const RouteArgs &R,
     if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
 }
 
+
+__device__ __noinline__ void fused_leaf(const DevModel &M, const RouteArgs &R, const IngestArgs &I, int32_t *rec, long long li,
+                                        int lane, unsigned long long *st_dom) {
+    if (route_leaf(M, R, rec, li, lane)) ingest_leaf(M, I, rec, lane, *st_dom);
+}
 
 // ---- wide waves: route + merge FOUR leaves per warp, eight lanes each ---------------------------------------------
 // One leaf is a chain of dependent global round trips (table slot, state key, edge cursor); with one leaf per warp the
@@ -1734,6 +1752,9 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
     __shared__ long long cs[S_COUNT];
     __shared__ ExpandArgs ea;           // the wave's arguments (launch parameters in the stand-alone kernels)
     __shared__ int s_status, s_set;
+    __shared__ int s_fuse;              // this wave's leaves are routed and merged inside expand (no leaf phase)
+    __shared__ RouteArgs s_ra;          // ... with these arguments
+    __shared__ IngestArgs s_ia;
     __shared__ int s_resident;          // constraint set whose metadata this CTA holds in shared memory (kept across waves)
     const bool controller = blockIdx.x == 0 && threadIdx.x == 0;    // the one thread that reports to the host
     auto stamp = [&](int k) {
@@ -1790,10 +1811,14 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
         static_assert(C_COUNT <= 32, "one warp reads all counters");
         if (ln != 0) return;
         if (after_expand) {
+            // (a fused wave has merged its leaves already; its frontier cannot overflow -- see the guard at wave start -- and if
+            //  it did, re-running the wave would duplicate edges: the host is told that a pool overflowed)
+            const long long pend = s_fuse ? 0 : v_leaves;
+            if (s_fuse && (v_ovf & 1)) cs[S_OVERFLOW] |= 64;
             s_ovf = (int)(v_ovf & 1);
-            s_leaves = v_leaves;
+            s_leaves = pend;
             s_out = v_out;
-            if ((v_ovf & 1) || v_out + v_leaves > A.out_cap || v_leaves > 0) return;    // leaving, or the leaf phase comes first
+            if ((v_ovf & 1) || v_out + pend > A.out_cap || pend > 0) return;    // leaving, or the leaf phase comes first
         }
         s_status = v_unres != 0 ? SEARCH_RESOLVE : SEARCH_RUN;
         if (v_unres != 0) return;               // the host finishes this wave and counts it
@@ -1832,6 +1857,47 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             ea.counters = A.counters + set * kCounterStride;
             ea.dbg = A.trace ? A.trace + 5 * A.trace_cap : nullptr;     // block 0's timeline follows the per-wave stamps
             ea.dbg_cap = A.trace ? 4096 : 0;
+            // Narrow waves (a CTA or a warp per node): the warp that finds a leaf routes and merges it at once, while the
+            // other nodes of the wave are still being propagated -- one grid barrier per wave, and the leaf's chain of
+            // dependent L2 round trips is hidden behind the slowest node.  Only when the wave cannot overflow the output
+            // frontier (a node makes at most max(64, fan) children or one new state; a fused wave cannot be run again) and
+            // never on the quad-mode waves, whose leaf phase overlaps four chains per warp anyway.
+            const int wmode = pick_expand_mode(M, c_n_in, gridDim.x);
+            const long long per_node = ea.fan > 64 ? ea.fan : 64;
+            const int fuse = st == SEARCH_RUN && A.fuse_leaves && wmode != EXPAND_QUAD && c_n_in * per_node <= A.out_cap;
+            s_fuse = fuse;
+            ea.fuse_route = nullptr;
+            ea.fuse_ingest = nullptr;
+            if (fuse) {
+                s_ra.leaves = A.leaves;
+                s_ra.list = nullptr;
+                s_ra.count = 0;
+                s_ra.capmap = A.capmap;
+                s_ra.capvals = A.capvals;
+                s_ra.capmap_mask = A.capmap_mask;
+                s_ra.unresolved = A.unresolved;
+                s_ra.unresolved_cap = A.unresolved_cap;
+                s_ra.counters = ea.counters;
+                s_ia.records = A.leaves;
+                s_ia.count = 0;
+                s_ia.table = A.table;
+                s_ia.table_mask = A.table_mask;
+                s_ia.state_key = A.state_key;
+                s_ia.state_cap = A.state_cap;
+                s_ia.edge_src = A.edge_src;
+                s_ia.edge_dst = A.edge_dst;
+                s_ia.edge_label = A.edge_label;
+                s_ia.edge_cap = A.edge_cap;
+                s_ia.out_nodes = ea.out_nodes;
+                s_ia.out_base = 0;
+                s_ia.out_cap = A.out_cap;
+                s_ia.counters = ea.counters;
+                s_ia.totals = A.counters;
+                s_ia.n_segs = 0;
+                s_ia.fused = 1;
+                ea.fuse_route = &s_ra;
+                ea.fuse_ingest = &s_ia;
+            }
         }
         __syncthreads();
         if (s_status == SEARCH_DONE) {
@@ -1972,6 +2038,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             ia.counters = ea.counters;
             ia.totals = A.counters;
             ia.n_segs = 0;
+            ia.fused = 0;
             if (n_leaves >= 4ll * kExpandWarps * gridDim.x || M.force_mode == EXPAND_QUAD + 1)
                 leaf_body_quad<true, true>(M, ra, ia, n_leaves);    // four leaves per warp
             else leaf_body(M, ra, ia, n_leaves);            // route + ingest in one pass
@@ -1979,13 +2046,13 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             stamp(2);
             if (threadIdx.x < 32) wave_counters(cnt, false);
             __syncthreads();
-            if (s_status == SEARCH_RESOLVE) {
-                // leaves with an unseen constraint-set transition are still pending: the host resolves and ingests them
-                leave(SEARCH_RESOLVE, true);
-                return;
-            }
         } else {
             stamp(2);
+        }
+        if (s_status == SEARCH_RESOLVE) {
+            // leaves with an unseen constraint-set transition are still pending: the host resolves and ingests them
+            leave(SEARCH_RESOLVE, true);
+            return;
         }
         stamp(3);
         stamp(4);

@@ -54,6 +54,8 @@ struct DevModel {
     int32_t multi_branch;       // 1: narrow waves branch on up to three variables at once (branch_fan)
     int32_t fan_warps;          // children a narrow wave may create in total (2 x SM count), see branch_fan
     int32_t dbg_flags;          // experiments (environment STCSP_DBG_FLAGS); 0 in production
+    int32_t scalar_walk;        // longest relation-table walk (prefix tuples) ONE lane takes on in warp-per-node mode; longer
+                                // walks go to the 32-lane revision
     long long enum_now, enum_ahead;
     const int32_t *lb, *width, *sig_vars;
     const DevSet *sets;
@@ -87,6 +89,10 @@ struct ExpandArgs {
     unsigned long long *counters;
     unsigned long long *dbg;    // optional timeline of block 0 (CTA mode): dbg[0] = entries used, then (tag, %globaltimer) pairs
     int dbg_cap;
+    // search_kernel, narrow waves: a node that turns out to be a leaf is routed and merged into the automaton right away by
+    // the warp that found it (no leaf phase, no second grid barrier); null in the stand-alone expand kernels
+    const struct RouteArgs *fuse_route;
+    const struct IngestArgs *fuse_ingest;
 };
 
 struct RouteArgs {
@@ -119,6 +125,8 @@ struct IngestArgs {
     // segments, and segment q lies in the OUTBOX OF RANK q -- peer memory, read over NVLink by the ingesting warps themselves
     // (the exchange and the merge are one kernel; nothing is staged in an inbox).
     int32_t n_segs;
+    int32_t fused;                  // 1: called from inside expand (search_kernel, narrow waves): the first nodes of new states
+                                    // are appended through expand's own cursor C_OUT (out_base = 0) instead of C_NEW
     const int32_t *seg_base[kMaxWorld];
     long long seg_count[kMaxWorld];
 };
@@ -169,6 +177,7 @@ struct SearchArgs {
     long long state_cap;
     int32_t *edge_src, *edge_dst, *edge_label;
     long long edge_cap;
+    int32_t fuse_leaves;                // 1: narrow waves route and merge their leaves inside expand (see search_kernel)
     long long max_frontier;             // > 0: yield to the host when a wave is wider (it gives up, or runs the wave step-wise)
     FinishArgs fin;
     unsigned long long *trace;          // optional: 5 %globaltimer stamps per wave (start, expanded, routed, ingested, end)

@@ -647,6 +647,7 @@ struct stcsp_session {
     }
 
     void upload_model() {
+        const double t_up0 = now_s();
         upload(model->d_lb, model->sets.lb());
         upload(model->d_width, model->sets.width());
         upload(model->d_sigvars, model->sets.sig_vars());
@@ -663,6 +664,7 @@ struct stcsp_session {
         upload(model->d_arr_off, model->sets.arr_off);
         upload(model->d_arr_val, model->sets.arr_val);
         CK(cudaStreamSynchronize(stream));      // the host vectors may be reallocated by the next set
+        const double t_up = now_s();
         refresh_model();
         // fill the relation tables of constraints seen for the first time
         if (!model->sets.table_jobs.empty()) {
@@ -678,6 +680,9 @@ struct stcsp_session {
             CK(cudaStreamSynchronize(stream));
             t_launches++;
         }
+        if (opt.verbosity > 0)
+            fprintf(stderr, "[stcsp r%d] upload_model: pools + copies %.2f ms, relation tables (%lld words) %.2f ms\n", rank,
+                    (t_up - t_up0) * 1e3, (long long)model->sets.table_words, (now_s() - t_up) * 1e3);
         model->sets.table_jobs.clear();
         model->tables_built = model->sets.table_words;
         model->sets.clear_dirty();
@@ -715,6 +720,11 @@ struct stcsp_session {
         {
             static const int flags = getenv("STCSP_DBG_FLAGS") ? atoi(getenv("STCSP_DBG_FLAGS")) : 0;
             dm.dbg_flags = flags;
+        }
+        dm.scalar_walk = 192;
+        {
+            static const int walk_override = getenv("STCSP_SCALAR_WALK") ? atoi(getenv("STCSP_SCALAR_WALK")) : 0;     // tuning experiments
+            if (walk_override > 0) dm.scalar_walk = walk_override;
         }
         if (dm.V >= (1 << 10) - 1) dm.multi_branch = 0;        // the node header packs variable indices in ten bits
         // four node blocks per warp (quad mode for wide waves) when three CTAs still fit an SM
@@ -814,8 +824,10 @@ struct stcsp_session {
         } catch (const std::runtime_error &ex) {
             throw Failure(STCSP_ERR_INVALID, ex.what());
         }
+        const double t_compiled = now_s();
         if (!model->uploaded || model->sets.dirty()) upload_model();
         else refresh_model();
+        const double t_uploaded = now_s();
         counters.reserve(kCounterSets * kCounterStride, 0, stream);
         CK(cudaMemsetAsync(counters.p, 0, kCounterSets * kCounterStride * sizeof(unsigned long long), stream));
         h_counters = pinned_cache().acquire();       // C_COUNT counters + room for the search control block
@@ -861,6 +873,9 @@ struct stcsp_session {
             n_in = 1;
         }
         ensure_table(std::max<long long>(std::max<long long>(n_states, 1), model->hint_table / 2));
+        if (opt.verbosity > 0)
+            fprintf(stderr, "[stcsp r%d] init: context + model lookup / compile %.2f ms, upload + relation tables %.2f ms, pools + root %.2f ms\n",
+                    rank, (t_compiled - t_create) * 1e3, (t_uploaded - t_compiled) * 1e3, (now_s() - t_uploaded) * 1e3);
     }
 
     // Pools big enough for a wave over `nin` input nodes (see the SEARCH_GROW test in search_kernel).
@@ -906,6 +921,7 @@ struct stcsp_session {
             sa.edge_dst = edge_dst.p;
             sa.edge_label = edge_label.p;
             sa.edge_cap = (long long)std::min(edge_src.cap, edge_label.cap / (size_t)V);
+            sa.fuse_leaves = (dm.dbg_flags & 1) ? 0 : 1;        // STCSP_DBG_FLAGS=1: the separate leaf phase on every wave (A/B timing)
             const long long wide = opt.wide_wave_nodes < 0 ? 0 : opt.wide_wave_nodes > 0 ? opt.wide_wave_nodes : kWideWaveNodes;
             sa.max_frontier = opt.max_frontier_nodes > 0 && (wide == 0 || opt.max_frontier_nodes < wide) ? opt.max_frontier_nodes : wide;
             // An instance whose waves stay narrow gets one CTA per SM: with a third of the CTAs the grid barrier is cheaper
