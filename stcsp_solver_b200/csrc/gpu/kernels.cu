@@ -1778,15 +1778,21 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
         if (blockIdx.x != 0) return;
         if (mid_wave && s_set != 0 && threadIdx.x >= C_OUT && threadIdx.x < C_COUNT)
             A.counters[threadIdx.x] = A.counters[s_set * kCounterStride + threadIdx.x];
+        // host mirror of counter set 0 (the threads that may just have copied a word read that word back: program order)
+        if (A.h_counters != nullptr && threadIdx.x < C_COUNT) A.h_counters[threadIdx.x] = tot[threadIdx.x];
         if (threadIdx.x == 0) {
-            ctl->status = st;
-            ctl->n_in = cs[S_N_IN];
-            ctl->cur = (int)cs[S_CUR];
-            ctl->t_nodes = cs[S_NODES]; ctl->t_fails = cs[S_FAILS]; ctl->t_tuples = cs[S_TUPLES]; ctl->t_revisions = cs[S_REV];
-            ctl->t_dominance = cs[S_DOM]; ctl->t_leaves = cs[S_LEAVES]; ctl->t_waves = cs[S_WAVES];
-            ctl->waves_left = cs[S_WAVES_LEFT];
-            ctl->overflow = (int)cs[S_OVERFLOW];
-            ctl->t_max_in = cs[S_MAX_IN];
+            SearchCtl c;
+            c.status = st;
+            c.n_in = cs[S_N_IN];
+            c.cur = (int)cs[S_CUR];
+            c.t_nodes = cs[S_NODES]; c.t_fails = cs[S_FAILS]; c.t_tuples = cs[S_TUPLES]; c.t_revisions = cs[S_REV];
+            c.t_dominance = cs[S_DOM]; c.t_leaves = cs[S_LEAVES]; c.t_waves = cs[S_WAVES];
+            c.waves_left = cs[S_WAVES_LEFT];
+            c.overflow = (int)cs[S_OVERFLOW];
+            c.t_max_in = cs[S_MAX_IN];
+            c.finished = 0; c.dead_edges = 0; c.changed = 0; c.pushed = 0; c.pad = 0;
+            *const_cast<SearchCtl *>(ctl) = c;
+            if (A.h_ctl != nullptr) *A.h_ctl = c;
         }
     };
     // Warp 0: one parallel load of the wave's counters (frozen while it runs).  after_expand: publish expand's results
@@ -1978,7 +1984,23 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
                 }
                 grid.sync();
             }
-            if (gtid == 0) ctl->finished = 1;
+            // ---- push: no edge died, so the grouped arrays are final -- write them into the host's pinned buffers
+            const bool push = F.h_src != nullptr && ctl->dead_edges == 0 && ns <= F.h_cap_states && ne <= F.h_cap_edges;
+            if (push) {
+                const long long nsig = ns * (KW - 1);
+                for (long long i = gtid; i < ns; i += gsize) { F.h_cset[i] = F.rows_cset[i]; F.h_failed[i] = F.failed[i]; }
+                for (long long i = gtid; i < nsig; i += gsize) F.h_sig[i] = F.rows_sig[i];
+                for (long long e = gtid; e < ne; e += gsize) { F.h_src[e] = F.s_src[e]; F.h_dst[e] = F.s_dst[e]; }
+                for (long long i = gtid; i < ne * V; i += gsize) F.h_label[i] = F.s_label[i];
+            }
+            if (gtid == 0) {
+                ctl->finished = 1;
+                if (A.h_ctl != nullptr) {
+                    A.h_ctl->dead_edges = ctl->dead_edges;
+                    A.h_ctl->finished = 1;
+                    A.h_ctl->pushed = push ? 1 : 0;
+                }
+            }
             return;
         }
         if (s_status != SEARCH_RUN) { leave(s_status, false); return; }

@@ -149,6 +149,7 @@ struct SearchCtl {
     long long t_nodes, t_fails, t_tuples, t_revisions, t_dominance, t_leaves, t_waves;
     long long t_max_in;     // widest wave this launch ran
     int dead_edges, changed;
+    int pushed, pad;        // 1: the finished automaton was also written into the host's pinned buffers (FinishArgs::h_*)
 };
 // Scratch for finishing a small automaton inside the search kernel (all null / 0: the host launches the finishing kernels).
 struct FinishArgs {
@@ -158,10 +159,18 @@ struct FinishArgs {
     int32_t *rows_cset, *rows_sig;              // state rows
     long long cap_states, cap_edges;
     int do_trim;
+    // PUSH (optional, null = off): pinned host buffers, mapped into the device's address space.  A small automaton whose
+    // fail rule killed no edge is written there by the kernel itself, so the host needs ONE synchronisation per solve and
+    // no device-to-host copy at all (a copy of a few KB costs 5-8 us of stream time each, and there were nine of them).
+    int32_t *h_cset, *h_sig, *h_src, *h_dst, *h_label;
+    uint8_t *h_failed;
+    long long h_cap_states, h_cap_edges;
 };
 struct SearchArgs {
     SearchCtl *ctl;
     unsigned long long *counters;
+    SearchCtl *h_ctl;                   // optional: pinned host mirrors of ctl / counter set 0 (mapped); the kernel writes them
+    unsigned long long *h_counters;     // when it leaves, so the host reads them after one stream synchronisation
     int32_t *frontier[2];
     long long out_cap;                  // capacity of EACH frontier buffer, in nodes
     int32_t *leaves;

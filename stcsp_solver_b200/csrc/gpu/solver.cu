@@ -267,6 +267,7 @@ struct ModelState {
     // pool sizes the last solve of this model ended with: the next one starts there and never has to grow
     long long hint_frontier = 0, hint_states = 0, hint_edges = 0, hint_table = 0;
     long long hint_max_wave = 0;        // widest wave of the last solve (0: unknown)
+    long long hint_out_states = 0, hint_out_edges = 0;     // the automaton the last solve returned (0: unknown)
 };
 
 struct ModelCache {
@@ -453,7 +454,7 @@ struct HostCache {
             populate(0, bytes);
         }
         kind = PINNED;
-        if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        if (cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess) {
             cudaGetLastError();
             kind = PAGEABLE;
         }
@@ -581,6 +582,12 @@ struct stcsp_session {
                                     // unreachable as long as every path pre-reserves n_states + n, fatal for the session if not
     bool prefinished = false;       // the search kernel already grouped + trimmed (fb_* hold the result)
     long long prefinished_dead = 0;
+    // PUSH (FinishArgs::h_*): pinned output buffers handed to the search kernel, which writes a small automaton into them
+    unsigned long long *host_mirror = nullptr;     // device-side address of h_counters (mapped pinned memory), or null
+    PinnedStore *push_store = nullptr;
+    long long push_cap_states = 0, push_cap_edges = 0;
+    bool pushed = false;            // ... and did (no device-to-host copy is needed)
+    long long out_states = 0, out_edges = 0;        // size of the automaton this solve returned
     SearchCtl *h_ctl = nullptr;     // pinned, behind h_counters
     int search_grid = 0;
     // search pools
@@ -603,6 +610,7 @@ struct stcsp_session {
 
     ~stcsp_session() {
         if (stream) cudaStreamSynchronize(stream);
+        delete push_store;
         if (h_counters) pinned_cache().give_back(h_counters);
         // Only a solve that ran to the end hands its model back: after a failure (an exception between the host and the
         // device update of the transition map, a timeout, a CUDA error) the host and device copies may disagree.
@@ -613,6 +621,8 @@ struct stcsp_session {
             model->hint_edges = (long long)edge_src.cap;
             model->hint_table = table_size;
             if (search_complete) model->hint_max_wave = max_wave;
+            model->hint_out_states = out_states;
+            model->hint_out_edges = out_edges;
             model_cache().put(cache_key, std::move(model));       // the compiled model stays resident for the next solve
         }
         release_all();
@@ -831,6 +841,12 @@ struct stcsp_session {
         counters.reserve(kCounterSets * kCounterStride, 0, stream);
         CK(cudaMemsetAsync(counters.p, 0, kCounterSets * kCounterStride * sizeof(unsigned long long), stream));
         h_counters = pinned_cache().acquire();       // C_COUNT counters + room for the search control block
+        {
+            void *d = nullptr;
+            static const bool no_push = getenv("STCSP_NO_PUSH") != nullptr;       // A/B timing
+            if (!no_push && cudaHostGetDevicePointer(&d, h_counters, 0) == cudaSuccess) host_mirror = (unsigned long long *)d;
+            else cudaGetLastError();
+        }
         d_offsets.reserve(2 * kMaxWorld, 0, stream);
 
         const int NW = dm.node_words, KW = dm.key_words;
@@ -953,6 +969,43 @@ struct stcsp_session {
                 sa.fin.rows_cset = fb_cset.p; sa.fin.rows_sig = fb_sig.p;
                 sa.fin.cap_states = cs; sa.fin.cap_edges = ce;
                 sa.fin.do_trim = finish_trim ? 1 : 0;
+                // PUSH: the last solve of this model returned a small automaton -- pinned output buffers of that size (plus a
+                // margin) go to the kernel, which writes the result into them itself (see FinishArgs)
+                const long long hs = model->hint_out_states, he = model->hint_out_edges;
+                if (host_mirror && hs > 0 && he * (V + 2) * 4 + hs * (SLm + 2) * 4 <= (4ll << 20)) {
+                    if (!push_store) {
+                        push_cap_states = hs + hs / 8 + 16;
+                        push_cap_edges = he + he / 8 + 16;
+                        auto *st = new PinnedStore();
+                        try {
+                            st->sig_vars.alloc(model->sets.sig_vars().size() * 4);
+                            st->state_sig.alloc((size_t)push_cap_states * SLm * 4);
+                            st->state_cset.alloc((size_t)push_cap_states * 4);
+                            st->state_failed.alloc((size_t)push_cap_states);
+                            st->edge_src.alloc((size_t)push_cap_edges * 4);
+                            st->edge_dst.alloc((size_t)push_cap_edges * 4);
+                            st->edge_label.alloc((size_t)push_cap_edges * V * 4);
+                        } catch (...) { delete st; throw; }
+                        const bool all_pinned = st->state_sig.pinned() && st->state_cset.pinned() && st->state_failed.pinned() &&
+                                                st->edge_src.pinned() && st->edge_dst.pinned() && st->edge_label.pinned();
+                        if (all_pinned) push_store = st; else delete st;
+                    }
+                    if (push_store) {
+                        auto dev = [&](void *h) { void *d = nullptr; return cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess ? d : nullptr; };
+                        sa.fin.h_sig = (int32_t *)dev(push_store->state_sig.p);
+                        sa.fin.h_cset = (int32_t *)dev(push_store->state_cset.p);
+                        sa.fin.h_failed = (uint8_t *)dev(push_store->state_failed.p);
+                        sa.fin.h_src = (int32_t *)dev(push_store->edge_src.p);
+                        sa.fin.h_dst = (int32_t *)dev(push_store->edge_dst.p);
+                        sa.fin.h_label = (int32_t *)dev(push_store->edge_label.p);
+                        sa.fin.h_cap_states = push_cap_states;
+                        sa.fin.h_cap_edges = push_cap_edges;
+                        if (!sa.fin.h_sig || !sa.fin.h_cset || !sa.fin.h_failed || !sa.fin.h_src || !sa.fin.h_dst || !sa.fin.h_label) {
+                            cudaGetLastError();
+                            sa.fin.h_src = nullptr;        // no mapping: the classic downloads
+                        }
+                    }
+                }
             }
             DBuf<unsigned long long> trace;
             const long long trace_waves = 256;
@@ -970,11 +1023,19 @@ struct stcsp_session {
             CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof *h_ctl, cudaMemcpyHostToDevice, stream));
             zero_wave_counters();
             const int grid = narrow ? std::min(search_grid, sm_count) : search_grid;
+            sa.h_ctl = host_mirror ? reinterpret_cast<SearchCtl *>(host_mirror + C_COUNT) : nullptr;
+            sa.h_counters = host_mirror;
             CK(cudaEventRecord(evk0, stream));
             CK(launch_search(dm, sa, grid, sm_count, stream));
             CK(cudaEventRecord(evk1, stream));
-            CK(cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof *h_ctl, cudaMemcpyDeviceToHost, stream));
-            read_counters();
+            if (host_mirror) {
+                // the kernel wrote its control block and counter set 0 into the pinned block itself: one synchronisation
+                CK(cudaStreamSynchronize(stream));
+                d2h += C_COUNT * 8;
+            } else {
+                CK(cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof *h_ctl, cudaMemcpyDeviceToHost, stream));
+                read_counters();
+            }
             {
                 float kms = 0;
                 CK(cudaEventElapsedTime(&kms, evk0, evk1));
@@ -1032,6 +1093,7 @@ struct stcsp_session {
                     n_in = 0;
                     prefinished = h_ctl->finished != 0;
                     prefinished_dead = h_ctl->dead_edges;
+                    pushed = prefinished && h_ctl->pushed != 0 && sa.fin.h_src != nullptr;
                     break;
                 case SEARCH_YIELD:
                     if (narrow && n_in > kNarrowInstanceWave) wide_grid = true;     // from here on: the full grid
@@ -1769,16 +1831,21 @@ struct stcsp_session {
         if (timing_open) {
             CK(cudaEventRecord(ev1, stream));
         }
-        auto *st = new PinnedStore();
+        // a small automaton that the search kernel pushed into the pinned buffers it was given is on the host already
+        const bool use_push = pre && pushed && push_store != nullptr;
+        PinnedStore *st = use_push ? push_store : new PinnedStore();
+        if (use_push) push_store = nullptr;
         Release guard{stream};
         try {
-            st->sig_vars.alloc(model->sets.sig_vars().size() * 4);
-            st->state_sig.alloc((size_t)ns * SL * 4);
-            st->state_cset.alloc((size_t)ns * 4);
-            st->state_failed.alloc((size_t)ns);
-            st->edge_src.alloc((size_t)n_final * 4);
-            st->edge_dst.alloc((size_t)n_final * 4);
-            st->edge_label.alloc((size_t)n_final * V * 4);
+            if (!use_push) {
+                st->sig_vars.alloc(model->sets.sig_vars().size() * 4);
+                st->state_sig.alloc((size_t)ns * SL * 4);
+                st->state_cset.alloc((size_t)ns * 4);
+                st->state_failed.alloc((size_t)ns);
+                st->edge_src.alloc((size_t)n_final * 4);
+                st->edge_dst.alloc((size_t)n_final * 4);
+                st->edge_label.alloc((size_t)n_final * V * 4);
+            }
             if (liveness || adv) {
                 st->state_final.alloc((size_t)ns);
                 st->state_valid.alloc((size_t)ns);
@@ -1788,18 +1855,18 @@ struct stcsp_session {
                 if (n_final) download(st->edge_alive, fb_palive.p, (size_t)n_final);
             }
             if (!model->sets.sig_vars().empty()) memcpy(st->sig_vars.p, model->sets.sig_vars().data(), model->sets.sig_vars().size() * 4);
-            if (ns) {
+            if (ns && !use_push) {
                 if (SL) download(st->state_sig, rows_sig.p, (size_t)ns * SL * 4);
                 download(st->state_cset, rows_cset.p, (size_t)ns * 4);
                 download(st->state_failed, failed.p, (size_t)ns);
             }
-            if (n_final) {
+            if (n_final && !use_push) {
                 download(st->edge_src, f_src, (size_t)n_final * 4);
                 download(st->edge_dst, f_dst, (size_t)n_final * 4);
                 download(st->edge_label, f_label, (size_t)n_final * V * 4);
             }
             if (small && !pre && !compacted_early) CK(cudaMemcpyAsync(h_counters, counters.p + C_OUT, 8, cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
+            if (timing_open || !use_push || liveness || adv) CK(cudaStreamSynchronize(stream));
             if (timing_open) CK(cudaEventElapsedTime(&ms, ev0, ev1));
             const long long dead = compacted_early ? 0 : pre ? prefinished_dead : (small ? (long long)(int32_t)h_counters[0] : 0);
             if (dead > 0) {
@@ -1826,6 +1893,8 @@ struct stcsp_session {
             throw;
         }
         d2h += ns * (SL + 1) * 4 + ns + n_final * (2 + V) * 4;
+        out_states = ns;
+        out_edges = n_final;
         out->n_states = ns;
         out->n_edges = n_final;
         fill_header(out, ms);

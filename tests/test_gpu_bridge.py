@@ -49,7 +49,19 @@ def test_bridge_code_with_the_cpu_oracle_behind_the_abi(key, tmp_path):
     run_bridge("stcsp_ref_bridge_cpu", REFERENCE[key], tmp_path)
 
 
+# Every run is a fresh process that creates a CUDA context (2-3 s on a cold box), so the default suite takes a representative
+# third of the cases -- every model family, every flag, every feature group of the probes; STCSP_FULL_BRIDGE=1 runs them all
+# (all green on B200, gpurun_out/pytest_gpu_r02l.log: 81 cases).
+BRIDGE_GPU = [k for k in ALL if REFERENCE[k]["edges"] <= 400000]
+if not os.environ.get("STCSP_FULL_BRIDGE"):
+    _KEEP = ("juggling_b4_f4", "juggling_b5_f6", "juggling_b5_f6_nosym", "juggling_b6_f6_nosym", "partialorder_10", "partialorder_12",
+             "digitinvader1", "digitinvader3", "digitinvader5", "digitinvader8", "digitinvader1_a", "digitinvader3_a", "digitinvader3_z",
+             "digitinvader7_z", "digitinvader9_a")
+    BRIDGE_GPU = [k for k in BRIDGE_GPU if k in _KEEP or (k.startswith("probe_") and any(
+        t in k for t in ("adversarial", "until_two", "first_capture", "at2", "fby_expr", "k1", "k3", "unsat", "dead", "quirk", "arr")))]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("key", [k for k in ALL if REFERENCE[k]["edges"] <= 400000])
+@pytest.mark.parametrize("key", BRIDGE_GPU)
 def test_reference_host_around_the_gpu_search(key, tmp_path):
     run_bridge("stcsp_ref_gpu", REFERENCE[key], tmp_path)
