@@ -1764,13 +1764,31 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             A.trace[cs[S_WAVE] * 5 + k] = t;
         }
     };
+    if (A.make_root && blockIdx.x == 0) {
+        // The root state (signature "S", reference src/solveralgorithm.cpp:951-954) and its search node -- every variable at
+        // its declared range at every offset -- written here instead of by three host-to-device copies.  Wave 0 is this one
+        // node, and block 0 is the block that expands it (after the barrier at the top of the wave loop).
+        for (int j = threadIdx.x; j < M.key_words; j += blockDim.x) A.state_key[j] = (j == 0 && M.sig_len != 0) ? -1 : 0;
+        int32_t *node = A.frontier[A.cur0];
+        if (threadIdx.x < 4) node[threadIdx.x] = threadIdx.x == 3 ? -1 : 0;
+        u64 *nd = reinterpret_cast<u64 *>(node + 4);
+        for (int i = threadIdx.x; i < M.V * M.k; i += blockDim.x) nd[i] = width_mask(M.width[i / M.k]);
+        if (threadIdx.x == 0) {
+            A.counters[C_STATES] = 1ull;
+            // ... and its slot in the (fresh) state table, like rehash_kernel does for every known state
+            uint32_t h = 0;
+            for (int j = 0; j < M.key_words; j++) h ^= key_word_hash((j == 0 && M.sig_len != 0) ? -1 : 0, j);
+            A.table[(long long)mix32(h) & A.table_mask] = 0;
+        }
+        __threadfence();
+    }
     if (threadIdx.x == 0) {
         s_resident = -1;
         for (int i = 0; i < S_COUNT; i++) cs[i] = 0;
-        cs[S_N_IN] = ctl->n_in;
-        cs[S_CUR] = ctl->cur;
-        cs[S_WAVES_LEFT] = ctl->waves_left;
-        cs[S_STATES] = (long long)tot[C_STATES];
+        cs[S_N_IN] = A.n_in0;
+        cs[S_CUR] = A.cur0;
+        cs[S_WAVES_LEFT] = A.waves_left0;
+        cs[S_STATES] = A.make_root ? 1ll : (long long)tot[C_STATES];
         cs[S_EDGES] = (long long)tot[C_EDGES];
     }
     // Leave the kernel (all threads call it, every block with the same status).  The host reads set 0.

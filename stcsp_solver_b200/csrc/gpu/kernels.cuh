@@ -169,6 +169,9 @@ struct FinishArgs {
 struct SearchArgs {
     SearchCtl *ctl;
     unsigned long long *counters;
+    long long n_in0, waves_left0;       // where this launch starts: frontier size, buffer index, wave budget (no control-block upload)
+    int32_t cur0;
+    int32_t make_root;                  // 1: first launch of a solve -- block 0 writes the root state and its search node itself
     SearchCtl *h_ctl;                   // optional: pinned host mirrors of ctl / counter set 0 (mapped); the kernel writes them
     unsigned long long *h_counters;     // when it leaves, so the host reads them after one stream synchronisation
     int32_t *frontier[2];

@@ -587,6 +587,9 @@ struct stcsp_session {
     PinnedStore *push_store = nullptr;
     long long push_cap_states = 0, push_cap_edges = 0;
     bool pushed = false;            // ... and did (no device-to-host copy is needed)
+    bool root_in_kernel = false;    // set by stcsp_gpu_solve before init(): the persistent path creates the root on the device
+    bool root_pending = false;      // ... and has not done so yet
+    bool counters_fresh = false;    // every counter set is zero (init() has just cleared them)
     long long out_states = 0, out_edges = 0;        // size of the automaton this solve returned
     SearchCtl *h_ctl = nullptr;     // pinned, behind h_counters
     int search_grid = 0;
@@ -781,7 +784,7 @@ struct stcsp_session {
         fresh.reserve((size_t)want, 0, stream);
         launch_fill(fresh.p, want, -1, stream);
         // (the root's key starts with -1 unless its signature is empty, so it can sit in the table unreachable)
-        if (n_states > 0) {
+        if (n_states > 0 && !root_pending) {     // (root_pending: the only state is the root, which search_kernel inserts itself)
             launch_rehash(dm, fresh.p, want - 1, state_key.p, n_states, sm_count * 4, stream);
             t_launches++;
         }
@@ -840,6 +843,7 @@ struct stcsp_session {
         const double t_uploaded = now_s();
         counters.reserve(kCounterSets * kCounterStride, 0, stream);
         CK(cudaMemsetAsync(counters.p, 0, kCounterSets * kCounterStride * sizeof(unsigned long long), stream));
+        counters_fresh = true;
         h_counters = pinned_cache().acquire();       // C_COUNT counters + room for the search control block
         {
             void *d = nullptr;
@@ -867,7 +871,11 @@ struct stcsp_session {
         h_ctl = reinterpret_cast<SearchCtl *>(h_counters + C_COUNT);
         search_grid = search_max_grid(dm, sm_count);
         if (!coop_launch) search_grid = 0;
-        if (rank == 0) {
+        if (rank == 0 && root_in_kernel && search_grid > 0 && world == 1) {
+            root_pending = true;        // search_kernel writes the root state and its node itself (SearchArgs::make_root)
+            n_states = 1;
+            n_in = 1;
+        } else if (rank == 0) {
             // root state (reference src/solveralgorithm.cpp:951-954) and its search node
             std::vector<int32_t> key(KW, 0);
             key[0] = dm.sig_len == 0 ? 0 : -1;
@@ -1016,12 +1024,13 @@ struct stcsp_session {
                 sa.trace_cap = trace_waves;
             }
             memset(h_ctl, 0, sizeof *h_ctl);
-            h_ctl->n_in = n_in;
-            h_ctl->cur = cur;
-            h_ctl->status = SEARCH_RUN;
-            h_ctl->waves_left = deadline > 0 ? 256 : (1ll << 40);
-            CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof *h_ctl, cudaMemcpyHostToDevice, stream));
-            zero_wave_counters();
+            sa.n_in0 = n_in;
+            sa.cur0 = cur;
+            sa.waves_left0 = deadline > 0 ? 256 : (1ll << 40);
+            sa.make_root = root_pending ? 1 : 0;
+            root_pending = false;
+            if (!counters_fresh) zero_wave_counters();
+            counters_fresh = false;
             const int grid = narrow ? std::min(search_grid, sm_count) : search_grid;
             sa.h_ctl = host_mirror ? reinterpret_cast<SearchCtl *>(host_mirror + C_COUNT) : nullptr;
             sa.h_counters = host_mirror;
@@ -1068,7 +1077,6 @@ struct stcsp_session {
                 CK(cudaStreamSynchronize(stream));
             }
             t_launches++;
-            h2d += sizeof *h_ctl;
             d2h += sizeof *h_ctl;
             t_nodes += h_ctl->t_nodes;
             t_fails += h_ctl->t_fails;
@@ -2810,6 +2818,7 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
     const bool verbose = options && options->verbosity > 0;
     int rc = guarded([&] {
         s = new stcsp_session();
+        s->root_in_kernel = !(options && options->profile_kernels);
         s->init(problem, options, 0, 1);
         t_init = now_s();
         const double deadline = s->opt.time_limit_s > 0 ? t0 + s->opt.time_limit_s : 0;

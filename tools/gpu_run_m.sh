@@ -1,6 +1,6 @@
 set -x
 ( time timeout 600 python -m pytest tests/test_gpu_fuzz.py tests/test_gpu_parity.py tests/test_gpu_sharded.py -x -q -k "not semantic and not partialorder_14 and not partialorder_13 and not partialorder_12 and not digitinvader9 and not digitinvader8 and not digitinvader7 and not cli" ) > gpurun_out/pytest_fast_r02m.log 2>&1; tail -4 gpurun_out/pytest_fast_r02m.log
-for n in juggling_b4_f4 juggling_b6_f6_nosym juggling_b5_f6 digitinvader3 probe_until_two; do
+for n in juggling_b4_f4 juggling_b6_f6_nosym juggling_b5_f6 digitinvader3; do
   python tools/wave_trace.py $n 0 > gpurun_out/t.txt 2>&1; echo "push: $(tail -1 gpurun_out/t.txt)"
   STCSP_NO_PUSH=1 python tools/wave_trace.py $n 0 > gpurun_out/t.txt 2>&1; echo "nopush: $(tail -1 gpurun_out/t.txt)"
 done
