@@ -1037,6 +1037,7 @@ struct stcsp_session {
             CK(cudaEventRecord(evk0, stream));
             CK(launch_search(dm, sa, grid, sm_count, stream));
             CK(cudaEventRecord(evk1, stream));
+            h2d += sizeof dm + sizeof sa;       // the launch parameters (model descriptor, start values) are what goes down per launch
             if (host_mirror) {
                 // the kernel wrote its control block and counter set 0 into the pinned block itself: one synchronisation
                 CK(cudaStreamSynchronize(stream));
