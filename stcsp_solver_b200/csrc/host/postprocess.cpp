@@ -10,13 +10,16 @@
 // numbered breadth-first from the root with out-edges in label order, which
 // is the canonical form the parity tests compare.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
+#include <memory>
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cstdio>
@@ -108,9 +111,41 @@ void greatest_fixpoint(Work &w, Check check) {
     }
 }
 
+// Host threads for the passes that are linear in the automaton (sorting out-edges, filling the solution arrays,
+// formatting text): a partialorder_20-size automaton has 63 M edges and 10 GB of canonical text.
+int host_threads() {
+    static const int n = [] {
+        int t = (int)std::thread::hardware_concurrency();
+        if (const char *e = getenv("STCSP_HOST_THREADS")) t = atoi(e);
+        return std::max(1, std::min(t, 32));
+    }();
+    return n;
+}
+
+// f(begin, end) over [0, n) in chunks of `grain`, handed out dynamically; inline when the range is small.
+template <class F>
+void parallel_chunks(int64_t n, int64_t grain, F f) {
+    const int T = (int)std::min<int64_t>(host_threads(), (n + grain - 1) / grain);
+    if (T <= 1) { if (n > 0) f((int64_t)0, n); return; }
+    std::atomic<int64_t> next{0};
+    auto body = [&] {
+        for (;;) {
+            const int64_t b = next.fetch_add(grain);
+            if (b >= n) return;
+            f(b, std::min(n, b + grain));
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(body);
+    body();
+    for (auto &x : th) x.join();
+}
+
 struct SolutionStore {
-    std::vector<int32_t> cset, sig, src, dst, label;
-    std::vector<uint8_t> fin;
+    // plain arrays, not vectors: nothing zero-fills 10 GB of labels before they are written
+    std::unique_ptr<int32_t[]> cset, sig, src, dst, label;
+    std::unique_ptr<uint8_t[]> fin;
+    std::vector<int64_t> first;             // CSR over the canonical edges: out-edges of vertex v = [first[v], first[v+1])
 };
 
 char *dup_string(const std::string &s) {
@@ -238,51 +273,85 @@ int stcsp_postprocess(const stcsp_problem_t *problem, const stcsp_automaton_t *a
     out->sig_len = a->n_sig_vars + a->n_until_vars;
     impl->sig_vars.assign(a->sig_vars, a->sig_vars + a->n_sig_vars);
     SolutionStore &st = impl->store;
+    int64_t n_out = 0, m_out = 0;
     if (out->root_valid) {
+        // out-edges of every state in label order: one index array over the surviving edges, ranges sorted in parallel
+        std::vector<int64_t> pfirst(w.n + 1, 0);
+        for (int64_t s = 0; s < w.n; s++) {
+            int64_t c = 0;
+            for (int64_t e = w.first_edge[s]; e < w.first_edge[s + 1]; e++) c += w.alive[e] != 0;
+            pfirst[s + 1] = pfirst[s] + c;
+        }
+        std::unique_ptr<int64_t[]> perm(new int64_t[pfirst[w.n] + 1]);
+        const int32_t nv = w.nv;
+        const int32_t *labels = a->edge_label;
+        parallel_chunks(w.n, 4096, [&](int64_t b, int64_t e_) {
+            for (int64_t s = b; s < e_; s++) {
+                int64_t *o = perm.get() + pfirst[s], *o0 = o;
+                bool sorted = true;
+                for (int64_t e = w.first_edge[s]; e < w.first_edge[s + 1]; e++) {
+                    if (!w.alive[e]) continue;
+                    if (o != o0 && sorted)
+                        sorted = !std::lexicographical_compare(labels + e * nv, labels + e * nv + nv, labels + o[-1] * nv, labels + o[-1] * nv + nv);
+                    *o++ = e;
+                }
+                if (!sorted)
+                    std::sort(o0, o, [&](int64_t x, int64_t y) {
+                        return std::lexicographical_compare(labels + x * nv, labels + x * nv + nv, labels + y * nv, labels + y * nv + nv);
+                    });
+            }
+        });
+        // breadth-first numbering from the root: the visiting order IS the queue
         std::vector<int32_t> number(w.n, -1), order;
-        std::deque<int32_t> queue;
+        order.reserve(w.n);
         number[0] = 0;
-        queue.push_back(0);
-        std::vector<std::vector<int64_t>> sorted_edges;
-        auto label_less = [&](int64_t x, int64_t y) {
-            return std::lexicographical_compare(w.label(x), w.label(x) + w.nv, w.label(y), w.label(y) + w.nv);
-        };
-        while (!queue.empty()) {
-            int32_t s = queue.front();
-            queue.pop_front();
-            order.push_back(s);
-            std::vector<int64_t> es;
-            for (int64_t e = w.first_edge[s]; e < w.first_edge[s + 1]; e++)
-                if (w.alive[e]) es.push_back(e);
-            std::sort(es.begin(), es.end(), label_less);
-            for (int64_t e : es) {
-                int32_t d = a->edge_dst[e];
-                if (number[d] < 0) { number[d] = (int32_t)order.size() + (int32_t)queue.size(); queue.push_back(d); }
-            }
-            sorted_edges.push_back(std::move(es));
-        }
-        std::map<int32_t, int32_t> cmap;
-        for (size_t i = 0; i < order.size(); i++) {
-            int32_t s = order[i];
-            int32_t c = (int32_t)cmap.emplace(a->state_cset[s], (int32_t)cmap.size()).first->second;
-            st.cset.push_back(c);
-            st.fin.push_back(w.fin[s]);
-            for (int32_t k = 0; k < out->sig_len; k++) st.sig.push_back(s == 0 ? 0 : a->state_sig[(int64_t)s * a->sig_len + k]);
-            for (int64_t e : sorted_edges[i]) {
-                st.src.push_back((int32_t)i);
-                st.dst.push_back(number[a->edge_dst[e]]);
-                st.label.insert(st.label.end(), w.label(e), w.label(e) + w.nv);
+        order.push_back(0);
+        for (size_t head = 0; head < order.size(); head++) {
+            const int32_t s = order[head];
+            for (int64_t i = pfirst[s]; i < pfirst[s + 1]; i++) {
+                const int32_t d = a->edge_dst[perm[i]];
+                if (number[d] < 0) { number[d] = (int32_t)order.size(); order.push_back(d); }
             }
         }
+        n_out = (int64_t)order.size();
+        st.first.assign(n_out + 1, 0);
+        for (int64_t i = 0; i < n_out; i++) st.first[i + 1] = st.first[i] + (pfirst[order[i] + 1] - pfirst[order[i]]);
+        m_out = st.first[n_out];
+        const int32_t SL = out->sig_len;
+        st.cset.reset(new int32_t[n_out + 1]);
+        st.fin.reset(new uint8_t[n_out + 1]);
+        st.sig.reset(new int32_t[n_out * (int64_t)SL + 1]);
+        st.src.reset(new int32_t[m_out + 1]);
+        st.dst.reset(new int32_t[m_out + 1]);
+        st.label.reset(new int32_t[m_out * (int64_t)nv + 1]);
+        std::map<int32_t, int32_t> cmap;        // constraint sets in order of first appearance (a handful)
+        for (int64_t i = 0; i < n_out; i++)
+            st.cset[i] = cmap.emplace(a->state_cset[order[i]], (int32_t)cmap.size()).first->second;
+        parallel_chunks(n_out, 2048, [&](int64_t b, int64_t e_) {
+            for (int64_t i = b; i < e_; i++) {
+                const int32_t s = order[i];
+                st.fin[i] = w.fin[s];
+                for (int32_t k = 0; k < SL; k++) st.sig[i * SL + k] = s == 0 ? 0 : a->state_sig[(int64_t)s * a->sig_len + k];
+                int64_t o = st.first[i];
+                for (int64_t j = pfirst[s]; j < pfirst[s + 1]; j++, o++) {
+                    const int64_t e = perm[j];
+                    st.src[o] = (int32_t)i;
+                    st.dst[o] = number[a->edge_dst[e]];
+                    memcpy(st.label.get() + o * nv, labels + e * nv, (size_t)nv * 4);
+                }
+            }
+        });
+    } else {
+        st.first.assign(1, 0);
     }
-    out->n_states = (int64_t)st.cset.size();
-    out->n_edges = (int64_t)st.src.size();
-    out->state_cset = st.cset.data();
-    out->state_final = st.fin.data();
-    out->state_sig = st.sig.data();
-    out->edge_src = st.src.data();
-    out->edge_dst = st.dst.data();
-    out->edge_label = st.label.data();
+    out->n_states = n_out;
+    out->n_edges = m_out;
+    out->state_cset = st.cset.get();
+    out->state_final = st.fin.get();
+    out->state_sig = st.sig.get();
+    out->edge_src = st.src.get();
+    out->edge_dst = st.dst.get();
+    out->edge_label = st.label.get();
     return STCSP_OK;
 }
 
@@ -294,80 +363,168 @@ void stcsp_solution_free(stcsp_solution_t *s) {
 
 }  // extern "C"
 
-// Both texts are produced line by line through a sink, so they can be streamed to a file or into SHA-256 without
-// ever holding the whole text (82 MB at partialorder_14, ~10 GB at partialorder_20).
+// Both texts are produced through a sink in chunks of a megabyte or so, so they can be streamed to a file or into
+// SHA-256 without ever holding the whole text (82 MB at partialorder_14, ~10 GB at partialorder_20).  Chunks are
+// formatted by host threads side by side and handed to the sink in order while the next ones are being formatted.
 namespace {
+
+struct TextBuf {
+    std::vector<char> mem;
+    size_t len = 0;
+    char *room(size_t n) {                 // at least n more bytes
+        if (len + n > mem.size()) mem.resize(std::max(mem.size() * 2, len + n + (1 << 16)));
+        return mem.data() + len;
+    }
+    void put(const char *p, size_t n) { memcpy(room(n), p, n); len += n; }
+    void put(const std::string &t) { put(t.data(), t.size()); }
+};
+
+inline char *put_int(char *p, int64_t v) {
+    uint64_t u = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+    if (v < 0) *p++ = '-';
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+inline char *put_lit(char *p, const char *lit, size_t n) { memcpy(p, lit, n); return p + n; }
+#define LIT(p, s) put_lit(p, s, sizeof(s) - 1)
+
+// fmt(chunk index, buffer) for chunks 0 .. n_chunks-1; the sink sees the buffers in chunk order
+template <class Sink, class Fmt>
+void emit_chunks(int64_t n_chunks, Fmt fmt, Sink &sink) {
+    const int T = (int)std::min<int64_t>(host_threads(), n_chunks);
+    if (T <= 1) {
+        TextBuf b;
+        for (int64_t c = 0; c < n_chunks; c++) { b.len = 0; fmt(c, b); sink(b.mem.data(), b.len); }
+        return;
+    }
+    std::vector<TextBuf> bufs[2] = {std::vector<TextBuf>(T), std::vector<TextBuf>(T)};
+    int64_t filled[2] = {0, 0};
+    for (int64_t base = 0, r = 0; base < n_chunks || filled[(r + 1) & 1]; base += T, r++) {
+        const int cur = (int)(r & 1), prev = cur ^ 1;
+        const int64_t cnt = std::max<int64_t>(0, std::min<int64_t>(T, n_chunks - base));
+        std::vector<std::thread> th;
+        for (int64_t t = 0; t < cnt; t++)
+            th.emplace_back([&, t] { bufs[cur][t].len = 0; fmt(base + t, bufs[cur][t]); });
+        for (int64_t t = 0; t < filled[prev]; t++) sink(bufs[prev][t].mem.data(), bufs[prev][t].len);   // the round before, in order
+        filled[prev] = 0;
+        for (auto &x : th) x.join();
+        filled[cur] = cnt;
+    }
+}
+
+const std::vector<int64_t> &edge_first(const stcsp_solution_t *s) { return ((const Impl *)s->impl)->store.first; }
+
+// vertices [v0, v1) cut into chunks of about `weight` lines (a vertex with its out-edges stays in one chunk)
+std::vector<int64_t> vertex_chunks(const stcsp_solution_t *s, int64_t weight) {
+    const std::vector<int64_t> &first = edge_first(s);
+    std::vector<int64_t> cut{0};
+    int64_t acc = 0;
+    for (int64_t v = 0; v < s->n_states; v++) {
+        acc += 1 + first[v + 1] - first[v];
+        if (acc >= weight) { cut.push_back(v + 1); acc = 0; }
+    }
+    if (cut.back() != s->n_states) cut.push_back(s->n_states);
+    return cut;
+}
 
 template <class Sink>
 void emit_dot(const stcsp_problem_t *p, const stcsp_solution_t *s, Sink &&sink) {
     const Impl *impl = (const Impl *)s->impl;
-    std::string line;
-    line = "# Number of nodes = " + std::to_string(s->n_table_states) + "\n";
-    sink(line);
-    sink(header_line(p, s, false, nullptr, 0) + "\n");
-    sink(header_line(p, s, true, impl->sig_vars.data(), (int32_t)impl->sig_vars.size()) + "\n");
-    sink(std::string("digraph \"StCSP\" {\n"));
-    int64_t e = 0;
+    std::string head = "# Number of nodes = " + std::to_string(s->n_table_states) + "\n";
+    head += header_line(p, s, false, nullptr, 0) + "\n";
+    head += header_line(p, s, true, impl->sig_vars.data(), (int32_t)impl->sig_vars.size()) + "\n";
+    head += "digraph \"StCSP\" {\n";
+    sink(head.data(), head.size());
+    const std::vector<int64_t> &first = edge_first(s);
+    const std::vector<int64_t> cut = vertex_chunks(s, 1 << 14);
+    const size_t vmax = 64 + 14 * (size_t)std::max(1, s->sig_len), emax = 48 + 14 * (size_t)std::max(1, s->n_vars);
     // the reference prints numSignVar + numUntil(distinct variables) values per vertex label
-    for (int64_t v = 0; v < s->n_states; v++) {
-        line = std::to_string(v) + " [shape=" + (s->state_final[v] ? "doublecircle" : "circle") + ", label=\"" +
-               std::to_string(s->state_cset[v]) + ": ";
-        if (v == 0) line += "S";
-        else
-            for (int32_t k = 0; k < s->sig_len; k++) {
-                if (k) line += ", ";
-                line += std::to_string(s->state_sig[v * s->sig_len + k]);
+    emit_chunks((int64_t)cut.size() - 1, [&](int64_t c, TextBuf &b) {
+        for (int64_t v = cut[c]; v < cut[c + 1]; v++) {
+            char *q = b.room(vmax), *q0 = q;
+            q = put_int(q, v);
+            q = s->state_final[v] ? LIT(q, " [shape=doublecircle, label=\"") : LIT(q, " [shape=circle, label=\"");
+            q = put_int(q, s->state_cset[v]);
+            q = LIT(q, ": ");
+            if (v == 0) *q++ = 'S';
+            else
+                for (int32_t k = 0; k < s->sig_len; k++) {
+                    if (k) q = LIT(q, ", ");
+                    q = put_int(q, s->state_sig[v * s->sig_len + k]);
+                }
+            q = LIT(q, "\"];\n");
+            b.len += q - q0;
+            for (int64_t e = first[v]; e < first[v + 1]; e++) {
+                q = q0 = b.room(emax);
+                q = put_int(q, v);
+                q = LIT(q, " -> ");
+                q = put_int(q, s->edge_dst[e]);
+                q = LIT(q, " [label=\"");
+                const int32_t *lab = s->edge_label + e * s->n_vars;
+                for (int32_t k = 0; k < s->n_vars; k++) {
+                    if (k) q = LIT(q, ", ");
+                    q = put_int(q, lab[k]);
+                }
+                q = LIT(q, "\"];\n");
+                b.len += q - q0;
             }
-        line += "\"];\n";
-        sink(line);
-        for (; e < s->n_edges && s->edge_src[e] == v; e++) {
-            line = std::to_string(v) + " -> " + std::to_string(s->edge_dst[e]) + " [label=\"";
-            for (int32_t k = 0; k < s->n_vars; k++) {
-                if (k) line += ", ";
-                line += std::to_string(s->edge_label[e * s->n_vars + k]);
-            }
-            line += "\"];\n";
-            sink(line);
         }
-    }
-    sink(std::string("}\n"));
+    }, sink);
+    sink("}\n", 2);
 }
 
 template <class Sink>
 void emit_canonical(const stcsp_problem_t *p, const stcsp_solution_t *s, Sink &&sink) {
-    if (!s->root_valid) { sink(std::string("EMPTY")); return; }
+    if (!s->root_valid) { sink("EMPTY", 5); return; }
     const Impl *impl = (const Impl *)s->impl;
-    sink(header_line(p, s, false, nullptr, 0) + "\n");
-    sink(header_line(p, s, true, impl->sig_vars.data(), (int32_t)impl->sig_vars.size()) + "\n");
-    std::string line;
-    for (int64_t v = 0; v < s->n_states; v++) {
-        line = "V " + std::to_string(v) + " " + (s->state_final[v] ? "F" : "N") + " " + std::to_string(s->state_cset[v]) + " ";
-        if (v == 0) line += "S";
-        else
-            for (int32_t k = 0; k < s->sig_len; k++) {
-                if (k) line += " ";
-                line += std::to_string(s->state_sig[v * s->sig_len + k]);
-            }
-        line += "\n";
-        sink(line);
-    }
-    char buf[16];
-    for (int64_t e = 0; e < s->n_edges; e++) {
-        line = "E " + std::to_string(s->edge_src[e]) + " " + std::to_string(s->edge_dst[e]);
-        const int32_t *lab = s->edge_label + e * s->n_vars;
-        for (int32_t k = 0; k < s->n_vars; k++) {
-            snprintf(buf, sizeof buf, " %d", lab[k]);
-            line += buf;
+    std::string head = header_line(p, s, false, nullptr, 0) + "\n";
+    head += header_line(p, s, true, impl->sig_vars.data(), (int32_t)impl->sig_vars.size()) + "\n";
+    sink(head.data(), head.size());
+    const size_t vmax = 64 + 12 * (size_t)std::max(1, s->sig_len), emax = 48 + 12 * (size_t)std::max(1, s->n_vars);
+    const int64_t VC = 1 << 14, EC = 1 << 14;
+    emit_chunks((s->n_states + VC - 1) / VC, [&](int64_t c, TextBuf &b) {
+        for (int64_t v = c * VC; v < std::min(s->n_states, (c + 1) * VC); v++) {
+            char *q = b.room(vmax), *q0 = q;
+            q = LIT(q, "V ");
+            q = put_int(q, v);
+            q = s->state_final[v] ? LIT(q, " F ") : LIT(q, " N ");
+            q = put_int(q, s->state_cset[v]);
+            *q++ = ' ';
+            if (v == 0) *q++ = 'S';
+            else
+                for (int32_t k = 0; k < s->sig_len; k++) {
+                    if (k) *q++ = ' ';
+                    q = put_int(q, s->state_sig[v * s->sig_len + k]);
+                }
+            *q++ = '\n';
+            b.len += q - q0;
         }
-        line += "\n";
-        sink(line);
-    }
+    }, sink);
+    emit_chunks((s->n_edges + EC - 1) / EC, [&](int64_t c, TextBuf &b) {
+        for (int64_t e = c * EC; e < std::min(s->n_edges, (c + 1) * EC); e++) {
+            char *q = b.room(emax), *q0 = q;
+            q = LIT(q, "E ");
+            q = put_int(q, s->edge_src[e]);
+            *q++ = ' ';
+            q = put_int(q, s->edge_dst[e]);
+            const int32_t *lab = s->edge_label + e * s->n_vars;
+            for (int32_t k = 0; k < s->n_vars; k++) {
+                *q++ = ' ';
+                q = put_int(q, lab[k]);
+            }
+            *q++ = '\n';
+            b.len += q - q0;
+        }
+    }, sink);
 }
 
 struct FileSink {
     FILE *f;
     bool ok = true;
-    void operator()(const std::string &l) { ok = ok && fwrite(l.data(), 1, l.size(), f) == l.size(); }
+    void operator()(const char *p, size_t n) { ok = ok && fwrite(p, 1, n, f) == n; }
 };
 
 template <class Emit>
@@ -389,13 +546,13 @@ extern "C" {
 
 char *stcsp_solution_dot(const stcsp_problem_t *p, const stcsp_solution_t *s) {
     std::string out;
-    emit_dot(p, s, [&](const std::string &l) { out += l; });
+    emit_dot(p, s, [&](const char *t, size_t n) { out.append(t, n); });
     return dup_string(out);
 }
 
 char *stcsp_solution_canonical(const stcsp_problem_t *p, const stcsp_solution_t *s) {
     std::string out;
-    emit_canonical(p, s, [&](const std::string &l) { out += l; });
+    emit_canonical(p, s, [&](const char *t, size_t n) { out.append(t, n); });
     return dup_string(out);
 }
 
@@ -412,7 +569,7 @@ int stcsp_solution_write_canonical(const stcsp_problem_t *p, const stcsp_solutio
 int stcsp_solution_canonical_sha256(const stcsp_problem_t *p, const stcsp_solution_t *s, char out_hex[65]) {
     if (!p || !s || !out_hex) { stcsp::set_error("null argument"); return STCSP_ERR_INVALID; }
     stcsp::Sha256 sha;
-    emit_canonical(p, s, [&](const std::string &l) { sha.update(l.data(), l.size()); });
+    emit_canonical(p, s, [&](const char *t, size_t n) { sha.update(t, n); });
     const std::string hex = sha.hex();
     memcpy(out_hex, hex.c_str(), 65);
     return STCSP_OK;

@@ -8,6 +8,12 @@
 
 #include <string>
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <cpuid.h>
+#include <immintrin.h>
+#define STCSP_SHA_NI 1
+#endif
+
 namespace stcsp {
 
 class Sha256 {
@@ -23,6 +29,12 @@ class Sha256 {
     void update(const void *data, size_t n) {
         const unsigned char *p = (const unsigned char *)data;
         total_ += n;
+        if (fill_ == 0 && n >= 64) {        // whole blocks straight from the caller's buffer
+            const size_t nb = n / 64;
+            blocks(p, nb);
+            p += nb * 64;
+            n -= nb * 64;
+        }
         while (n > 0) {
             size_t take = 64 - fill_;
             if (take > n) take = n;
@@ -31,8 +43,14 @@ class Sha256 {
             p += take;
             n -= take;
             if (fill_ == 64) {
-                block(buf_);
+                blocks(buf_, 1);
                 fill_ = 0;
+                if (n >= 64) {
+                    const size_t nb = n / 64;
+                    blocks(p, nb);
+                    p += nb * 64;
+                    n -= nb * 64;
+                }
             }
         }
     }
@@ -54,7 +72,7 @@ class Sha256 {
 
   private:
     static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
-    void block(const unsigned char *p) {
+    static const uint32_t *round_constants() {
         static const uint32_t K[64] = {
             0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
             0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
@@ -64,6 +82,64 @@ class Sha256 {
             0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
             0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
             0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+        return K;
+    }
+    void blocks(const unsigned char *p, size_t nb) {
+#ifdef STCSP_SHA_NI
+        static const bool ni = have_sha_ni();
+        if (ni) { blocks_ni(p, nb); return; }
+#endif
+        for (size_t i = 0; i < nb; i++) block(p + 64 * i);
+    }
+#ifdef STCSP_SHA_NI
+    // the x86 SHA extensions (CPUID.7.0:EBX bit 29) hash ~5x faster than the portable rounds below; same digest
+    static bool have_sha_ni() {
+        unsigned a, b, c, d;
+        if (!__get_cpuid_count(7, 0, &a, &b, &c, &d)) return false;
+        const bool sha = (b >> 29) & 1u;
+        if (!__get_cpuid(1, &a, &b, &c, &d)) return false;
+        return sha && ((c >> 19) & 1u) && ((c >> 9) & 1u);      // + SSE4.1, SSSE3
+    }
+    __attribute__((target("sha,sse4.1,ssse3"))) void blocks_ni(const unsigned char *p, size_t nb) {
+        const uint32_t *K = round_constants();
+        const __m128i bswap = _mm_set_epi64x(0x0c0d0e0f08090a0bll, 0x0405060700010203ll);
+        __m128i t = _mm_loadu_si128((const __m128i *)&h_[0]);       // a b c d
+        __m128i s1 = _mm_loadu_si128((const __m128i *)&h_[4]);      // e f g h
+        t = _mm_shuffle_epi32(t, 0xB1);                             // c d a b
+        s1 = _mm_shuffle_epi32(s1, 0x1B);                           // e f g h reversed
+        __m128i s0 = _mm_alignr_epi8(t, s1, 8);                     // a b e f
+        s1 = _mm_blend_epi16(s1, t, 0xF0);                          // c d g h
+        for (; nb; nb--, p += 64) {
+            const __m128i save0 = s0, save1 = s1;
+            __m128i m[4];
+            for (int i = 0; i < 4; i++) m[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 16 * i)), bswap);
+#pragma GCC unroll 16
+            for (int r = 0; r < 16; r++) {
+                // four rounds per step; m[r & 3] holds w[4r .. 4r+3]
+                __m128i msg = _mm_add_epi32(m[r & 3], _mm_loadu_si128((const __m128i *)(K + 4 * r)));
+                s1 = _mm_sha256rnds2_epu32(s1, s0, msg);
+                msg = _mm_shuffle_epi32(msg, 0x0E);
+                s0 = _mm_sha256rnds2_epu32(s0, s1, msg);
+                if (r < 12) {
+                    // schedule w[4(r+4) .. 4(r+4)+3] into the slot that is no longer needed
+                    __m128i x = _mm_sha256msg1_epu32(m[r & 3], m[(r + 1) & 3]);
+                    x = _mm_add_epi32(x, _mm_alignr_epi8(m[(r + 3) & 3], m[(r + 2) & 3], 4));
+                    m[r & 3] = _mm_sha256msg2_epu32(x, m[(r + 3) & 3]);
+                }
+            }
+            s0 = _mm_add_epi32(s0, save0);
+            s1 = _mm_add_epi32(s1, save1);
+        }
+        t = _mm_shuffle_epi32(s0, 0x1B);                            // f e b a
+        s1 = _mm_shuffle_epi32(s1, 0xB1);                           // d c h g
+        s0 = _mm_blend_epi16(t, s1, 0xF0);                          // a b c d
+        s1 = _mm_alignr_epi8(s1, t, 8);                             // e f g h
+        _mm_storeu_si128((__m128i *)&h_[0], s0);
+        _mm_storeu_si128((__m128i *)&h_[4], s1);
+    }
+#endif
+    void block(const unsigned char *p) {
+        const uint32_t *K = round_constants();
         uint32_t w[64];
         for (int i = 0; i < 16; i++)
             w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
