@@ -208,6 +208,13 @@ void stcsp_gpu_release_caches(void);
 /* Number of usable CUDA devices (0 if none); never fails. */
 int stcsp_gpu_device_count(void);
 
+/* Optional one-time set-up for a process that will solve more than once (a service, a benchmark loop; the command-line
+ * tool, like the reference, solves once and does not call it): creates the context on `device` (-1 = current), loads
+ * the kernel modules, reserves the first device arena and pins `pinned_bytes` of host memory for results (0 = none), so
+ * that the first solve of a model costs what a new MODEL costs (compile, upload, relation tables), not what a new process
+ * costs.  No reference counterpart (the reference is a one-shot program, src/solver.cpp:181-345). */
+int stcsp_gpu_warmup(int32_t device, int64_t pinned_bytes);
+
 /* ---------------------------------------------------------------------------------------------
  * Step-wise session API: the same search, one frontier wave at a time, so that a multi-GPU
  * driver (one process per GPU) can exchange leaf records by hash owner between `expand` and

@@ -128,6 +128,8 @@ def lib() -> C.CDLL:
         L.stcsp_solution_canonical_sha256.argtypes = [C.POINTER(Problem), C.POINTER(SolutionC), C.c_char_p]
         L.stcsp_gpu_device_count.restype = C.c_int
         L.stcsp_gpu_release_caches.restype = None
+        L.stcsp_gpu_warmup.argtypes = [C.c_int32, C.c_int64]
+        L.stcsp_gpu_warmup.restype = C.c_int
         L.stcsp_session_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.c_int32, C.c_int32,
                                            C.POINTER(C.c_void_p)]
         L.stcsp_session_destroy.argtypes = [C.c_void_p]
@@ -315,6 +317,12 @@ def solve(model: Model, options: Optional[Options] = None) -> Automaton:
     opts = options if options is not None else default_options()
     _check(lib().stcsp_gpu_solve(model.problem, C.byref(opts), C.byref(out)))
     return Automaton(out, lib().stcsp_automaton_free)
+
+
+def warmup(device: int = -1, pinned_bytes: int = 0) -> None:
+    """One-time set-up of a process that will solve more than once (stcsp_gpu_warmup): context, kernel modules, arenas,
+    and `pinned_bytes` of pinned host memory for results."""
+    _check(lib().stcsp_gpu_warmup(int(device), int(pinned_bytes)))
 
 
 def release_caches() -> None:

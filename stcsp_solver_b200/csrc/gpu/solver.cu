@@ -27,6 +27,7 @@
 #include "../host/error.h"
 #include "kernels.cuh"
 #include "stcsp_b200.h"
+#include "stcsp_host.h"
 
 namespace stcsp {
 namespace {
@@ -402,6 +403,15 @@ struct HostCache {
                 it->second.pop_back();
                 return p;
             }
+            if (bytes > kSmall && big_state.load(std::memory_order_acquire) == 2) {
+                // the arena prepared in the background (prepare_big): large blocks are carved out of it, page-aligned
+                const size_t need = (bytes + 4095) & ~(size_t)4095;
+                if (big.size - big.used >= need) {
+                    void *p = big.base + big.used;
+                    big.used += need;
+                    return p;
+                }
+            }
             if (bytes <= kSmall) {
                 for (Arena &a : arenas)
                     if (a.size - a.used >= bytes) {
@@ -420,6 +430,29 @@ struct HostCache {
             }
         }
         return map_and_register(bytes, kind);
+    }
+    // ---- a large pinned arena, prepared ahead of time (stcsp_gpu_warmup) ---------------------------------------------
+    // Pinning fresh host memory costs ~4-7 GB/s here (the OS zeroes the pages, the driver registers them): 15 of the 22 ms of
+    // a FIRST partialorder_14 solve in a warm process went into the 91 MB of its result.  A process that will solve more than
+    // once can pin one arena up front; from then on a result block of a size class not seen before is a pointer bump.
+    // Blocks given back are kept by size class like any other; what does not fit goes the old way.  (Doing this behind the
+    // caller's back in a background thread was tried and dropped: cudaHostRegister of 512 MB holds the driver for the better
+    // part of a second, and a solve that runs meanwhile stalls -- partialorder_14 6 ms -> 99 ms.)
+    Arena big{nullptr, 0, 0};
+    std::atomic<int> big_state{0};             // 0 none, 2 ready
+    void prepare_big(size_t bytes) {
+        if (bytes == 0 || big_state.load() != 0) return;
+        bytes = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        int kind = PINNED;
+        void *p = map_and_register(bytes, kind);
+        if (kind != PINNED) {
+            munmap(p, bytes);
+            throw Failure(STCSP_ERR_CUDA, "cannot pin the host arena");
+        }
+        std::lock_guard<std::mutex> g(mu);
+        big = Arena{(char *)p, bytes, 0};
+        arenas.push_back(Arena{(char *)p, bytes, bytes});      // (known to release_all; nothing small is carved out of it)
+        big_state.store(2, std::memory_order_release);
     }
     void give_back(void *p, size_t bytes, int kind) {
         if (kind == PAGEABLE) { munmap(p, bytes); return; }
@@ -2858,6 +2891,27 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
     if (rc == STCSP_OK) out->wall_ms = (now_s() - t0) * 1e3;
     else stcsp_automaton_free(out);
     return rc;
+}
+
+int stcsp_gpu_warmup(int32_t device, int64_t pinned_bytes) {
+    // everything a first call would otherwise pay for: context, kernel modules, streams, the first device and pinned
+    // arenas (one solve of a two-state model walks through all of it), then the host arena for results
+    stcsp_model_t *m = nullptr;
+    int rc = stcsp_model_parse_text("var X : [0, 1];\nnext X == 1 - X;\n", 0, &m);
+    if (rc != STCSP_OK) return rc;
+    stcsp_options_t opt;
+    memset(&opt, 0, sizeof opt);
+    opt.device = device;
+    stcsp_automaton_t a;
+    rc = stcsp_gpu_solve(stcsp_model_problem(m), &opt, &a);
+    stcsp_model_free(m);
+    if (rc != STCSP_OK) return rc;
+    stcsp_automaton_free(&a);
+    return guarded([&] {
+        preload_search_kernels();
+        preload_automaton_kernels(nullptr);
+        if (pinned_bytes > 0) host_cache().prepare_big((size_t)pinned_bytes);
+    });
 }
 
 void stcsp_automaton_free(stcsp_automaton_t *a) {

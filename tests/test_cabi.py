@@ -57,6 +57,13 @@ def test_solve_without_gpu_fails_loudly():
     assert "no CPU fallback" in str(e.value)
 
 
+@pytest.mark.skipif(binding.lib().stcsp_gpu_device_count() > 0, reason="a GPU is present")
+def test_warmup_without_gpu_fails_loudly():
+    with pytest.raises(binding.StcspError) as e:
+        binding.warmup(-1, 1 << 20)
+    assert e.value.status == binding.ERR_CUDA
+
+
 def test_cli_without_gpu_or_with(tmp_path):
     import subprocess
     p = tmp_path / "m.csp"

@@ -231,6 +231,17 @@ def test_release_caches_then_solve_again():
     assert s1.canonical_sha256() == s2.canonical_sha256() == g["sha256"]
 
 
+def test_warmup_then_results_come_from_the_pinned_arena():
+    """stcsp_gpu_warmup: one-time set-up (context, modules, arenas, pinned host memory for results); solves after it give the
+    same automata, including results larger than what is left of the arena (those are pinned the ordinary way)."""
+    binding.warmup(-1, 8 << 20)
+    binding.warmup(-1, 8 << 20)           # idempotent
+    for name in ("partialorder_11", "partialorder_13", "digitinvader6", "juggling_b5_f6_nosym"):
+        binding.release_caches()
+        _, _, sol = run_gpu(instances.by_name(name))
+        assert sol.canonical_sha256() == GOLDENS[name]["sha256"], name
+
+
 def test_frontier_limit_reports_capacity():
     model = binding.Model(instances.by_name("partialorder_10"))
     with pytest.raises(binding.StcspError) as e:
