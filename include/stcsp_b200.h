@@ -102,9 +102,13 @@ typedef struct stcsp_options {
     int32_t profile_kernels;         /* 1: step-wise path (one expand / route / ingest launch per wave) with every expand launch
                                         timed by CUDA events, instead of the persistent search kernel */
     int32_t no_trim;                 /* 1: stcsp_gpu_solve returns the untrimmed automaton */
-    int32_t lookahead;               /* pointwise constraints at time offsets >= 1: 0 default, 1 eager (propagated like the
-                                        current point, the reference's prefix-k consistency), 2 lazy (checked once, when every
-                                        variable of the current point is bound).  Never changes the automaton. */
+    int32_t lookahead;               /* pointwise constraints at time offsets >= 1: 0 automatic (eager; dropped while 4096 or
+                                        more search nodes have run them, fewer than one in 64 of those failed because of one
+                                        and 1024 complete assignments have been seen -- but for one wave in 13, which keeps
+                                        measuring), 1 eager (propagated like the current
+                                        point, the reference's prefix-k consistency), 2 lazy (checked once, when every variable
+                                        of the current point is bound), 3 never (a dead end is then found one state later and
+                                        removed by the fail rule).  Never changes the automaton. */
     int32_t wide_wave_nodes;         /* waves wider than this run as separate full-occupancy launches instead of inside the
                                         persistent search kernel: 0 = default (32768), < 0 = never */
     int32_t single_branch;           /* 1: a search node branches on ONE variable (the first unbound one), like the reference's

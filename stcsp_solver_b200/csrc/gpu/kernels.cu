@@ -633,7 +633,16 @@ __device__ int scalar_revise(const DevModel &M, const DevSet &S, int q, u64 *dom
             nfree++;
         }
     }
-    if (nfree > 2) return SR_HEAVY;
+    // Three or more unbound prefix variables: the 32-lane walk (revise_table) would only take it on below its enumeration
+    // budget.  Deciding that HERE costs one multiplication per variable; handing it over just to be turned away cost a
+    // microsecond of a warp per propagator and round (digitinvader9: twenty such calls per search node).  A skipped
+    // propagator is re-armed by the next shrink in its scope, as before.
+    if (nfree > 2) {
+        float walk = 1.0f;                              // prefix tuples (exact below 2^24; the comparison is all that is needed)
+        for (int i = 0; i < n; i++)
+            if (i != pv) walk *= (float)__popcll(dom[M.scope[con.scope_off + i] * k + off]);
+        return walk > (float)(off == 0 ? M.enum_now : M.enum_ahead) ? SR_OK : SR_HEAVY;
+    }
     if (nfree == 2 && __popcll(Dy) > __popcll(Dz)) {            // y: the smaller domain, walked in the outer loop
         const u64 td = Dy; Dy = Dz; Dz = td;
         int t = iy; iy = iz; iz = t;
@@ -670,17 +679,21 @@ __device__ __forceinline__ uint32_t cheap_mask(const DevSet &S, int w) {
 //   phase A  rounds of scalar revisions over the dirty cheap propagators, one per thread of the group
 //   phase B  what needs 32 lanes (bytecode enumerations, tables with many unbound variables): warp-cooperative,
 //            one at a time (warp per node) or dealt to the warps of the CTA (CTA per node); then back to A
+//   never       the look-ahead propagators are not run at all (ExpandArgs::skip_ahead)
+//   ahead_fail  out: the wipe-out came from a look-ahead propagator (uniform over the group; only set when true is returned)
 template <bool CTA>
-__device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned &st_rev, unsigned &my_tuples) {
+__device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned &st_rev, unsigned &my_tuples, const bool never,
+                          bool &ahead_fail) {
     const DevModel &M = ctx.M;
     const DevSet &S = ctx.S;
     WarpMem &wm = ctx.wm;
     const int lane = ctx.lane;
     // look-ahead row of the wake table: pointwise propagators at offsets >= 1
     const uint32_t *ahead = M.wake + S.wake_off + (size_t)M.V * M.k * S.n_words;
-    bool held = M.lazy_ahead != 0;                      // look-ahead propagators are held back (uniform over the group)
+    bool held = M.lazy_ahead != 0 || never;             // look-ahead propagators are held back (uniform over the group)
+    ahead_fail = false;
     for (;;) {
-        if (held) {
+        if (held && !never) {
             // released once every variable of the current time point is bound; then all of them run, once
             bool unbound = false;
             for (int v = gtid; v < M.V; v += gthreads) unbound |= __popcll(ctx.dom[v * M.k]) > 1;
@@ -696,7 +709,7 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
         }
         // ---- phase A
         for (;;) {
-            bool myfail = false;
+            bool myfail = false, my_af = false;
             for (int q = gtid; q < S.n_cheap; q += gthreads) {
                 const uint32_t bit = 1u << (q & 31);
                 if (!(wm.dirty[q >> 5] & bit)) continue;
@@ -706,7 +719,7 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                                             // this propagator instead of being erased while it still sees the old domain
                 const int r = scalar_revise(M, S, q, ctx.dom, wm.dirty, ctx.expire, my_tuples, CTA ? kScalarWalkCta : M.scalar_walk);
                 st_rev++;
-                if (r == SR_FAIL) myfail = true;
+                if (r == SR_FAIL) { myfail = true; my_af = (ahead[q >> 5] & bit) != 0u; }
                 else if (r == SR_HEAVY) atomicOr(&wm.hvy[q >> 5], bit);
             }
             bool more, bad;
@@ -720,7 +733,10 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                                                    (wm.dirty[lane] & cheap_mask(S, lane) & (held ? ~ahead[lane] : ~0u)) != 0u);
             }
             dbg_stamp(ctx.dbg, ctx.dbg_cap, 10);           // scalar round done
-            if (bad) return true;
+            if (bad) {
+                ahead_fail = CTA ? __syncthreads_or(my_af) != 0 : __any_sync(0xffffffffu, my_af) != 0;
+                return true;
+            }
             if (!more) break;
         }
         // ---- phase B
@@ -738,7 +754,7 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                 }
             }
             if (q < 0) {                                // fixpoint ...
-                if (!held) return false;
+                if (!held || never) return false;
                 bool unbound = false;                   // ... unless the look-ahead propagators were held and are due now
                 for (int v = lane; v < M.V; v += 32) unbound |= __popcll(ctx.dom[v * M.k]) > 1;
                 if (__any_sync(0xffffffffu, unbound)) return false;
@@ -756,7 +772,10 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
             __syncwarp();
             dbg_stamp(ctx.dbg, ctx.dbg_cap, 30);           // one 32-lane revision done (warp per node)
             st_rev += lane == 0;
-            if (!ok) return true;
+            if (!ok) {
+                ahead_fail = ((ahead[q >> 5] >> (q & 31)) & 1u) != 0u;
+                return true;
+            }
         } else {
             if (threadIdx.x == 0) {
                 int total = 0;
@@ -772,14 +791,14 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
             }
             __syncthreads();
             if (wm.flag[1] == 0) {                      // fixpoint ...
-                if (!held) return false;
+                if (!held || never) return false;
                 bool unbound = false;                   // ... unless the held look-ahead propagators are due now
                 for (int v = gtid; v < M.V; v += gthreads) unbound |= __popcll(ctx.dom[v * M.k]) > 1;
                 if (__syncthreads_or(unbound)) return false;
                 continue;
             }
             int seen_bits = 0;
-            bool ok = true;
+            bool ok = true, my_af = false;
             for (int w = 0; ok && w < S.n_words; w++) {
                 uint32_t bits = wm.dcur[w];
                 while (ok && bits) {
@@ -787,12 +806,16 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                     bits &= bits - 1;
                     if ((seen_bits++ % kExpandWarps) != gw) continue;
                     ok = revise<true>(ctx, w * 32 + b);
+                    if (!ok) my_af = ((ahead[w] >> b) & 1u) != 0u;
                     __syncwarp();
                     st_rev += lane == 0;
                 }
             }
             dbg_stamp(ctx.dbg, ctx.dbg_cap, 20 + (unsigned long long)wm.flag[1]);   // cooperative round done (20 + props)
-            if (__syncthreads_or(!ok)) return true;
+            if (__syncthreads_or(!ok)) {
+                ahead_fail = __syncthreads_or(my_af) != 0;
+                return true;
+            }
         }
     }
 }
@@ -876,6 +899,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
     const int gw = CTA ? warp : 0;                      // this warp's index among them
     const int gtid = CTA ? threadIdx.x : lane, gthreads = gwarps * 32;
     unsigned st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;    // per launch and thread
+    unsigned st_an = 0, st_af = 0;                      // nodes that ran their look-ahead propagators / failed because of one
     unsigned long long st_dom = 0;                      // fused leaves that hit an existing state
     // stage the constraint set of this CTA's first node (waves are almost always homogeneous)
     const long long probe = CTA ? (long long)blockIdx.x : (long long)blockIdx.x * kExpandWarps;
@@ -905,7 +929,12 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
         for (int w = gtid; w < S.n_words; w += gthreads) wm.dirty[w] = initial_dirty(M, S, bvar, w);
         if (CTA) __syncthreads(); else __syncwarp();
 
-        if (!fail) fail = propagate<CTA>(ctx, gw, gtid, gthreads, st_rev, my_tuples);   // `fail` is uniform over the group
+        const bool never = P.skip_ahead != 0;
+        bool ahead_fail = false;
+        if (!fail) {
+            fail = propagate<CTA>(ctx, gw, gtid, gthreads, st_rev, my_tuples, never, ahead_fail);   // `fail` is uniform over the group
+            if (gw == 0 && !never) { st_an++; st_af += fail && ahead_fail; }
+        }
         dbg_stamp(dbg, P.dbg_cap, 2);                   // propagated
         st_tuples += ctx.tuples;
         if (gw == 0) st_nodes++;
@@ -1033,6 +1062,10 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
         if (st_rev) atomicAdd(&P.counters[C_REVISIONS], (unsigned long long)st_rev);
     }
     if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+    if (lane == 0 && st_an && P.ahead_stats != nullptr) {
+        atomicAdd(&P.ahead_stats[C_AHEAD_NODES], (unsigned long long)st_an);
+        if (st_af) atomicAdd(&P.ahead_stats[C_AHEAD_FAILS], (unsigned long long)st_af);
+    }
 }
 
 // ---- wide waves: FOUR search nodes per warp, eight lanes each ----------------------------------------------------
@@ -1046,6 +1079,7 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
     const long long n_in = P.n_in;
     const int V = Mg.V, k = Mg.k, NW = Mg.node_words;
     unsigned st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;    // per launch and thread
+    unsigned st_an = 0, st_af = 0;                      // nodes that ran their look-ahead propagators / failed because of one
     const long long probe = (long long)blockIdx.x * kExpandWarps * 4;
     const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1, resident);
     const DevModel &Ms = *reinterpret_cast<const DevModel *>(stage_base(smem, Mg));
@@ -1076,19 +1110,24 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
         __syncwarp();
 
         // ---- propagate the four nodes in lock step (the host never picks this mode with lazy look-ahead)
-        bool done = !have || fail;
+        // never: this group's node does not run its look-ahead propagators (ExpandArgs::skip_ahead); their dirty bits stay set
+        // and are masked out wherever work is looked for
+        const bool never = P.skip_ahead != 0;
+        const uint32_t *ahead = M.wake + S.wake_off + (size_t)V * k * S.n_words;
+        bool done = !have || fail, ahead_fail = false;
         for (;;) {
             // phase A: one scalar round for every group that still has cheap work
-            bool myfail = false;
+            bool myfail = false, my_af = false;
             if (!done) {
                 for (int q = gl; q < S.n_cheap; q += 8) {
                     const uint32_t bit = 1u << (q & 31);
                     if (!(wm.dirty[q >> 5] & bit)) continue;
+                    if (never && (ahead[q >> 5] & bit)) continue;
                     atomicAnd(&wm.dirty[q >> 5], ~bit);
                     __threadfence_block();  // as in propagate(): clear the bit, THEN read the domains
                     const int r = scalar_revise(M, S, q, dom, wm.dirty, expire, my_tuples, kScalarWalk);
                     st_rev++;
-                    if (r == SR_FAIL) myfail = true;
+                    if (r == SR_FAIL) { myfail = true; my_af = (ahead[q >> 5] & bit) != 0u; }
                     else if (r == SR_HEAVY) atomicOr(&wm.hvy[q >> 5], bit);
                 }
             }
@@ -1096,15 +1135,16 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
             bool p_more = false, p_heavy = false;
             if (!done) {
                 for (int w = gl; w < S.n_words; w += 8) {
-                    const uint32_t cm = cheap_mask(S, w);
-                    p_more |= (wm.dirty[w] & cm) != 0u;
-                    p_heavy |= (wm.hvy[w] | (wm.dirty[w] & ~cm)) != 0u;
+                    const uint32_t cm = cheap_mask(S, w), keep = never ? ~ahead[w] : ~0u;
+                    p_more |= (wm.dirty[w] & cm & keep) != 0u;
+                    p_heavy |= ((wm.hvy[w] | (wm.dirty[w] & ~cm)) & keep) != 0u;
                 }
             }
             const unsigned bf = __ballot_sync(0xffffffffu, myfail);
             const unsigned bm = __ballot_sync(0xffffffffu, p_more);
             const unsigned bh = __ballot_sync(0xffffffffu, p_heavy);
-            if (!done && (bf & gmask)) { fail = true; done = true; }
+            const unsigned ba = __ballot_sync(0xffffffffu, my_af);
+            if (!done && (bf & gmask)) { fail = true; done = true; ahead_fail = (ba & gmask) != 0u; }
             const bool more = !done && (bm & gmask) != 0u;
             const bool heavy = !done && !more && (bh & gmask) != 0u;
             if (!done && !more && !heavy) done = true;          // this node is at its fixpoint
@@ -1119,9 +1159,12 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
                 const int cq = wq.nodew[1];
                 const DevModel &Mq = cq == staged ? Ms : Mg;
                 const DevSet Sq = Mg.sets[cq];
+                const uint32_t *aheadq = Mq.wake + Sq.wake_off + (size_t)V * k * Sq.n_words;
+                const bool neverq = __shfl_sync(0xffffffffu, (int)never, gg * 8) != 0;
                 int q = -1;
                 for (int base = 0; base < Sq.n_words; base += 32) {
-                    const uint32_t w = base + lane < Sq.n_words ? (wq.hvy[base + lane] | (wq.dirty[base + lane] & ~cheap_mask(Sq, base + lane))) : 0u;
+                    uint32_t w = base + lane < Sq.n_words ? (wq.hvy[base + lane] | (wq.dirty[base + lane] & ~cheap_mask(Sq, base + lane))) : 0u;
+                    if (neverq && base + lane < Sq.n_words) w &= ~aheadq[base + lane];
                     const unsigned b = __ballot_sync(0xffffffffu, w != 0u);
                     if (b) {
                         const int l = __ffs(b) - 1;
@@ -1144,12 +1187,16 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
                 __syncwarp();
                 st_rev += lane == 0;
                 st_tuples += cx.tuples;
-                if (!ok && g == gg) { fail = true; done = true; }
+                if (!ok && g == gg) { fail = true; done = true; ahead_fail = ((aheadq[q >> 5] >> (q & 31)) & 1u) != 0u; }
             }
         }
 
         // ---- emit: eight lanes per node
-        if (have && gl == 0) { st_nodes++; st_fails += fail; }
+        if (have && gl == 0) {
+            st_nodes++;
+            st_fails += fail;
+            if (!never) { st_an++; st_af += fail && ahead_fail; }
+        }
         const bool live = have && !fail;
         int bv = -1;
         for (int base = 0; base < V; base += 8) {               // uniform trip count
@@ -1213,6 +1260,12 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
     st_nodes = __reduce_add_sync(0xffffffffu, st_nodes);
     st_fails = __reduce_add_sync(0xffffffffu, st_fails);
     st_tuples += __reduce_add_sync(0xffffffffu, my_tuples);
+    st_an = __reduce_add_sync(0xffffffffu, st_an);
+    st_af = __reduce_add_sync(0xffffffffu, st_af);
+    if (lane == 0 && st_an && P.ahead_stats != nullptr) {
+        atomicAdd(&P.ahead_stats[C_AHEAD_NODES], (unsigned long long)st_an);
+        if (st_af) atomicAdd(&P.ahead_stats[C_AHEAD_FAILS], (unsigned long long)st_af);
+    }
     if (lane == 0 && (st_nodes | st_tuples | st_rev)) {
         if (st_nodes) atomicAdd(&P.counters[C_NODES], (unsigned long long)st_nodes);
         if (st_fails) atomicAdd(&P.counters[C_FAILS], (unsigned long long)st_fails);
@@ -1798,6 +1851,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             A.counters[threadIdx.x] = A.counters[s_set * kCounterStride + threadIdx.x];
         // host mirror of counter set 0 (the threads that may just have copied a word read that word back: program order)
         if (A.h_counters != nullptr && threadIdx.x < C_COUNT) A.h_counters[threadIdx.x] = tot[threadIdx.x];
+        if (A.h_counters != nullptr && threadIdx.x >= C_AHEAD_NODES && threadIdx.x <= C_AHEAD_FAILS)
+            A.h_counters[kHostAheadWord + threadIdx.x - C_AHEAD_NODES] = tot[threadIdx.x];
         if (threadIdx.x == 0) {
             SearchCtl c;
             c.status = st;
@@ -1881,6 +1936,15 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             ea.counters = A.counters + set * kCounterStride;
             ea.dbg = A.trace ? A.trace + 5 * A.trace_cap : nullptr;     // block 0's timeline follows the per-wave stamps
             ea.dbg_cap = A.trace ? 4096 : 0;
+            // Look-ahead propagators: dropped while kAheadSample or more nodes have run them, fewer than one in kAheadRatio of
+            // those failed because of one and kAheadLeaves leaves have been seen (ahead_droppable) -- but for one WAVE in
+            // kAheadWavePeriod, which runs them in all its nodes and keeps the two totals alive.  (Sampling single nodes of a
+            // wave does not pay: a narrow wave lasts as long as its slowest node.)  The blocks agree (the totals are only
+            // written during expand, and this is read between two grid barriers), though nothing depends on that.
+            ea.ahead_stats = A.ahead_policy == 1 ? A.counters : nullptr;
+            ea.skip_ahead = A.ahead_policy == 2 ||
+                            (A.ahead_policy == 1 && !ahead_sample_wave(A.waves0 + cs[S_WAVES]) &&
+                             ahead_droppable((long long)tot[C_AHEAD_NODES], (long long)tot[C_AHEAD_FAILS], A.leaves0 + cs[S_LEAVES]));
             // Narrow waves (a CTA or a warp per node): the warp that finds a leaf routes and merges it at once, while the
             // other nodes of the wave are still being propagated -- one grid barrier per wave, and the leaf's chain of
             // dependent L2 round trips is hidden behind the slowest node.  Only when the wave cannot overflow the output

@@ -37,6 +37,10 @@ enum Counter : int {
     C_OWNER0,          // C_OWNER0 + r: routed leaves owned by rank r
     C_COUNT = C_OWNER0 + 16
 };
+// Two more running totals behind the counters proper, in set 0 (never cleared between waves): search nodes that ran their
+// look-ahead propagators, and how many of those FAILED because of one (search_kernel's automatic look-ahead policy).
+constexpr int C_AHEAD_NODES = 28, C_AHEAD_FAILS = 29;
+static_assert(C_COUNT <= C_AHEAD_NODES, "the look-ahead totals live behind the counters");
 constexpr int kCounterStride = 32;      // the session's counter block holds three sets (see search_kernel)
 constexpr int kCounterSets = 3;
 constexpr int kMaxWorld = 16;
@@ -89,6 +93,12 @@ struct ExpandArgs {
     unsigned long long *counters;
     unsigned long long *dbg;    // optional timeline of block 0 (CTA mode): dbg[0] = entries used, then (tag, %globaltimer) pairs
     int dbg_cap;
+    // Look-ahead propagators (pointwise constraints at time offsets >= 1) only ever detect a dead end one state early: a
+    // successor's first node is rebuilt from its signature, not from the offset-1 domains, and states without a way on are
+    // removed by the fail rule anyway.  0: run them (or hold them until the point is bound, DevModel::lazy_ahead);
+    // 1: skip them in every node of this wave.  Never changes the automaton.
+    int skip_ahead;
+    unsigned long long *ahead_stats;    // set 0 of the counter block (C_AHEAD_NODES / C_AHEAD_FAILS), or null: do not count
     // search_kernel, narrow waves: a node that turns out to be a leaf is routed and merged into the automaton right away by
     // the warp that found it (no leaf phase, no second grid barrier); null in the stand-alone expand kernels
     const struct RouteArgs *fuse_route;
@@ -190,12 +200,26 @@ struct SearchArgs {
     int32_t *edge_src, *edge_dst, *edge_label;
     long long edge_cap;
     int32_t fuse_leaves;                // 1: narrow waves route and merge their leaves inside expand (see search_kernel)
+    int32_t ahead_policy;               // look-ahead propagators: 0 always run, 1 automatic (ahead_droppable; sampled on), 2 never run
+    long long leaves0, waves0;          // complete assignments found / waves run before this launch
     long long max_frontier;             // > 0: yield to the host when a wave is wider (it gives up, or runs the wave step-wise)
     FinishArgs fin;
     unsigned long long *trace;          // optional: 5 %globaltimer stamps per wave (start, expanded, routed, ingested, end)
     long long trace_cap;                // in waves
 };
 
+constexpr long long kAheadSample = 4096;   // nodes that must have run their look-ahead propagators in vain before the
+                                           // automatic policy drops them (juggling_b6_f6_nosym, 3 913 nodes, never gets there:
+                                           // its failures come in the last two waves, and they ARE look-ahead failures)
+constexpr long long kAheadRatio = 64;
+constexpr long long kAheadLeaves = 1024;   // ... and complete assignments seen before: the sample must cover search trees down to their
+                                           // leaves (juggling_b7_f7_nosym fails nothing for five waves and a third of its nodes after)
+__host__ __device__ inline bool ahead_droppable(long long ahead_nodes, long long ahead_fails, long long leaves) {
+    return ahead_nodes >= kAheadSample && leaves >= kAheadLeaves && ahead_fails * kAheadRatio < ahead_nodes;
+}
+constexpr long long kAheadWavePeriod = 13; // one wave in thirteen keeps running them (odd: chains alternate branching and leaf waves)
+__host__ __device__ inline bool ahead_sample_wave(long long wave) { return wave % kAheadWavePeriod == kAheadWavePeriod - 1; }
+constexpr int kHostAheadWord = 256;        // where the two look-ahead totals are mirrored in the session's pinned counter block
 constexpr int kExpandWarps = 8;      // warps per CTA of the expand kernel (measured: 4 warps x 6 CTAs per SM is a wash)
 constexpr int kExpandCtasPerSm = 3;  // resident CTAs the launch bounds allow for (24 warps per SM, 80 registers per thread)
 

@@ -799,11 +799,16 @@ struct stcsp_session {
     }
 
     void zero_wave_counters() {
-        // all three sets of wave counters (search_kernel rotates through them; everything else uses set 0)
-        CK(cudaMemsetAsync(counters.p + C_OUT, 0, (kCounterSets * kCounterStride - C_OUT) * sizeof(unsigned long long), stream));
+        // all three sets of wave counters (search_kernel rotates through them; everything else uses set 0); the words behind
+        // C_COUNT -- the look-ahead totals of set 0 -- live as long as the solve
+        CK(cudaMemset2DAsync(counters.p + C_OUT, kCounterStride * sizeof(unsigned long long), 0,
+                             (C_COUNT - C_OUT) * sizeof(unsigned long long), kCounterSets, stream));
     }
     void read_counters() {
         CK(cudaMemcpyAsync(h_counters, counters.p, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        if (opt.lookahead == 0)     // the look-ahead totals behind the counters (automatic policy, see expand())
+            CK(cudaMemcpyAsync(h_counters + kHostAheadWord, counters.p + C_AHEAD_NODES, 2 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         d2h += C_COUNT * 8;
     }
@@ -878,6 +883,7 @@ struct stcsp_session {
         CK(cudaMemsetAsync(counters.p, 0, kCounterSets * kCounterStride * sizeof(unsigned long long), stream));
         counters_fresh = true;
         h_counters = pinned_cache().acquire();       // C_COUNT counters + room for the search control block
+        h_counters[kHostAheadWord] = h_counters[kHostAheadWord + 1] = 0;     // (the block is recycled)
         {
             void *d = nullptr;
             static const bool no_push = getenv("STCSP_NO_PUSH") != nullptr;       // A/B timing
@@ -979,6 +985,9 @@ struct stcsp_session {
             sa.edge_label = edge_label.p;
             sa.edge_cap = (long long)std::min(edge_src.cap, edge_label.cap / (size_t)V);
             sa.fuse_leaves = (dm.dbg_flags & 1) ? 0 : 1;        // STCSP_DBG_FLAGS=1: the separate leaf phase on every wave (A/B timing)
+            sa.ahead_policy = opt.lookahead == 3 ? 2 : opt.lookahead == 0 ? 1 : 0;     // 0 (default): automatic, see search_kernel
+            sa.leaves0 = t_leaves;
+            sa.waves0 = t_waves;
             const long long wide = opt.wide_wave_nodes < 0 ? 0 : opt.wide_wave_nodes > 0 ? opt.wide_wave_nodes : kWideWaveNodes;
             sa.max_frontier = opt.max_frontier_nodes > 0 && (wide == 0 || opt.max_frontier_nodes < wide) ? opt.max_frontier_nodes : wide;
             // An instance whose waves stay narrow gets one CTA per SM: with a third of the CTAs the grid barrier is cheaper
@@ -1265,6 +1274,11 @@ struct stcsp_session {
                 ea.leaf_cap = (long long)(leaves.cap / RW);
                 ea.fan = branch_fan(dm, n_in, ea.out_cap);
                 ea.counters = counters.p;
+                // look-ahead propagators: the same automatic policy as inside search_kernel, from the totals of the last read-back
+                ea.ahead_stats = opt.lookahead == 0 ? counters.p : nullptr;
+                ea.skip_ahead = opt.lookahead == 3 ||
+                                (opt.lookahead == 0 && !ahead_sample_wave(t_waves) &&
+                                 ahead_droppable((long long)h_counters[kHostAheadWord], (long long)h_counters[kHostAheadWord + 1], t_leaves));
                 // narrow wave: a whole CTA per node (intra-node parallelism); wide wave: a warp per node
                 const int mode = pick_expand_mode(dm, n_in, expand_grid_max);
                 const int grid = mode == EXPAND_CTA ? (int)std::min<long long>(n_in, expand_grid_max)

@@ -25,7 +25,8 @@ def test_random_model_matches_oracle(seed):
         TALLY["oracle_slow"] += 1
         pytest.skip("oracle needs more than 2 s")
     want = binding.Solution(model, oracle_automaton).canonical_text()
-    variants = [dict(), dict(lookahead=2), dict(profile_kernels=1), dict(enum_limit_now=4096, enum_limit_ahead=4096),
+    variants = [dict(), dict(lookahead=2), dict(lookahead=3), dict(lookahead=3, expand_mode=3), dict(lookahead=1), dict(profile_kernels=1),
+                dict(lookahead=3, profile_kernels=1), dict(enum_limit_now=4096, enum_limit_ahead=4096),
                 dict(expand_mode=3), dict(expand_mode=1), dict(expand_mode=2, profile_kernels=1), dict(expand_mode=3, profile_kernels=1),
                 dict(wide_wave_nodes=2), dict(wide_wave_nodes=8, expand_mode=3), dict(wide_wave_nodes=-1)]
     for kw in [variants[0], variants[1 + seed % (len(variants) - 1)]]:

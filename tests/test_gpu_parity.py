@@ -78,6 +78,19 @@ def test_matches_reference_golden(key):
         assert canonical.canonical_sha256(sol.to_python()) == g["sha256"]
 
 
+@pytest.mark.parametrize("lookahead", [1, 3])
+@pytest.mark.parametrize("key", [k for k in CASES if GOLDENS[k].get("edges", 0) <= 400_000])
+def test_lookahead_policy_does_not_change_the_automaton(key, lookahead):
+    """Pointwise constraints at time offsets >= 1 only find a dead end one state early (stcsp_options_t::lookahead): always run
+    (1) or never run (3; the default drops them by itself when they never fail anything), the automaton is the reference's --
+    dead ends are then created as states and removed by the fail rule (reference src/solveralgorithm.cpp:904-910)."""
+    g = GOLDENS[key]
+    flags = golden_flags(g)
+    _, _, sol = run_gpu(golden_text(g), flags, lookahead=lookahead)
+    assert (sol.n_states, sol.n_edges) == (g["states"], g["edges"])
+    assert sol.canonical_sha256_streamed() == g["sha256"]
+
+
 SMALL = [k for k in CASES if GOLDENS[k].get("wall_s", 99) <= 1.0]
 
 
@@ -109,8 +122,13 @@ def test_stepwise_path_equals_persistent_kernel(name):
     """profile_kernels=1 runs one expand / route / ingest launch per wave (the path the multi-GPU sessions use);
     the default is the persistent search kernel.  Same automaton, same search statistics."""
     g = GOLDENS[name]
-    _, a1, s1 = run_gpu(golden_text(g))
-    _, a2, s2 = run_gpu(golden_text(g), (), profile_kernels=1)
+    _, _, s0 = run_gpu(golden_text(g))
+    _, _, s3 = run_gpu(golden_text(g), (), profile_kernels=1)
+    assert s0.canonical_sha256() == s3.canonical_sha256() == g["sha256"]
+    # (statistics: with the look-ahead propagators always on -- the automatic policy samples by node index and decides from
+    #  running totals, so the two paths need not drop them for the same nodes)
+    _, a1, s1 = run_gpu(golden_text(g), (), lookahead=1)
+    _, a2, s2 = run_gpu(golden_text(g), (), profile_kernels=1, lookahead=1)
     assert s1.canonical_sha256() == s2.canonical_sha256() == g["sha256"]
     st1, st2 = a1.stats(), a2.stats()
     for key in ("n_states", "n_edges", "n_search_nodes", "n_fails", "n_leaves", "n_waves"):
@@ -134,8 +152,11 @@ def test_wide_waves_leaving_the_persistent_kernel(name, wide):
     """wide_wave_nodes: waves wider than this run as stand-alone launches between two runs of the search kernel;
     the automaton and the search statistics do not depend on where the switch happens."""
     g = GOLDENS[name]
-    _, base, _ = run_gpu(golden_text(g), ())
-    _, automaton, sol = run_gpu(golden_text(g), (), wide_wave_nodes=wide)
+    _, _, sol = run_gpu(golden_text(g), (), wide_wave_nodes=wide)
+    assert sol.canonical_sha256() == g["sha256"], (name, wide)
+    # (statistics with the look-ahead propagators always on: the automatic policy decides from running totals)
+    _, base, _ = run_gpu(golden_text(g), (), lookahead=1)
+    _, automaton, sol = run_gpu(golden_text(g), (), wide_wave_nodes=wide, lookahead=1)
     assert sol.canonical_sha256() == g["sha256"], (name, wide)
     st0, st1 = base.stats(), automaton.stats()
     for key in ("n_states", "n_edges", "n_search_nodes", "n_fails", "n_leaves", "n_dominance", "n_waves"):
