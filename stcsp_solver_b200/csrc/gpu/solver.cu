@@ -1444,7 +1444,9 @@ struct stcsp_session {
         pending.clear();
     }
 
-    void outbox(int32_t *outbox_dev, int64_t capacity, int64_t *counts) {
+    // wait: the records are in place when this returns (the step-wise C API promises that); the group's wave loop passes
+    // false -- its exchange kernel follows on the same stream, and that is all the ordering the peers need
+    void outbox(int32_t *outbox_dev, int64_t capacity, int64_t *counts, bool wait = true) {
         if (n_unres > 0) throw Failure(STCSP_ERR_INVALID, "outbox called with unresolved leaves pending");
         long long off[2 * kMaxWorld] = {0};
         long long total = 0;
@@ -1460,7 +1462,7 @@ struct stcsp_session {
         launch_scatter(dm, leaves.p, n_leaves, d_offsets.p, reinterpret_cast<unsigned long long *>(d_offsets.p + kMaxWorld),
                        outbox_dev, (int)std::min<long long>((n_leaves + 7) / 8, sm_count * 8), stream);
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(stream));
+        if (wait) CK(cudaStreamSynchronize(stream));
         t_launches++;
     }
 
@@ -2284,7 +2286,7 @@ void run_sharded(stcsp_session &s, stcsp_group &g, bool trim, stcsp_automaton_t 
                     DBuf<int32_t> &ob = outbox[wave & 1];
                     ob.reserve((size_t)s.n_leaves * RW, 0, s.stream);
                     int64_t counts[kMaxWorld] = {0};
-                    s.outbox(ob.p, (int64_t)(ob.cap / RW), counts);
+                    s.outbox(ob.p, (int64_t)(ob.cap / RW), counts, false);
                     long long off = 0;
                     for (int q = 0; q < W; q++) {
                         row[H_COUNT0 + q] = counts[q];
@@ -2304,7 +2306,9 @@ void run_sharded(stcsp_session &s, stcsp_group &g, bool trim, stcsp_automaton_t 
                 row[H_MODEL_SETS] = start_sets;
                 row[H_MODEL_CAPS] = start_caps;
             }
-            CK(cudaStreamSynchronize(s.stream));            // the outbox is complete before anybody is told about it
+            // the outbox is complete before anybody is told about it: the exchange kernel runs behind the scatter on this
+            // stream (and fences before it raises its flags); only the meeting in host memory needs the host to wait
+            if (g.host_exchange) CK(cudaStreamSynchronize(s.stream));
             const long long *rows = g.exchange(row, s.stream);
             if (wave == 0)          // set ids travel in the records: every rank must have started from the same numbering
                 for (int q = 0; q < W; q++)
@@ -2337,7 +2341,7 @@ void run_sharded(stcsp_session &s, stcsp_group &g, bool trim, stcsp_automaton_t 
                 memset(row, 0, sizeof row);
                 row[H_N_IN] = 1;                            // (only the sum matters, and it was not zero)
                 publish_outbox();
-                CK(cudaStreamSynchronize(s.stream));
+                if (g.host_exchange) CK(cudaStreamSynchronize(s.stream));
                 rows = g.exchange(row, s.stream);
             }
             stcsp_session::PullSegs segs;
