@@ -1526,7 +1526,11 @@ __device__ __forceinline__ void ingest_leaf(const DevModel &M, const IngestArgs 
         if (lane == 0) atomicOr(&P.counters[C_OVERFLOW], 8ull);
         return;
     }
-    if (lane == 0) { P.edge_src[e] = src; P.edge_dst[e] = dst_global; }
+    if (lane == 0) {
+        P.edge_src[e] = src;
+        P.edge_dst[e] = dst_global;
+        if (P.deg != nullptr && src < P.deg_cap) atomicAdd(&P.deg[src], 1);
+    }
     for (int v = lane; v < V; v += 32) P.edge_label[e * V + v] = rec[4 + v];
 }
 
@@ -1751,7 +1755,11 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
             if ((long long)e >= P.edge_cap) {
                 if (gl == 0) atomicOr(&P.counters[C_OVERFLOW], 8ull);
             } else {
-                if (gl == 0) { P.edge_src[e] = rec[0]; P.edge_dst[e] = dst_global; }
+                if (gl == 0) {
+                    P.edge_src[e] = rec[0];
+                    P.edge_dst[e] = dst_global;
+                    if (P.deg != nullptr && rec[0] < P.deg_cap) atomicAdd(&P.deg[rec[0]], 1);
+                }
                 for (int v = gl; v < V; v += 8) P.edge_label[e * V + v] = rec[4 + v];
             }
         }
@@ -1834,6 +1842,12 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             A.table[(long long)mix32(h) & A.table_mask] = 0;
         }
         __threadfence();
+    }
+    if (A.make_root && A.fin.deg != nullptr && A.fin.deg_counted) {
+        // out-degrees are counted while the edges are appended (IngestArgs::deg): start from zero.  No edge is appended
+        // before the grid barrier of wave 0 (its leaves, if the root is one, are not fused -- see `fuse` below).
+        const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long long)gridDim.x * blockDim.x;
+        for (long long i = gtid; i <= A.fin.cap_states; i += gsize) { A.fin.deg[i] = 0; A.fin.cursor[i] = 0; }
     }
     if (threadIdx.x == 0) {
         s_resident = -1;
@@ -1952,7 +1966,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             // never on the quad-mode waves, whose leaf phase overlaps four chains per warp anyway.
             const int wmode = pick_expand_mode(M, c_n_in, gridDim.x);
             const long long per_node = ea.fan > 64 ? ea.fan : 64;
-            const int fuse = st == SEARCH_RUN && A.fuse_leaves && wmode != EXPAND_QUAD && c_n_in * per_node <= A.out_cap;
+            const int fuse = st == SEARCH_RUN && A.fuse_leaves && wmode != EXPAND_QUAD && c_n_in * per_node <= A.out_cap &&
+                             !(A.make_root && cs[S_WAVES] == 0);
             s_fuse = fuse;
             ea.fuse_route = nullptr;
             ea.fuse_ingest = nullptr;
@@ -1983,6 +1998,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
                 s_ia.totals = A.counters;
                 s_ia.n_segs = 0;
                 s_ia.fused = 1;
+                s_ia.deg = A.fin.deg_counted ? A.fin.deg : nullptr;
+                s_ia.deg_cap = A.fin.cap_states;
                 ea.fuse_route = &s_ra;
                 ea.fuse_ingest = &s_ia;
             }
@@ -1997,6 +2014,84 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             const int V = M.V, KW = M.key_words;
             const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long long)gridDim.x * blockDim.x;
             const int lane = threadIdx.x & 31;
+            // (this launch's dynamic shared memory = expand_smem_bytes(M); nobody is using it any more)
+            const size_t smem_bytes = node_bytes(M) * M.node_slots + scratch_bytes(M) * kExpandWarps + align8(sizeof(DevModel)) +
+                                      align8((size_t)M.stage_bytes);
+            if (F.deg_counted && (size_t)(ns + 1 + blockDim.x) * 4 <= smem_bytes) {
+                // ---- degrees already counted: EVERY block scans them into its own shared memory, so positions are known
+                // without a grid barrier; when no state is a dead end (nothing to trim) the edges go straight to their final
+                // places, on the device and -- if the host gave pinned buffers -- on the host, and the kernel is done
+                int32_t *first_s = reinterpret_cast<int32_t *>(smem);
+                int32_t *partial = first_s + ns + 1;
+                const int nt = blockDim.x, tid = threadIdx.x;
+                const long long n = ns + 1, chunk = (n + nt - 1) / nt;
+                const long long lo = min((long long)tid * chunk, n), hi = min(lo + chunk, n);
+                int sum = 0;
+                bool dead_end = false;
+                for (long long i = lo; i < hi; i++) {
+                    const int d = i < ns ? F.deg[i] : 0;
+                    first_s[i] = d;
+                    sum += d;
+                    dead_end |= i < ns && d == 0;
+                }
+                partial[tid] = sum;
+                __syncthreads();
+                for (int off = 1; off < nt; off <<= 1) {
+                    const int v = tid >= off ? partial[tid - off] : 0;
+                    __syncthreads();
+                    partial[tid] += v;
+                    __syncthreads();
+                }
+                int run = partial[tid] - sum;
+                for (long long i = lo; i < hi; i++) { const int d = first_s[i]; first_s[i] = run; run += d; }
+                const bool any_dead_end = __syncthreads_or(dead_end && F.do_trim) != 0;     // (the barrier also publishes first_s)
+                if (!any_dead_end && first_s[ns] == (int)ne) {
+                    const bool push = F.h_src != nullptr && ns <= F.h_cap_states && ne <= F.h_cap_edges;
+                    const long long gwarp = gtid >> 5, nwarps = gsize >> 5;
+                    for (long long e = gwarp; e < ne; e += nwarps) {
+                        const int s = A.edge_src[e];
+                        int pos = 0;
+                        if (lane == 0) pos = first_s[s] + atomicAdd(&F.cursor[s], 1);
+                        pos = __shfl_sync(0xffffffffu, pos, 0);
+                        if (lane == 0) {
+                            const int d = A.edge_dst[e];
+                            F.s_src[pos] = s; F.s_dst[pos] = d; F.alive[pos] = 1;
+                            if (push) { F.h_src[pos] = s; F.h_dst[pos] = d; }
+                        }
+                        for (int v = lane; v < V; v += 32) {
+                            const int32_t x = A.edge_label[e * V + v];
+                            F.s_label[(long long)pos * V + v] = x;
+                            if (push) F.h_label[(long long)pos * V + v] = x;
+                        }
+                    }
+                    for (long long i = gtid; i < ns * KW; i += gsize) {
+                        const long long st = i / KW;
+                        const int j = (int)(i % KW), v = A.state_key[i];
+                        if (j == 0) {
+                            F.rows_cset[st] = v < 0 ? 0 : v;
+                            F.failed[st] = 0;
+                            if (push) { F.h_cset[st] = v < 0 ? 0 : v; F.h_failed[st] = 0; }
+                        } else {
+                            F.rows_sig[st * (KW - 1) + (j - 1)] = v;
+                            if (push) F.h_sig[st * (KW - 1) + (j - 1)] = v;
+                        }
+                    }
+                    if (gtid == 0) {
+                        ctl->changed = 0;
+                        ctl->dead_edges = 0;
+                        ctl->finished = 1;
+                        ctl->pad = 1;               // (which finishing path ran: shown at verbosity 1)
+                        if (A.h_ctl != nullptr) {
+                            A.h_ctl->dead_edges = 0;
+                            A.h_ctl->finished = 1;
+                            A.h_ctl->pushed = push ? 1 : 0;
+                            A.h_ctl->pad = 1;
+                        }
+                    }
+                    return;
+                }
+                grid.sync();            // a dead end (or a count that does not add up): the general path below, from scratch
+            }
             for (long long i = gtid; i <= ns; i += gsize) F.deg[i] = 0;
             if (gtid == 0) { ctl->changed = 0; ctl->dead_edges = 0; }
             grid.sync();
@@ -2143,6 +2238,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             ia.totals = A.counters;
             ia.n_segs = 0;
             ia.fused = 0;
+            ia.deg = A.fin.deg_counted ? A.fin.deg : nullptr;
+            ia.deg_cap = A.fin.cap_states;
             if (n_leaves >= 4ll * kExpandWarps * gridDim.x || M.force_mode == EXPAND_QUAD + 1)
                 leaf_body_quad<true, true>(M, ra, ia, n_leaves);    // four leaves per warp
             else leaf_body(M, ra, ia, n_leaves);            // route + ingest in one pass

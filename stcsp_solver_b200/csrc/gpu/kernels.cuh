@@ -134,6 +134,8 @@ struct IngestArgs {
     // PULL mode (multi-GPU, n_segs > 0): `records` is null; record number i is the i-th record of the concatenation of the
     // segments, and segment q lies in the OUTBOX OF RANK q -- peer memory, read over NVLink by the ingesting warps themselves
     // (the exchange and the merge are one kernel; nothing is staged in an inbox).
+    int32_t *deg;                   // optional: out-degree per (local = global, single rank) source state, counted as edges are
+    long long deg_cap;              // appended (FinishArgs::deg_counted); states >= deg_cap are not counted
     int32_t n_segs;
     int32_t fused;                  // 1: called from inside expand (search_kernel, narrow waves): the first nodes of new states
                                     // are appended through expand's own cursor C_OUT (out_base = 0) instead of C_NEW
@@ -175,6 +177,10 @@ struct FinishArgs {
     int32_t *h_cset, *h_sig, *h_src, *h_dst, *h_label;
     uint8_t *h_failed;
     long long h_cap_states, h_cap_edges;
+    // 1: `deg` (zeroed, like `cursor`, by the first launch of the solve) has been counting the out-degree of every state
+    // while the edges were appended (IngestArgs::deg) -- grouping then needs no counting pass and, when no state is a dead
+    // end, no grid barrier at all (every block scans the degrees into its own shared memory)
+    int32_t deg_counted;
 };
 struct SearchArgs {
     SearchCtl *ctl;

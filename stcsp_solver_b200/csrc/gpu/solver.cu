@@ -613,6 +613,10 @@ struct stcsp_session {
     bool search_complete = false;                           // the wave loop ran to the end (max_wave is the instance's)
     bool poisoned = false;          // a pool overflowed in mid-wave (table slots tombstoned, cursors past their capacity):
                                     // unreachable as long as every path pre-reserves n_states + n, fatal for the session if not
+    bool deg_ok = false;            // fb_deg has counted every edge of this solve so far (FinishArgs::deg_counted)
+    const int32_t *deg_ptr = nullptr, *cur_ptr = nullptr;
+    long long deg_cs = 0;
+    bool sa_first_launch_of_solve() const { return root_pending; }
     bool prefinished = false;       // the search kernel already grouped + trimmed (fb_* hold the result)
     long long prefinished_dead = 0;
     // PUSH (FinishArgs::h_*): pinned output buffers handed to the search kernel, which writes a small automaton into them
@@ -1019,6 +1023,11 @@ struct stcsp_session {
                 sa.fin.rows_cset = fb_cset.p; sa.fin.rows_sig = fb_sig.p;
                 sa.fin.cap_states = cs; sa.fin.cap_edges = ce;
                 sa.fin.do_trim = finish_trim ? 1 : 0;
+                // out-degrees counted while the edges are appended: from the first launch of the solve on, as long as these two
+                // blocks stay where they are and every edge is appended by the search kernel itself
+                if (sa_first_launch_of_solve()) { deg_ok = true; deg_ptr = fb_deg.p; cur_ptr = fb_fill.p; deg_cs = cs; }
+                else if (deg_ptr != fb_deg.p || cur_ptr != fb_fill.p || deg_cs != cs) deg_ok = false;
+                sa.fin.deg_counted = deg_ok ? 1 : 0;
                 // PUSH: the last solve of this model returned a small automaton -- pinned output buffers of that size (plus a
                 // margin) go to the kernel, which writes the result into them itself (see FinishArgs)
                 const long long hs = model->hint_out_states, he = model->hint_out_edges;
@@ -1131,9 +1140,10 @@ struct stcsp_session {
             max_wave = std::max<long long>(max_wave, h_ctl->t_max_in);
             if (opt.verbosity > 0)
                 fprintf(stderr, "[stcsp r%d] t=%.3f ms search kernel returned: status %d after %lld waves, n_in %lld, states %llu, edges %llu, "
-                                "out %llu leaves %llu overflow %d\n",
+                                "out %llu leaves %llu overflow %d finished %d (barrier-free %d) pushed %d\n",
                         rank, (now_s() - t_create) * 1e3, h_ctl->status, h_ctl->t_waves, h_ctl->n_in, h_counters[C_STATES],
-                        h_counters[C_EDGES], h_counters[C_OUT], h_counters[C_LEAVES], h_ctl->overflow);
+                        h_counters[C_EDGES], h_counters[C_OUT], h_counters[C_LEAVES], h_ctl->overflow, h_ctl->finished, h_ctl->pad,
+                        h_ctl->pushed);
             if (h_ctl->overflow & ~1) { poisoned = true; throw Failure(STCSP_ERR_CAPACITY, "internal: a pool overflowed inside the search kernel"); }
             n_in = h_ctl->n_in;
             cur = h_ctl->cur;
@@ -1474,6 +1484,7 @@ struct stcsp_session {
     void ingest(const int32_t *inbox, int64_t n, int64_t *frontier_next, const PullSegs *segs = nullptr) {
         if (poisoned) throw Failure(STCSP_ERR_CAPACITY, "session unusable: a pool overflowed in an earlier wave");
         if (n_unres > 0) throw Failure(STCSP_ERR_INVALID, "ingest called with unresolved leaves pending");
+        deg_ok = false;         // edges appended by a stand-alone launch are not counted in fb_deg (FinishArgs::deg_counted)
         const int NW = dm.node_words, KW = dm.key_words, V = dm.V;
         if (segs) {
             n = 0;
