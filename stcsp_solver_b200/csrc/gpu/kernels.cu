@@ -820,6 +820,34 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
     }
 }
 
+// A warp's statistics of one expand pass.  Stand-alone kernels add them to the wave's counters in global memory; inside
+// search_kernel they go to the BLOCK's shared-memory totals, which the block flushes once before the grid barrier: eight
+// times fewer reductions on the few lines every block reads right after that barrier -- the L2 works such a burst off one
+// operation at a time, and the reads queue behind it (3.5 us per wave on juggling_b6_f6_nosym).
+enum BlockStat : int { BS_NODES, BS_FAILS, BS_TUPLES, BS_REV, BS_DOM, BS_AHEAD_NODES, BS_AHEAD_FAILS, BS_COUNT };
+__device__ __forceinline__ void flush_warp_stats(const ExpandArgs &P, unsigned nodes, unsigned fails, unsigned tuples, unsigned rev,
+                                                 unsigned long long dom, unsigned an, unsigned af) {
+    if (P.block_stats != nullptr) {
+        if (nodes) atomicAdd(&P.block_stats[BS_NODES], nodes);
+        if (fails) atomicAdd(&P.block_stats[BS_FAILS], fails);
+        if (tuples) atomicAdd(&P.block_stats[BS_TUPLES], tuples);
+        if (rev) atomicAdd(&P.block_stats[BS_REV], rev);
+        if (dom) atomicAdd(&P.block_stats[BS_DOM], (unsigned)dom);
+        if (an) atomicAdd(&P.block_stats[BS_AHEAD_NODES], an);
+        if (af) atomicAdd(&P.block_stats[BS_AHEAD_FAILS], af);
+        return;
+    }
+    if (nodes) atomicAdd(&P.counters[C_NODES], (unsigned long long)nodes);
+    if (fails) atomicAdd(&P.counters[C_FAILS], (unsigned long long)fails);
+    if (tuples) atomicAdd(&P.counters[C_TUPLES], (unsigned long long)tuples);
+    if (rev) atomicAdd(&P.counters[C_REVISIONS], (unsigned long long)rev);
+    if (dom) atomicAdd(&P.counters[C_DOMINANCE], dom);
+    if (an && P.ahead_stats != nullptr) {
+        atomicAdd(&P.ahead_stats[C_AHEAD_NODES], (unsigned long long)an);
+        if (af) atomicAdd(&P.ahead_stats[C_AHEAD_FAILS], (unsigned long long)af);
+    }
+}
+
 // ---- constraint-set metadata staged in shared memory ------------------------------------------------------
 // The propagators of a set (descriptors, scopes, strides, wake masks, bytecode, variable bounds) are read over and
 // over by every revision; the CTA copies the set most of its nodes belong to into shared memory once per wave and
@@ -1055,17 +1083,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
     // st_rev / my_tuples are per thread (scalar revisions), st_tuples is warp-uniform (cooperative revisions)
     st_rev = __reduce_add_sync(0xffffffffu, st_rev);
     st_tuples += __reduce_add_sync(0xffffffffu, my_tuples);
-    if (lane == 0 && (st_nodes | st_tuples | st_rev)) {
-        if (st_nodes) atomicAdd(&P.counters[C_NODES], (unsigned long long)st_nodes);
-        if (st_fails) atomicAdd(&P.counters[C_FAILS], (unsigned long long)st_fails);
-        if (st_tuples) atomicAdd(&P.counters[C_TUPLES], (unsigned long long)st_tuples);
-        if (st_rev) atomicAdd(&P.counters[C_REVISIONS], (unsigned long long)st_rev);
-    }
-    if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
-    if (lane == 0 && st_an && P.ahead_stats != nullptr) {
-        atomicAdd(&P.ahead_stats[C_AHEAD_NODES], (unsigned long long)st_an);
-        if (st_af) atomicAdd(&P.ahead_stats[C_AHEAD_FAILS], (unsigned long long)st_af);
-    }
+    if (lane == 0) flush_warp_stats(P, st_nodes, st_fails, st_tuples, st_rev, st_dom, P.ahead_stats != nullptr ? st_an : 0u, st_af);
 }
 
 // ---- wide waves: FOUR search nodes per warp, eight lanes each ----------------------------------------------------
@@ -1262,16 +1280,7 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
     st_tuples += __reduce_add_sync(0xffffffffu, my_tuples);
     st_an = __reduce_add_sync(0xffffffffu, st_an);
     st_af = __reduce_add_sync(0xffffffffu, st_af);
-    if (lane == 0 && st_an && P.ahead_stats != nullptr) {
-        atomicAdd(&P.ahead_stats[C_AHEAD_NODES], (unsigned long long)st_an);
-        if (st_af) atomicAdd(&P.ahead_stats[C_AHEAD_FAILS], (unsigned long long)st_af);
-    }
-    if (lane == 0 && (st_nodes | st_tuples | st_rev)) {
-        if (st_nodes) atomicAdd(&P.counters[C_NODES], (unsigned long long)st_nodes);
-        if (st_fails) atomicAdd(&P.counters[C_FAILS], (unsigned long long)st_fails);
-        if (st_tuples) atomicAdd(&P.counters[C_TUPLES], (unsigned long long)st_tuples);
-        if (st_rev) atomicAdd(&P.counters[C_REVISIONS], (unsigned long long)st_rev);
-    }
+    if (lane == 0) flush_warp_stats(P, st_nodes, st_fails, st_tuples, st_rev, 0ull, P.ahead_stats != nullptr ? st_an : 0u, st_af);
 }
 
 __global__ void __launch_bounds__(kExpandWarps * 32, kExpandCtasPerSm) expand_quad_kernel(const DevModel M, const ExpandArgs P) {
@@ -1817,6 +1826,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
     __shared__ RouteArgs s_ra;          // ... with these arguments
     __shared__ IngestArgs s_ia;
     __shared__ int s_resident;          // constraint set whose metadata this CTA holds in shared memory (kept across waves)
+    __shared__ long long s_an, s_af;    // look-ahead totals as of the last wave's end (C_AHEAD_NODES / C_AHEAD_FAILS)
+    __shared__ unsigned s_bstats[BS_COUNT];     // this block's statistics of the running expand pass (flush_warp_stats)
     const bool controller = blockIdx.x == 0 && threadIdx.x == 0;    // the one thread that reports to the host
     auto stamp = [&](int k) {
         if (A.trace != nullptr && controller && cs[S_WAVE] < A.trace_cap) {
@@ -1825,6 +1836,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             A.trace[cs[S_WAVE] * 5 + k] = t;
         }
     };
+    if (controller && A.trace != nullptr) dbg_stamp(A.trace + 5 * A.trace_cap, 4096, 90);     // kernel entered
     if (A.make_root && blockIdx.x == 0) {
         // The root state (signature "S", reference src/solveralgorithm.cpp:951-954) and its search node -- every variable at
         // its declared range at every offset -- written here instead of by three host-to-device copies.  Wave 0 is this one
@@ -1849,6 +1861,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
         const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long long)gridDim.x * blockDim.x;
         for (long long i = gtid; i <= A.fin.cap_states; i += gsize) { A.fin.deg[i] = 0; A.fin.cursor[i] = 0; }
     }
+    if (threadIdx.x < BS_COUNT) s_bstats[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
         s_resident = -1;
         for (int i = 0; i < S_COUNT; i++) cs[i] = 0;
@@ -1857,6 +1870,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
         cs[S_WAVES_LEFT] = A.waves_left0;
         cs[S_STATES] = A.make_root ? 1ll : (long long)tot[C_STATES];
         cs[S_EDGES] = (long long)tot[C_EDGES];
+        s_an = A.make_root || A.ahead_policy != 1 ? 0ll : (long long)tot[C_AHEAD_NODES];
+        s_af = A.make_root || A.ahead_policy != 1 ? 0ll : (long long)tot[C_AHEAD_FAILS];
     }
     // Leave the kernel (all threads call it, every block with the same status).  The host reads set 0.
     auto leave = [&](int st, bool mid_wave) {
@@ -1888,21 +1903,37 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
     __shared__ int s_ovf;
     auto wave_counters = [&](volatile unsigned long long *cnt, bool after_expand) {
         const int ln = threadIdx.x;
-        const unsigned long long c = ln < C_COUNT ? (ln < C_OUT ? tot[ln] : cnt[ln]) : 0ull;
-        const long long v_out = (long long)__shfl_sync(0xffffffffu, c, C_OUT);
-        const long long v_new = (long long)__shfl_sync(0xffffffffu, c, C_NEW);
-        const long long v_nodes = (long long)__shfl_sync(0xffffffffu, c, C_NODES);
-        const long long v_fails = (long long)__shfl_sync(0xffffffffu, c, C_FAILS);
-        const long long v_tuples = (long long)__shfl_sync(0xffffffffu, c, C_TUPLES);
-        const long long v_rev = (long long)__shfl_sync(0xffffffffu, c, C_REVISIONS);
-        const long long v_dom = (long long)__shfl_sync(0xffffffffu, c, C_DOMINANCE);
-        const long long v_ovf = (long long)__shfl_sync(0xffffffffu, c, C_OVERFLOW);
-        const long long v_states = (long long)__shfl_sync(0xffffffffu, c, C_STATES);
-        const long long v_edges = (long long)__shfl_sync(0xffffffffu, c, C_EDGES);
-        const long long v_leaves = (long long)__shfl_sync(0xffffffffu, c, C_LEAVES);
-        const long long v_unres = (long long)__shfl_sync(0xffffffffu, c, C_UNRESOLVED);
-        static_assert(C_COUNT <= 32, "one warp reads all counters");
+        // Every block reads the same few words at the same moment -- right after the grid barrier -- and an L2 slice serves
+        // requests for one line one after the other: with a 64-bit load per counter and lane (30 per block, 4 440 in all) a
+        // block that had waited at the barrier got its values 3.7 us later (the block that arrives last reads before the
+        // others have noticed the release: 0.5 us).  So: 16-byte loads, only of what the block's decisions need (five
+        // requests); the statistics are the controller block's business alone (two more).
+        static_assert(C_STATES == 0 && C_EDGES == 1 && C_OUT == 2 && C_NEW == 3 && C_LEAVES == 4 && C_UNRESOLVED == 5 &&
+                      C_OVERFLOW == 6 && C_NODES == 7 && C_FAILS == 8 && C_TUPLES == 9 && C_REVISIONS == 10 && C_DOMINANCE == 11 &&
+                      C_AHEAD_NODES == 28 && C_AHEAD_FAILS == 29, "pairs of counters are loaded together");
+        const ulonglong2 *pt = reinterpret_cast<const ulonglong2 *>(const_cast<const unsigned long long *>(tot));
+        const ulonglong2 *pc = reinterpret_cast<const ulonglong2 *>(const_cast<const unsigned long long *>(cnt));
+        ulonglong2 c = make_ulonglong2(0ull, 0ull);
+        if (ln == 0) c = __ldcg(pt);                                    // C_STATES, C_EDGES
+        else if (ln <= 3) c = __ldcg(pc + ln);                          // (C_OUT, C_NEW) (C_LEAVES, C_UNRESOLVED) (C_OVERFLOW, C_NODES)
+        else if (ln == 4 && A.ahead_policy == 1) c = __ldcg(pt + 14);   // C_AHEAD_NODES, C_AHEAD_FAILS
+        else if ((ln == 5 || ln == 6) && blockIdx.x == 0) c = __ldcg(pc + ln - 1);     // (C_FAILS, C_TUPLES) (C_REVISIONS, C_DOMINANCE)
+        const long long v_states = (long long)__shfl_sync(0xffffffffu, c.x, 0);
+        const long long v_edges = (long long)__shfl_sync(0xffffffffu, c.y, 0);
+        const long long v_out = (long long)__shfl_sync(0xffffffffu, c.x, 1);
+        const long long v_new = (long long)__shfl_sync(0xffffffffu, c.y, 1);
+        const long long v_leaves = (long long)__shfl_sync(0xffffffffu, c.x, 2);
+        const long long v_unres = (long long)__shfl_sync(0xffffffffu, c.y, 2);
+        const long long v_ovf = (long long)__shfl_sync(0xffffffffu, c.x, 3);
+        const long long v_nodes = (long long)__shfl_sync(0xffffffffu, c.y, 3);
+        const long long v_an = (long long)__shfl_sync(0xffffffffu, c.x, 4);
+        const long long v_af = (long long)__shfl_sync(0xffffffffu, c.y, 4);
+        const long long v_fails = (long long)__shfl_sync(0xffffffffu, c.x, 5);     // (zero in every block but the controller's,
+        const long long v_tuples = (long long)__shfl_sync(0xffffffffu, c.y, 5);    //  which alone reports the statistics: leave())
+        const long long v_rev = (long long)__shfl_sync(0xffffffffu, c.x, 6);
+        const long long v_dom = (long long)__shfl_sync(0xffffffffu, c.y, 6);
         if (ln != 0) return;
+        if (after_expand) { s_an = v_an; s_af = v_af; }
         if (after_expand) {
             // (a fused wave has merged its leaves already; its frontier cannot overflow -- see the guard at wave start -- and if
             //  it did, re-running the wave would duplicate edges: the host is told that a pool overflowed)
@@ -1956,9 +1987,10 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             // wave does not pay: a narrow wave lasts as long as its slowest node.)  The blocks agree (the totals are only
             // written during expand, and this is read between two grid barriers), though nothing depends on that.
             ea.ahead_stats = A.ahead_policy == 1 ? A.counters : nullptr;
+            ea.block_stats = s_bstats;
             ea.skip_ahead = A.ahead_policy == 2 ||
                             (A.ahead_policy == 1 && !ahead_sample_wave(A.waves0 + cs[S_WAVES]) &&
-                             ahead_droppable((long long)tot[C_AHEAD_NODES], (long long)tot[C_AHEAD_FAILS], A.leaves0 + cs[S_LEAVES]));
+                             ahead_droppable(s_an, s_af, A.leaves0 + cs[S_LEAVES]));
             // Narrow waves (a CTA or a warp per node): the warp that finds a leaf routes and merges it at once, while the
             // other nodes of the wave are still being propagated -- one grid barrier per wave, and the leaf's chain of
             // dependent L2 round trips is hidden behind the slowest node.  Only when the wave cannot overflow the output
@@ -2006,6 +2038,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
         }
         __syncthreads();
         if (s_status == SEARCH_DONE) {
+            if (controller && A.trace != nullptr) dbg_stamp(A.trace + 5 * A.trace_cap, 4096, 91);     // search done, finishing begins
             leave(SEARCH_DONE, false);
             // ---- small automaton: group the edges by source and apply the fail rule right here (no further launches)
             const long long ns = (long long)tot[C_STATES], ne = (long long)tot[C_EDGES];
@@ -2077,6 +2110,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
                         }
                     }
                     if (gtid == 0) {
+                        if (A.trace != nullptr) dbg_stamp(A.trace + 5 * A.trace_cap, 4096, 92);       // block 0's share of the finishing done
                         ctl->changed = 0;
                         ctl->dead_edges = 0;
                         ctl->finished = 1;
@@ -2187,7 +2221,19 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
         if (mode == EXPAND_CTA) expand_body<true>(M, ea, smem, &s_resident);
         else if (mode == EXPAND_QUAD) expand_body_quad(M, ea, smem, &s_resident);
         else expand_body<false>(M, ea, smem, &s_resident);
+        // the block's statistics of this pass: one reduction per counter and BLOCK (flush_warp_stats)
+        __syncthreads();
+        if (threadIdx.x < BS_COUNT && s_bstats[threadIdx.x] != 0u) {
+            const int t = threadIdx.x;
+            unsigned long long *dst = t == BS_AHEAD_NODES ? &A.counters[C_AHEAD_NODES] : t == BS_AHEAD_FAILS ? &A.counters[C_AHEAD_FAILS]
+                                    : &ea.counters[t == BS_NODES ? C_NODES : t == BS_FAILS ? C_FAILS : t == BS_TUPLES ? C_TUPLES
+                                                   : t == BS_REV ? C_REVISIONS : C_DOMINANCE];
+            atomicAdd(dst, (unsigned long long)s_bstats[t]);
+            s_bstats[t] = 0u;
+        }
+        if (controller && A.trace != nullptr) dbg_stamp(A.trace + 5 * A.trace_cap, 4096, 96);     // block 0 at the grid barrier
         grid.sync();
+        if (controller && A.trace != nullptr) dbg_stamp(A.trace + 5 * A.trace_cap, 4096, 97);     // ... through it
         stamp(1);
         // the previous wave's counter set is no longer read by anybody: clear it for the wave after this one
         // (the same threads that copy the current set for the host when the kernel leaves in mid-wave: program order)
@@ -2199,8 +2245,11 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
         // Warp 0 reads all counters with one parallel load and publishes what the block needs; on a wave without leaves
         // that load also serves the end-of-wave bookkeeping (nothing changes any more), so such a wave costs one grid
         // barrier and one L2 round trip.
+        if (controller && A.trace != nullptr) dbg_stamp(A.trace + 5 * A.trace_cap, 4096, 93);     // counters cleared
         if (threadIdx.x < 32) wave_counters(cnt, true);
+        if (controller && A.trace != nullptr) dbg_stamp(A.trace + 5 * A.trace_cap, 4096, 94);     // wave counters read
         __syncthreads();
+        if (controller && A.trace != nullptr) dbg_stamp(A.trace + 5 * A.trace_cap, 4096, 95);     // ... and published to the block
         // the frontier buffer overflowed: only scratch was written, the host grows it and the wave runs again
         if (s_ovf) { leave(SEARCH_RETRY, true); return; }
         const long long n_leaves = s_leaves;

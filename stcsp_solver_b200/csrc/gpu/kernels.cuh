@@ -97,6 +97,7 @@ struct ExpandArgs {
     // successor's first node is rebuilt from its signature, not from the offset-1 domains, and states without a way on are
     // removed by the fail rule anyway.  0: run them (or hold them until the point is bound, DevModel::lazy_ahead);
     // 1: skip them in every node of this wave.  Never changes the automaton.
+    unsigned *block_stats;      // search_kernel: the block's shared-memory totals of this pass (see flush_warp_stats); else null
     int skip_ahead;
     unsigned long long *ahead_stats;    // set 0 of the counter block (C_AHEAD_NODES / C_AHEAD_FAILS), or null: do not count
     // search_kernel, narrow waves: a node that turns out to be a leaf is routed and merged into the automaton right away by
