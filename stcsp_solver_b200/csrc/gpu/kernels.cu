@@ -1387,7 +1387,7 @@ __device__ __forceinline__ bool route_leaf(const DevModel &M, const RouteArgs &P
         rec[1] = ncid;
         rec[2] = nexp;
         rec[3] = (int32_t)h;
-        atomicAdd(&P.counters[C_OWNER0 + leaf_owner(M, ncid, h)], 1ull);
+        if (M.world > 1) atomicAdd(&P.counters[C_OWNER0 + leaf_owner(M, ncid, h)], 1ull);      // (who gets how many: sharded searches only)
     }
     __syncwarp();
     return true;

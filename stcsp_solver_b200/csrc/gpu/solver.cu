@@ -1461,7 +1461,7 @@ struct stcsp_session {
         long long off[2 * kMaxWorld] = {0};
         long long total = 0;
         for (int q = 0; q < world; q++) {
-            counts[q] = (int64_t)h_counters[C_OWNER0 + q];
+            counts[q] = world == 1 ? (int64_t)n_leaves : (int64_t)h_counters[C_OWNER0 + q];     // (one rank: route_leaf does not count owners)
             off[q] = total;
             total += counts[q];
         }
