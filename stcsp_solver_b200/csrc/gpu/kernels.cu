@@ -567,8 +567,8 @@ __device__ __forceinline__ bool revise(NodeCtx &c, int q) {
 // Domains are shared by the lanes: every write is an atomicAnd, every wake an atomicOr.
 enum ScalarResult : int { SR_OK = 0, SR_FAIL = 1, SR_HEAVY = 2 };
 constexpr int kScalarWalk = 192;        // longest enumeration (prefix tuples) one thread takes on when nodes are plenty
-constexpr int kScalarWalkCta = 32;      // ... and when a whole CTA works on one node: the slowest thread is the round's
-                                        // duration, so longer walks go to 32 lanes (measured: b6_nosym 0.434 -> 0.404 ms)
+// (DevModel::scalar_walk_cta = 32 when a whole CTA works on one node: the slowest thread is the round's duration, so longer
+//  walks go to 32 lanes; measured again at the end of round 2: 16 / 32 / 64 / 128 -> b5_f6 1.09 / 1.02 / 1.15 / 1.15 ms)
 
 __device__ __forceinline__ bool scalar_shrink(const DevModel &M, const DevSet &S, u64 *dom, uint32_t *dirty, int q, int idx,
                                               u64 nd) {
@@ -717,7 +717,7 @@ __device__ bool propagate(NodeCtx &ctx, int gw, int gtid, int gthreads, unsigned
                 atomicAnd(&wm.dirty[q >> 5], ~bit);
                 __threadfence_block();      // the domains are read AFTER the bit is cleared: a wake that lands in between re-arms
                                             // this propagator instead of being erased while it still sees the old domain
-                const int r = scalar_revise(M, S, q, ctx.dom, wm.dirty, ctx.expire, my_tuples, CTA ? kScalarWalkCta : M.scalar_walk);
+                const int r = scalar_revise(M, S, q, ctx.dom, wm.dirty, ctx.expire, my_tuples, CTA ? M.scalar_walk_cta : M.scalar_walk);
                 st_rev++;
                 if (r == SR_FAIL) { myfail = true; my_af = (ahead[q >> 5] & bit) != 0u; }
                 else if (r == SR_HEAVY) atomicOr(&wm.hvy[q >> 5], bit);
@@ -1872,6 +1872,13 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
         cs[S_EDGES] = (long long)tot[C_EDGES];
         s_an = A.make_root || A.ahead_policy != 1 ? 0ll : (long long)tot[C_AHEAD_NODES];
         s_af = A.make_root || A.ahead_policy != 1 ? 0ll : (long long)tot[C_AHEAD_FAILS];
+    }
+    // A solve starts with ONE node on one block.  The other blocks use the time to stage the root's constraint set (it is every
+    // node's set in most models), so that their first node does not wait for that.  (Pulling small relation tables into every
+    // SM's L1 here as well was measured: no effect.)
+    if (A.make_root && blockIdx.x != 0) {
+        __syncthreads();                        // s_resident = -1 is in place
+        stage_set(M, smem, 0, &s_resident);
     }
     // Leave the kernel (all threads call it, every block with the same status).  The host reads set 0.
     auto leave = [&](int st, bool mid_wave) {

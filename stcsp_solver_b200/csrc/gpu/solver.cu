@@ -772,6 +772,11 @@ struct stcsp_session {
             dm.dbg_flags = flags;
         }
         dm.scalar_walk = 192;
+        dm.scalar_walk_cta = 32;
+        {
+            static const int cta_override = getenv("STCSP_SCALAR_WALK_CTA") ? atoi(getenv("STCSP_SCALAR_WALK_CTA")) : 0;     // tuning experiments
+            if (cta_override > 0) dm.scalar_walk_cta = cta_override;
+        }
         {
             static const int walk_override = getenv("STCSP_SCALAR_WALK") ? atoi(getenv("STCSP_SCALAR_WALK")) : 0;     // tuning experiments
             if (walk_override > 0) dm.scalar_walk = walk_override;
