@@ -389,8 +389,30 @@ struct HostCache {
     struct Arena {
         char *base;
         size_t size, used;
+        char *dev_base = nullptr;       // where the device sees `base` (mapped registration), asked for once per arena
+        bool dev_asked = false;
     };
     std::vector<Arena> arenas;
+    // Device-side address of a pinned block.  Blocks carved out of an arena share its mapping, so the driver is asked once
+    // per arena, not seven times per solve (cudaHostGetDevicePointer is a driver call of about a microsecond).
+    void *device_ptr(void *h) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (Arena &a : arenas)
+                if ((char *)h >= a.base && (char *)h < a.base + a.size) {
+                    if (!a.dev_asked) {
+                        void *d = nullptr;
+                        a.dev_asked = true;
+                        if (cudaHostGetDevicePointer(&d, a.base, 0) == cudaSuccess) a.dev_base = (char *)d;
+                        else cudaGetLastError();
+                    }
+                    return a.dev_base ? a.dev_base + ((char *)h - a.base) : nullptr;
+                }
+        }
+        void *d = nullptr;
+        if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return d;
+    }
     static constexpr size_t kSmall = (size_t)256 << 10;
     static constexpr size_t kFirstArena = (size_t)1 << 20;
     void *acquire(size_t bytes, int &kind) {
@@ -896,8 +918,8 @@ struct stcsp_session {
         {
             void *d = nullptr;
             static const bool no_push = getenv("STCSP_NO_PUSH") != nullptr;       // A/B timing
-            if (!no_push && cudaHostGetDevicePointer(&d, h_counters, 0) == cudaSuccess) host_mirror = (unsigned long long *)d;
-            else cudaGetLastError();
+            if (!no_push) d = host_cache().device_ptr(h_counters);
+            host_mirror = (unsigned long long *)d;
         }
         d_offsets.reserve(2 * kMaxWorld, 0, stream);
 
@@ -1055,7 +1077,7 @@ struct stcsp_session {
                         if (all_pinned) push_store = st; else delete st;
                     }
                     if (push_store) {
-                        auto dev = [&](void *h) { void *d = nullptr; return cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess ? d : nullptr; };
+                        auto dev = [&](void *h) { return host_cache().device_ptr(h); };
                         sa.fin.h_sig = (int32_t *)dev(push_store->state_sig.p);
                         sa.fin.h_cset = (int32_t *)dev(push_store->state_cset.p);
                         sa.fin.h_failed = (uint8_t *)dev(push_store->state_failed.p);
