@@ -931,7 +931,7 @@ __device__ __forceinline__ void expand_body(const DevModel &Mg, const ExpandArgs
     unsigned long long st_dom = 0;                      // fused leaves that hit an existing state
     // stage the constraint set of this CTA's first node (waves are almost always homogeneous)
     const long long probe = CTA ? (long long)blockIdx.x : (long long)blockIdx.x * kExpandWarps;
-    const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1, resident);
+    const int staged = stage_set(Mg, smem, probe < n_in ? (Mg.n_sets == 1 ? 0 : P.in_nodes[probe * NW + 1]) : -1, resident);
     const DevModel &Ms = *reinterpret_cast<const DevModel *>(stage_base(smem, Mg));
     if (blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(P.dbg, P.dbg_cap, 0);     // wave entered, set staged
 
@@ -1099,7 +1099,7 @@ __device__ __forceinline__ void expand_body_quad(const DevModel &Mg, const Expan
     unsigned st_nodes = 0, st_fails = 0, st_tuples = 0, st_rev = 0, my_tuples = 0;    // per launch and thread
     unsigned st_an = 0, st_af = 0;                      // nodes that ran their look-ahead propagators / failed because of one
     const long long probe = (long long)blockIdx.x * kExpandWarps * 4;
-    const int staged = stage_set(Mg, smem, probe < n_in ? P.in_nodes[probe * NW + 1] : -1, resident);
+    const int staged = stage_set(Mg, smem, probe < n_in ? (Mg.n_sets == 1 ? 0 : P.in_nodes[probe * NW + 1]) : -1, resident);
     const DevModel &Ms = *reinterpret_cast<const DevModel *>(stage_base(smem, Mg));
     const long long first = ((long long)blockIdx.x * kExpandWarps + warp) * 4, step = (long long)gridDim.x * kExpandWarps * 4;
 

@@ -58,6 +58,7 @@ struct DevModel {
     int32_t multi_branch;       // 1: narrow waves branch on up to three variables at once (branch_fan)
     int32_t fan_warps;          // children a narrow wave may create in total (2 x SM count), see branch_fan
     int32_t dbg_flags;          // experiments (environment STCSP_DBG_FLAGS); 0 in production
+    int32_t n_sets;             // constraint sets of the model as of this launch (1: every node's set is set 0, no need to look)
     int32_t scalar_walk_cta;    // the same with a whole CTA on one node (the slowest thread is the round's duration)
     int32_t scalar_walk;        // longest relation-table walk (prefix tuples) ONE lane takes on in warp-per-node mode; longer
                                 // walks go to the 32-lane revision

@@ -793,6 +793,7 @@ struct stcsp_session {
             static const int flags = getenv("STCSP_DBG_FLAGS") ? atoi(getenv("STCSP_DBG_FLAGS")) : 0;
             dm.dbg_flags = flags;
         }
+        dm.n_sets = (int32_t)model->sets.n_sets();
         dm.scalar_walk = 192;
         dm.scalar_walk_cta = 32;
         {
