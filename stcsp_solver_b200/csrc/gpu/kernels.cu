@@ -1568,7 +1568,10 @@ __device__ __forceinline__ void ingest_body(const DevModel &M, const IngestArgs 
         }
         ingest_leaf(M, P, rec, lane, st_dom);
     }
-    if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+    if (lane == 0 && st_dom) {
+        if (P.block_stats != nullptr) atomicAdd(&P.block_stats[BS_DOM], (unsigned)st_dom);      // (flushed by the block, see search_kernel)
+        else atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+    }
 }
 
 // Route and merge in one pass (single rank): what cannot be routed yet is left for the host.
@@ -1581,7 +1584,10 @@ __device__ __forceinline__ void leaf_body(const DevModel &M, const RouteArgs &R,
         int32_t *rec = R.leaves + li * M.rec_words;
         if (route_leaf(M, R, rec, li, lane)) ingest_leaf(M, P, rec, lane, st_dom);
     }
-    if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+    if (lane == 0 && st_dom) {
+        if (P.block_stats != nullptr) atomicAdd(&P.block_stats[BS_DOM], (unsigned)st_dom);      // (flushed by the block, see search_kernel)
+        else atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+    }
 }
 
 
@@ -1774,7 +1780,10 @@ __device__ __forceinline__ void leaf_body_quad(const DevModel &M, const RouteArg
         }
     }
     st_dom = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)st_dom);
-    if (lane == 0 && st_dom) atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+    if (lane == 0 && st_dom) {
+        if (P.block_stats != nullptr) atomicAdd(&P.block_stats[BS_DOM], (unsigned)st_dom);      // (flushed by the block, see search_kernel)
+        else atomicAdd(&P.counters[C_DOMINANCE], st_dom);
+    }
 }
 
 // Step-wise launches (multi-GPU sessions, profile_kernels): wide lists take the four-per-warp path too.
@@ -1964,6 +1973,17 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
         cs[S_STATES] = v_states;
         cs[S_EDGES] = v_edges;
     };
+    auto flush_block_stats = [&]() {
+        __syncthreads();
+        if (threadIdx.x < BS_COUNT && s_bstats[threadIdx.x] != 0u) {
+            const int t = threadIdx.x;
+            unsigned long long *dst = t == BS_AHEAD_NODES ? &A.counters[C_AHEAD_NODES] : t == BS_AHEAD_FAILS ? &A.counters[C_AHEAD_FAILS]
+                                    : &ea.counters[t == BS_NODES ? C_NODES : t == BS_FAILS ? C_FAILS : t == BS_TUPLES ? C_TUPLES
+                                                   : t == BS_REV ? C_REVISIONS : C_DOMINANCE];
+            atomicAdd(dst, (unsigned long long)s_bstats[t]);
+            s_bstats[t] = 0u;
+        }
+    };
     for (;;) {
         // ---- wave start: can this wave run without the host?
         if (threadIdx.x == 0) {
@@ -2037,6 +2057,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
                 s_ia.totals = A.counters;
                 s_ia.n_segs = 0;
                 s_ia.fused = 1;
+                s_ia.block_stats = nullptr;     // (fused leaves count through expand's own statistics)
                 s_ia.deg = A.fin.deg_counted ? A.fin.deg : nullptr;
                 s_ia.deg_cap = A.fin.cap_states;
                 ea.fuse_route = &s_ra;
@@ -2229,15 +2250,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
         else if (mode == EXPAND_QUAD) expand_body_quad(M, ea, smem, &s_resident);
         else expand_body<false>(M, ea, smem, &s_resident);
         // the block's statistics of this pass: one reduction per counter and BLOCK (flush_warp_stats)
-        __syncthreads();
-        if (threadIdx.x < BS_COUNT && s_bstats[threadIdx.x] != 0u) {
-            const int t = threadIdx.x;
-            unsigned long long *dst = t == BS_AHEAD_NODES ? &A.counters[C_AHEAD_NODES] : t == BS_AHEAD_FAILS ? &A.counters[C_AHEAD_FAILS]
-                                    : &ea.counters[t == BS_NODES ? C_NODES : t == BS_FAILS ? C_FAILS : t == BS_TUPLES ? C_TUPLES
-                                                   : t == BS_REV ? C_REVISIONS : C_DOMINANCE];
-            atomicAdd(dst, (unsigned long long)s_bstats[t]);
-            s_bstats[t] = 0u;
-        }
+        flush_block_stats();
         if (controller && A.trace != nullptr) dbg_stamp(A.trace + 5 * A.trace_cap, 4096, 96);     // block 0 at the grid barrier
         grid.sync();
         if (controller && A.trace != nullptr) dbg_stamp(A.trace + 5 * A.trace_cap, 4096, 97);     // ... through it
@@ -2294,11 +2307,13 @@ __global__ void __launch_bounds__(kExpandWarps * 32, CTAS) search_kernel(const D
             ia.totals = A.counters;
             ia.n_segs = 0;
             ia.fused = 0;
+            ia.block_stats = s_bstats;
             ia.deg = A.fin.deg_counted ? A.fin.deg : nullptr;
             ia.deg_cap = A.fin.cap_states;
             if (n_leaves >= 4ll * kExpandWarps * gridDim.x || M.force_mode == EXPAND_QUAD + 1)
                 leaf_body_quad<true, true>(M, ra, ia, n_leaves);    // four leaves per warp
             else leaf_body(M, ra, ia, n_leaves);            // route + ingest in one pass
+            flush_block_stats();                            // (dominance hits of the leaf phase)
             grid.sync();
             stamp(2);
             if (threadIdx.x < 32) wave_counters(cnt, false);

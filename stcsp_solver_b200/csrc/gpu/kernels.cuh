@@ -137,6 +137,7 @@ struct IngestArgs {
     // PULL mode (multi-GPU, n_segs > 0): `records` is null; record number i is the i-th record of the concatenation of the
     // segments, and segment q lies in the OUTBOX OF RANK q -- peer memory, read over NVLink by the ingesting warps themselves
     // (the exchange and the merge are one kernel; nothing is staged in an inbox).
+    unsigned *block_stats;          // search_kernel's leaf phase: the block's shared-memory totals (flush_warp_stats), else null
     int32_t *deg;                   // optional: out-degree per (local = global, single rank) source state, counted as edges are
     long long deg_cap;              // appended (FinishArgs::deg_counted); states >= deg_cap are not counted
     int32_t n_segs;
