@@ -4,6 +4,7 @@
 #define STCSP_HOST_SHA256_H
 
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -86,7 +87,7 @@ class Sha256 {
     }
     void blocks(const unsigned char *p, size_t nb) {
 #ifdef STCSP_SHA_NI
-        static const bool ni = have_sha_ni();
+        static const bool ni = have_sha_ni() && getenv("STCSP_NO_SHA_NI") == nullptr;      // (the variable: tests of the portable rounds)
         if (ni) { blocks_ni(p, nb); return; }
 #endif
         for (size_t i = 0; i < nb; i++) block(p + 64 * i);
