@@ -461,14 +461,22 @@ struct HostCache {
     // caller's back in a background thread was tried and dropped: cudaHostRegister of 512 MB holds the driver for the better
     // part of a second, and a solve that runs meanwhile stalls -- partialorder_14 6 ms -> 99 ms.)
     Arena big{nullptr, 0, 0};
-    std::atomic<int> big_state{0};             // 0 none, 2 ready
+    std::atomic<int> big_state{0};             // 0 none, 1 being prepared, 2 ready
     void prepare_big(size_t bytes) {
-        if (bytes == 0 || big_state.load() != 0) return;
+        int expect = 0;
+        if (bytes == 0 || !big_state.compare_exchange_strong(expect, 1)) return;       // (one arena per process; 1 = being prepared)
         bytes = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
         int kind = PINNED;
-        void *p = map_and_register(bytes, kind);
+        void *p = nullptr;
+        try {
+            p = map_and_register(bytes, kind);
+        } catch (...) {
+            big_state.store(0);
+            throw;
+        }
         if (kind != PINNED) {
             munmap(p, bytes);
+            big_state.store(0);
             throw Failure(STCSP_ERR_CUDA, "cannot pin the host arena");
         }
         std::lock_guard<std::mutex> g(mu);
