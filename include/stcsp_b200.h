@@ -213,7 +213,8 @@ void stcsp_gpu_release_caches(void);
 int stcsp_gpu_device_count(void);
 
 /* Optional one-time set-up for a process that will solve more than once (a service, a benchmark loop; the command-line
- * tool, like the reference, solves once and does not call it): creates the context on `device` (-1 = current), loads
+ * tool, like the reference, solves once and does not call it): creates the context on `device` (as
+ * stcsp_options_t::device with use_current_device = 0: a negative ordinal means device 0), loads
  * the kernel modules, reserves the first device arena and pins `pinned_bytes` of host memory for results (0 = none), so
  * that the first solve of a model costs what a new MODEL costs (compile, upload, relation tables), not what a new process
  * costs.  No reference counterpart (the reference is a one-shot program, src/solver.cpp:181-345). */
