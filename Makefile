@@ -7,7 +7,7 @@ CXX ?= g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
 INC := -Iinclude -Istcsp_solver_b200/csrc/host -Istcsp_solver_b200/csrc/gpu
 NVFLAGS := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter $(INC)
-CXXFLAGS := -std=c++17 -O2 -fPIC -Wall -Wextra $(INC)
+CXXFLAGS := -std=c++17 -O2 -fPIC -Wall -Wextra $(INC) -I/usr/local/cuda/include
 B := build
 
 HOST_SRC := $(wildcard stcsp_solver_b200/csrc/host/*.cpp)
@@ -30,7 +30,7 @@ $(B):
 	mkdir -p $(B) bin
 
 $(LIB): $(OBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -cudart shared
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -cudart shared -ldl
 
 bin/stcsp: stcsp_solver_b200/csrc/cli/main.cpp $(LIB) $(HDR)
 	$(CXX) $(CXXFLAGS) -o $@ $< -Lstcsp_solver_b200 -lstcsp_b200 -Wl,-rpath,'$$ORIGIN/../stcsp_solver_b200'

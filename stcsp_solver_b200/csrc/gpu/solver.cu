@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../host/error.h"
+#include "../host/trace_ranges.h"
 #include "kernels.cuh"
 #include "stcsp_b200.h"
 #include "stcsp_host.h"
@@ -2915,11 +2916,16 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
     stcsp_session *s = nullptr;
     double t_init = 0, t_loop = 0, t_finish = 0;
     const bool verbose = options && options->verbosity > 0;
+    TraceRange whole("stcsp_gpu_solve");
     int rc = guarded([&] {
         s = new stcsp_session();
         s->root_in_kernel = !(options && options->profile_kernels);
-        s->init(problem, options, 0, 1);
+        {
+            TraceRange r("stcsp: init (model lookup / compile, upload, pools)");
+            s->init(problem, options, 0, 1);
+        }
         t_init = now_s();
+        TraceRange search("stcsp: search (wave loop)");
         const double deadline = s->opt.time_limit_s > 0 ? t0 + s->opt.time_limit_s : 0;
         int64_t frontier = s->n_in;
         std::vector<int32_t> req;
@@ -2943,6 +2949,7 @@ int stcsp_gpu_solve(const stcsp_problem_t *problem, const stcsp_options_t *optio
         }
         s->search_complete = true;
         t_loop = now_s();
+        TraceRange fin("stcsp: finish (group, trim, post-process, download)");
         s->finish_device(out, !(options && options->no_trim));
         t_finish = now_s();
     });

@@ -26,6 +26,7 @@
 
 #include "error.h"
 #include "sha256.h"
+#include "trace_ranges.h"
 #include "stcsp_host.h"
 
 namespace {
@@ -178,6 +179,7 @@ extern "C" {
 int stcsp_postprocess(const stcsp_problem_t *problem, const stcsp_automaton_t *a, int32_t adversarial1,
                       int32_t adversarial2, stcsp_solution_t *out) {
     if (!problem || !a || !out) { stcsp::set_error("null argument"); return STCSP_ERR_INVALID; }
+    stcsp::TraceRange range("stcsp_postprocess (fixpoints, canonical numbering)");
     memset(out, 0, sizeof *out);
     Work w;
     w.a = a;
@@ -558,6 +560,7 @@ char *stcsp_solution_canonical(const stcsp_problem_t *p, const stcsp_solution_t 
 
 int stcsp_solution_write_dot(const stcsp_problem_t *p, const stcsp_solution_t *s, const char *path) {
     if (!p || !s || !path) { stcsp::set_error("null argument"); return STCSP_ERR_INVALID; }
+    stcsp::TraceRange range("stcsp_solution_write_dot");
     return write_file(path, [&](FileSink &sink) { emit_dot(p, s, sink); });
 }
 
@@ -568,6 +571,7 @@ int stcsp_solution_write_canonical(const stcsp_problem_t *p, const stcsp_solutio
 
 int stcsp_solution_canonical_sha256(const stcsp_problem_t *p, const stcsp_solution_t *s, char out_hex[65]) {
     if (!p || !s || !out_hex) { stcsp::set_error("null argument"); return STCSP_ERR_INVALID; }
+    stcsp::TraceRange range("stcsp_solution_canonical_sha256");
     stcsp::Sha256 sha;
     emit_canonical(p, s, [&](const char *t, size_t n) { sha.update(t, n); });
     const std::string hex = sha.hex();
